@@ -1,0 +1,274 @@
+/*
+ * rt_api.h — C-ABI of the B200-native path tracer (librt_b200.so).
+ *
+ * This is the drop-in boundary for the per-pixel render path of
+ * slimem/raytracing_renderer_cuda.  The reference has no FFI;
+ * its "API" is (i) the device-side scene constructors called from
+ * populate_scene_balls (src/main.cu:188-356) and (ii) the `render` kernel
+ * launch + framebuffer convention (src/main.cu:97-132, :442-449, :475-491).
+ * (i) becomes the flat POD scene description below (filled by the header-only
+ * façade in include/rt/scene.hpp, which keeps the reference's class names and
+ * constructor signatures); (ii) becomes rt_render*().
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  Every entry returns
+ * an rt_status; the message of the last failure on the calling thread is
+ * available from rt_last_error().  The library never calls exit() or
+ * cudaDeviceReset() (reference: check_cuda, src/main.cu:23-30, does both).
+ *
+ * There is NO CPU fallback: every compute entry fails with RT_ERR_NO_DEVICE /
+ * RT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RT_API_H
+#define RT_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_API_VERSION 1
+#define RT_INVALID_ID 0xFFFFFFFFu
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID_ARG = 1,
+    RT_ERR_CUDA = 2,
+    RT_ERR_OOM = 3,
+    RT_ERR_UNSUPPORTED = 4,
+    RT_ERR_NO_DEVICE = 5,
+    RT_ERR_IO = 6
+} rt_status;
+
+/* ---- scene description (POD) ------------------------------------------- */
+
+/* material kinds; reference classes in src/material.h */
+enum {
+    RT_MAT_LAMBERTIAN = 0, /* lambertian(const text*)            material.h:59-70,105-116 */
+    RT_MAT_METAL = 1,      /* metal(vec3 albedo, float roughness) material.h:72-88,118-131 */
+    RT_MAT_DIELECTRIC = 2, /* dielectric(float ri, vec3 tint)     material.h:90-103,133-184 */
+    RT_MAT_EMITTER = 3     /* emitter(const text*, intensity=1)   material.h:38-56 (= diffuse_light) */
+};
+
+/* texture kinds; reference classes in src/texture.h */
+enum {
+    RT_TEX_CONSTANT = 0,   /* constant_texture(vec3)                    texture.h:18-28 */
+    RT_TEX_CHECKER = 1,    /* checker_texture(even, odd)                texture.h:30-48 */
+    RT_TEX_NOISE_PERLIN = 2,     /* noise_texture(PERLIN, density)      texture.h:58-59 */
+    RT_TEX_NOISE_TURBULANCE = 3, /* noise_texture(TURBULANCE, density)  texture.h:60-64 */
+    RT_TEX_NOISE_MARBLE = 4,     /* noise_texture(MARBLE, density)      texture.h:65-76 */
+    RT_TEX_WOOD = 5,       /* wood_texture(c1, c2, density, hardness)   texture.h:86-111 */
+    RT_TEX_IMAGE = 6       /* image_texture(float* rgb, w, h)           texture.h:113-148 */
+};
+
+/* acceleration structure request (the façade's bvh_node(...) is a request) */
+enum {
+    RT_BVH_AUTO = 0,     /* brute force for tiny scenes, host SAH for small, GPU LBVH for large */
+    RT_BVH_NONE = 1,     /* hitable_list with bvh==nullptr: linear closest-hit loop (hitable_list.h:66-78) */
+    RT_BVH_HOST_SAH = 2,
+    RT_BVH_GPU_LBVH = 3
+};
+
+/* integrator pipeline */
+enum {
+    RT_PIPE_AUTO = 0,
+    RT_PIPE_WAVEFRONT = 1, /* raygen / extend / per-material shade queues */
+    RT_PIPE_MEGAKERNEL = 2 /* one thread runs a whole path (reference structure, main.cu:35-74) */
+};
+
+#define RT_SPHERE_MOVING 1u /* built by moving_sphere(...) (sphere.h:30-58) */
+#define RT_SPHERE_INSIDE 2u /* sphere(..., inside=true); stored, no effect (sphere.h:27,133-138) */
+
+/* sphere(center, radius, material) / moving_sphere(c0, c1, t0, t1, radius, material) */
+typedef struct rt_sphere {
+    float center0[3];
+    float radius;
+    float center1[3]; /* == center0 for a static sphere */
+    float time0;
+    float time1;
+    uint32_t material; /* index into rt_scene_desc.materials */
+    uint32_t id;       /* the reference's set_id() value (hitable_object.h:78-79) */
+    uint32_t flags;    /* RT_SPHERE_* */
+} rt_sphere;
+
+typedef struct rt_material {
+    uint32_t kind;   /* RT_MAT_* */
+    int32_t texture; /* lambertian albedo / emitter texture; -1 otherwise */
+    float albedo[3]; /* metal albedo / dielectric tint */
+    float param;     /* metal: roughness (clamped to <=1 at construction); dielectric: ri; emitter: intensity */
+} rt_material;
+
+typedef struct rt_texture {
+    uint32_t kind;   /* RT_TEX_* */
+    int32_t even;    /* checker: texture index used when sines >= 0 */
+    int32_t odd;     /* checker: texture index used when sines <  0 */
+    int32_t image;   /* image: index into rt_scene_desc.images */
+    float color1[3]; /* constant: colour; wood: color1 */
+    float color2[3]; /* wood: color2 */
+    float density;   /* noise / wood (<=0 is replaced by 4 at construction) */
+    float hardness;  /* wood */
+} rt_texture;
+
+/* image_texture(float* buffer, int width, int height): row 0 = top, RGB floats */
+typedef struct rt_image {
+    const float* rgb; /* width*height*3 floats, borrowed until rt_scene_create returns */
+    int32_t width;
+    int32_t height;
+} rt_image;
+
+/* camera(lookfrom, lookat, up, vfov, aspect, aperture, focus_dist, time0, time1), camera.h:7-10 */
+typedef struct rt_camera {
+    float lookfrom[3];
+    float lookat[3];
+    float up[3];
+    float vfov; /* degrees, top to bottom */
+    float aspect;
+    float aperture;
+    float focus_dist;
+    float time0;
+    float time1;
+} rt_camera;
+
+typedef struct rt_scene_desc {
+    const rt_sphere* spheres;
+    uint32_t n_spheres;
+    const rt_material* materials;
+    uint32_t n_materials;
+    const rt_texture* textures;
+    uint32_t n_textures;
+    const rt_image* images;
+    uint32_t n_images;
+    rt_camera camera;
+    uint32_t bvh_mode; /* RT_BVH_* */
+} rt_scene_desc;
+
+/* ---- render parameters -------------------------------------------------- */
+
+/* The reference bakes these in: WIDTH/HEIGHT/RAY_BOUNCES/SEED (common.h:13-20),
+ * SAMPLES_PER_PIXEL (main.cu:15), tmin 1e-5f (main.cu:45), world colour
+ * (1,.8,.7) (main.cu:40) and the +0.1 "bloom" (main.cu:49). */
+typedef struct rt_render_params {
+    int32_t width;
+    int32_t height;
+    int32_t spp;           /* samples rendered by THIS call */
+    int32_t sample_offset; /* first global sample index (multi-GPU sample sharding) */
+    int32_t max_depth;     /* RAY_BOUNCES, 50 */
+    uint32_t seed;         /* SEED, 1000 */
+    float tmin;            /* 1e-5f */
+    float world[3];        /* (1, .8, .7) */
+    float bloom;           /* 0.1f */
+    uint32_t pipeline;     /* RT_PIPE_* */
+} rt_render_params;
+
+typedef struct rt_stats {
+    uint64_t paths;    /* width*height*spp */
+    uint64_t rays;     /* scene.hit() queries: primary + scattered */
+    float ms_total;    /* device time, first raygen .. last accumulate (CUDA events) */
+    float ms_tonemap;  /* device time of the tonemap pass (0 if not run) */
+    float ms_h2d;      /* not used by render; scene upload reports it via rt_scene_info */
+    float ms_d2h;      /* device->host copy of the result, if any */
+    uint32_t launches; /* kernels launched by this call */
+    uint32_t iterations; /* wavefront bounce iterations (1 for the megakernel) */
+} rt_stats;
+
+typedef struct rt_scene_info {
+    uint32_t n_spheres;
+    uint32_t n_nodes;    /* BVH nodes (0 for brute force) */
+    uint32_t bvh_mode;   /* resolved RT_BVH_* */
+    uint32_t bvh_depth;
+    float ms_build;      /* host SAH build (wall) or device LBVH build (events) */
+    float ms_upload;     /* H2D copies + device-side scene preparation */
+    float sah_cost;
+    uint64_t device_bytes;
+} rt_scene_info;
+
+/* ray / hit records of the parity hook */
+typedef struct rt_ray {
+    float origin[3];
+    float direction[3]; /* NOT normalised (ray.h:12, camera.h:37) */
+    float time;
+} rt_ray;
+
+typedef struct rt_hit {
+    float t;      /* FLT_MAX on miss */
+    uint32_t id;  /* rt_sphere.id of the closest object, RT_INVALID_ID on miss */
+    float p[3];
+    float n[3];   /* outward normal (sphere.h:123) */
+    float u, v;   /* get_sphere_uv (sphere.h:61-83); computed for every sphere kind */
+} rt_hit;
+
+typedef struct rt_context rt_context;
+typedef struct rt_scene rt_scene;
+
+/* ---- entry points -------------------------------------------------------- */
+
+int rt_api_version(void);
+const char* rt_last_error(void);
+void rt_default_render_params(rt_render_params* p); /* reference constants, 1200x600x100 */
+
+/* One context = one CUDA device + one stream (one process per GPU). Replaces
+ * the implicit device-0/default-stream use of main() (main.cu:368-509). */
+rt_status rt_context_create(int device, rt_context** out);
+void rt_context_destroy(rt_context* ctx);
+/* run on a caller-owned stream (e.g. torch's current stream) instead of the context's own */
+rt_status rt_context_set_stream(rt_context* ctx, void* cuda_stream);
+rt_status rt_context_synchronize(rt_context* ctx);
+
+/* Replaces populate_scene_balls<<<1,1>>> (main.cu:188-356, :423) + the image
+ * upload (main.cu:383-388): copies the POD scene to the device, prepares the
+ * SoA sphere arrays and builds the acceleration structure. */
+rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out);
+void rt_scene_destroy(rt_scene* scene); /* replaces free_scene<<<1,1>>> (main.cu:360-366) */
+rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info);
+
+/* Parity hook: closest hit of scene.hit(r, tmin, FLT_MAX) (hitable_list.h:60-79)
+ * for n caller-supplied rays. use_bvh=0 forces the brute-force list path. */
+rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n,
+                           float tmin, int use_bvh, rt_hit* hits);
+
+/* Replaces init_rand_state + render (main.cu:76-132, :438-449). out_rgb is a
+ * HOST buffer of width*height*3 floats in the reference framebuffer layout:
+ * index j*width+i, j=0 = bottom row, values /spp, saturated, sqrt-gamma'd. */
+rt_status rt_render(rt_context* ctx, const rt_scene* scene, const rt_render_params* p,
+                    float* out_rgb, rt_stats* stats);
+
+/* Un-tonemapped per-pixel sums: HOST buffer of width*height*4 floats
+ * (sum r, sum g, sum b, sample count). */
+rt_status rt_render_accum(rt_context* ctx, const rt_scene* scene, const rt_render_params* p,
+                          float* out_accum, rt_stats* stats);
+
+/* Device-resident variant: ADDS this call's samples into accum_dev (float4 per
+ * pixel, caller-allocated device memory, caller zeroes it). Asynchronous on the
+ * context stream unless stats != NULL (then it synchronises to fill stats). */
+rt_status rt_render_accum_device(rt_context* ctx, const rt_scene* scene, const rt_render_params* p,
+                                 void* accum_dev, rt_stats* stats);
+
+/* Pixel finalisation of main.cu:124-127 on the device: col * rz(1/count) ->
+ * saturate -> sqrt. out_rgb_dev: width*height*3 floats (reference layout) or NULL;
+ * out_rgb8_dev: width*height*3 bytes, Y-flipped and quantised as main.cu:476-487, or NULL. */
+rt_status rt_tonemap_device(rt_context* ctx, const void* accum_dev, int32_t width, int32_t height,
+                            void* out_rgb_dev, void* out_rgb8_dev);
+
+/* Host restatement of the writer loop main.cu:475-488 (Y flip + int(255.999f*c)&255). */
+rt_status rt_quantize_rgb8(const float* rgb, int32_t width, int32_t height, uint8_t* out_rgb8);
+rt_status rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t* rgb8);
+rt_status rt_read_ppm_f32(const char* path, float** out_rgb, int32_t* width, int32_t* height); /* byte/255.f */
+void rt_free(void* p);
+
+/* Built-in scene generators written against the façade (BASELINE configs C1..C4):
+ * "earth_emitter" (main.cu:188-356), "book1_final", "perlin_motion", "random_spheres".
+ * `image_rgb` (may be NULL unless the scene needs it) is the earth texture; `n` is
+ * the primitive count for "random_spheres" (ignored otherwise). The returned desc owns
+ * its arrays; release with rt_scene_desc_free. */
+rt_status rt_builtin_scene(const char* name, const float* image_rgb, int32_t image_w, int32_t image_h,
+                           uint32_t n, uint32_t bvh_mode, rt_scene_desc** out);
+void rt_scene_desc_free(rt_scene_desc* desc);
+/* flat binary scene file shared with the reference harness (oracle/ref_harness.cu) */
+rt_status rt_scene_desc_save(const rt_scene_desc* desc, const char* path);
+rt_status rt_scene_desc_load(const char* path, rt_scene_desc** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_API_H */

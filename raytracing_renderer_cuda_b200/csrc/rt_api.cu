@@ -1,0 +1,635 @@
+// rt_api.cu — C-ABI of librt_b200.so (include/rt_api.h): context, scene upload +
+// acceleration-structure build, render / accumulate / tonemap entry points.
+// Host logic only; the kernels live in rt_kernels.cu / rt_wavefront.cu / rt_lbvh.cu.
+#include <cfenv>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rt_bvh_host.hpp"
+#include "rt_kernels.cuh"
+#include "rt_lbvh.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));   \
+            return e__ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA;                 \
+        }                                                                                       \
+    } while (0)
+
+#define ARG_CHECK(cond, msg)                  \
+    do {                                      \
+        if (!(cond)) {                        \
+            set_error("invalid argument: %s", msg); \
+            return RT_ERR_INVALID_ARG;        \
+        }                                     \
+    } while (0)
+
+// round-toward-zero float subtraction on the host == __fsub_rz (used for c1 - c0 of
+// moving_sphere::center, sphere.h:51, which the reference evaluates with vec3 operator-)
+float host_sub_rz(float a, float b) {
+    const int old = std::fegetround();
+    std::fesetround(FE_TOWARDZERO);
+    volatile float va = a, vb = b;
+    volatile float r = va - vb;
+    std::fesetround(old);
+    return r;
+}
+
+} // namespace
+
+struct rt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 148;
+    unsigned long long* d_ray_counter = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float4* accum = nullptr; // scratch for rt_render / rt_render_accum
+    size_t accum_px = 0;
+    float* out_rgb = nullptr;
+    size_t out_px = 0;
+    rtd::WavefrontState* wf = nullptr;
+};
+
+struct rt_scene {
+    rt_context* ctx = nullptr;
+    rtd::DScene d{};
+    rt_scene_info info{};
+    std::vector<void*> allocs;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> texobjs;
+};
+
+namespace {
+
+rt_status make_current(const rt_context* ctx) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return RT_OK;
+}
+
+template <class T>
+rt_status dev_alloc(rt_scene* s, T** out, size_t count) {
+    *out = nullptr;
+    if (count == 0) return RT_OK;
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+    s->allocs.push_back(p);
+    s->info.device_bytes += count * sizeof(T);
+    *out = static_cast<T*>(p);
+    return RT_OK;
+}
+
+// camera ctor (camera.h:7-31) in host float arithmetic
+void make_camera(const rt_camera& c, rtd::DCamera& out) {
+    auto V = [](const float* p) { return rtd::V3{p[0], p[1], p[2]}; };
+    auto sub = [](rtd::V3 a, rtd::V3 b) { return rtd::V3{a.x - b.x, a.y - b.y, a.z - b.z}; };
+    auto mul = [](rtd::V3 a, float s) { return rtd::V3{a.x * s, a.y * s, a.z * s}; };
+    auto cross = [](rtd::V3 a, rtd::V3 b) {
+        return rtd::V3{a.y * b.z - a.z * b.y, -(a.x * b.z - a.z * b.x), a.x * b.y - a.y * b.x};
+    };
+    auto norm = [](rtd::V3 a) {
+        if (a.x == 0.f && a.y == 0.f && a.z == 0.f) return a;
+        float l = std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
+        return rtd::V3{a.x / l, a.y / l, a.z / l};
+    };
+    out.t0 = c.time0;
+    out.t1 = c.time1;
+    out.lens_radius = c.aperture / 2;
+    float theta = float(c.vfov * M_PI / 180.f);
+    float half_height = std::tan(theta / 2.f);
+    float half_width = c.aspect * half_height;
+    rtd::V3 lookfrom = V(c.lookfrom), lookat = V(c.lookat), up = V(c.up);
+    out.origin = lookfrom;
+    rtd::V3 w = norm(sub(lookfrom, lookat));
+    rtd::V3 u = norm(cross(up, w));
+    rtd::V3 v = cross(w, u);
+    out.u = u;
+    out.v = v;
+    out.lower_left = sub(sub(sub(out.origin, mul(u, half_width * c.focus_dist)), mul(v, half_height * c.focus_dist)),
+                         mul(w, c.focus_dist));
+    out.horizontal = mul(u, 2 * half_width * c.focus_dist);
+    out.vertical = mul(v, 2 * half_height * c.focus_dist);
+}
+
+rt_status validate_desc(const rt_scene_desc* d) {
+    ARG_CHECK(d != nullptr, "desc is NULL");
+    ARG_CHECK(d->n_spheres == 0 || d->spheres, "spheres is NULL");
+    ARG_CHECK(d->n_materials == 0 || d->materials, "materials is NULL");
+    ARG_CHECK(d->n_textures == 0 || d->textures, "textures is NULL");
+    ARG_CHECK(d->n_images == 0 || d->images, "images is NULL");
+    ARG_CHECK(d->n_images <= RT_MAX_IMAGES, "too many images (max 8)");
+    ARG_CHECK(d->bvh_mode <= RT_BVH_GPU_LBVH, "bad bvh_mode");
+    for (uint32_t i = 0; i < d->n_images; ++i)
+        ARG_CHECK(d->images[i].rgb && d->images[i].width > 0 && d->images[i].height > 0, "empty image");
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const rt_texture& t = d->textures[i];
+        ARG_CHECK(t.kind <= RT_TEX_IMAGE, "bad texture kind");
+        if (t.kind == RT_TEX_CHECKER)
+            ARG_CHECK(t.even >= 0 && uint32_t(t.even) < d->n_textures && t.odd >= 0 && uint32_t(t.odd) < d->n_textures,
+                      "checker child out of range");
+        if (t.kind == RT_TEX_IMAGE) ARG_CHECK(t.image >= 0 && uint32_t(t.image) < d->n_images, "image index out of range");
+    }
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const rt_material& m = d->materials[i];
+        ARG_CHECK(m.kind <= RT_MAT_EMITTER, "bad material kind");
+        if (m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_EMITTER)
+            ARG_CHECK(m.texture >= 0 && uint32_t(m.texture) < d->n_textures, "material texture out of range");
+    }
+    for (uint32_t i = 0; i < d->n_spheres; ++i) ARG_CHECK(d->spheres[i].material < d->n_materials, "sphere material out of range");
+    return RT_OK;
+}
+
+rt_status check_params(const rt_render_params* p) {
+    ARG_CHECK(p != nullptr, "params is NULL");
+    ARG_CHECK(p->width > 0 && p->height > 0, "width/height must be positive");
+    ARG_CHECK(p->spp >= 0 && p->sample_offset >= 0, "spp/sample_offset must be >= 0");
+    ARG_CHECK(p->max_depth >= 0 && p->max_depth < (1 << 23), "max_depth out of range");
+    ARG_CHECK(p->pipeline <= RT_PIPE_MEGAKERNEL, "bad pipeline");
+    ARG_CHECK(uint64_t(p->width) * uint64_t(p->height) < (1ull << 32), "frame has more than 2^32 pixels");
+    return RT_OK;
+}
+
+rtd::DRenderParams to_device_params(const rt_render_params& p) {
+    rtd::DRenderParams d;
+    d.width = p.width;
+    d.height = p.height;
+    d.spp = p.spp;
+    d.sample_offset = p.sample_offset;
+    d.max_depth = p.max_depth;
+    d.seed = p.seed;
+    d.tmin = p.tmin;
+    d.world_r = p.world[0];
+    d.world_g = p.world[1];
+    d.world_b = p.world[2];
+    d.bloom = p.bloom;
+    return d;
+}
+
+rt_status ensure_accum(rt_context* ctx, size_t npix) {
+    if (ctx->accum_px < npix) {
+        if (ctx->accum) cudaFree(ctx->accum);
+        ctx->accum = nullptr;
+        ctx->accum_px = 0;
+        CUDA_TRY(cudaMalloc(&ctx->accum, npix * sizeof(float4)));
+        ctx->accum_px = npix;
+    }
+    return RT_OK;
+}
+
+rt_status ensure_out(rt_context* ctx, size_t npix) {
+    if (ctx->out_px < npix) {
+        if (ctx->out_rgb) cudaFree(ctx->out_rgb);
+        ctx->out_rgb = nullptr;
+        ctx->out_px = 0;
+        CUDA_TRY(cudaMalloc(&ctx->out_rgb, npix * 3 * sizeof(float)));
+        ctx->out_px = npix;
+    }
+    return RT_OK;
+}
+
+// Core: adds p->spp samples per pixel into accum (device).  Fills stats if requested
+// (which synchronises the stream).
+rt_status render_into(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, float4* accum, rt_stats* stats) {
+    rtd::DRenderParams rp = to_device_params(*p);
+    const bool use_bvh = scene->d.nodes != nullptr;
+    uint32_t pipeline = p->pipeline == RT_PIPE_AUTO ? uint32_t(RT_PIPE_WAVEFRONT) : p->pipeline;
+    uint32_t launches = 0, iterations = 0;
+    if (stats) {
+        CUDA_TRY(cudaMemsetAsync(ctx->d_ray_counter, 0, sizeof(unsigned long long), ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    }
+    if (pipeline == RT_PIPE_MEGAKERNEL) {
+        rtd::launch_render_mega(scene->d, rp, use_bvh, accum, ctx->d_ray_counter, ctx->sm_count, ctx->stream);
+        launches = 1;
+        iterations = 1;
+    } else {
+        const size_t npaths = size_t(p->width) * size_t(p->height) * size_t(p->spp);
+        // pool of path slots: 1 Mi x 64 B records stay resident in the 126 MB L2 (RT_WF_POOL overrides)
+        size_t pool_cap = size_t(1) << 20;
+        if (const char* e = getenv("RT_WF_POOL")) {
+            long long v = atoll(e);
+            if (v >= 1024 && v <= (1ll << 28)) pool_cap = size_t(v);
+        }
+        size_t pool = npaths < pool_cap ? npaths : pool_cap;
+        if (pool < 1024) pool = 1024;
+        if (!ctx->wf || rtd::wavefront_pool(ctx->wf) < pool) {
+            if (ctx->wf) rtd::wavefront_destroy(ctx->wf);
+            ctx->wf = rtd::wavefront_create(pool, ctx->stream);
+            if (!ctx->wf) {
+                set_error("wavefront_create(%zu paths) failed: %s", pool, cudaGetErrorString(cudaGetLastError()));
+                return RT_ERR_OOM;
+            }
+        }
+        rtd::wavefront_render(ctx->wf, scene->d, rp, use_bvh, accum, ctx->d_ray_counter, ctx->sm_count, ctx->stream,
+                              &launches, &iterations);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (stats) {
+        CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+        unsigned long long rays = 0;
+        CUDA_TRY(cudaMemcpyAsync(&rays, ctx->d_ray_counter, sizeof rays, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        memset(stats, 0, sizeof *stats);
+        CUDA_TRY(cudaEventElapsedTime(&stats->ms_total, ctx->ev[0], ctx->ev[1]));
+        stats->paths = uint64_t(p->width) * uint64_t(p->height) * uint64_t(p->spp);
+        stats->rays = rays;
+        stats->launches = launches;
+        stats->iterations = iterations;
+    }
+    return RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int rt_api_version(void) { return RT_API_VERSION; }
+
+const char* rt_last_error(void) { return g_last_error.c_str(); }
+
+void rt_default_render_params(rt_render_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->width = 1200;  // common.h:13
+    p->height = 600;  // common.h:14
+    p->spp = 100;     // main.cu:15
+    p->sample_offset = 0;
+    p->max_depth = 50; // common.h:19
+    p->seed = 1000;    // common.h:20
+    p->tmin = 0.00001f; // main.cu:45
+    p->world[0] = 1.f;  // main.cu:40
+    p->world[1] = .8f;
+    p->world[2] = .7f;
+    p->bloom = 0.1f; // main.cu:49
+    p->pipeline = RT_PIPE_AUTO;
+}
+
+rt_status rt_context_create(int device, rt_context** out) {
+    ARG_CHECK(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        cudaGetLastError();
+        return RT_ERR_NO_DEVICE;
+    }
+    ARG_CHECK(device >= 0 && device < count, "device index out of range");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; librt_b200 carries sm_100a code only", device, prop.major, prop.minor);
+        return RT_ERR_UNSUPPORTED;
+    }
+    rt_context* ctx = new (std::nothrow) rt_context();
+    if (!ctx) return RT_ERR_OOM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&ctx->d_ray_counter, sizeof(unsigned long long)));
+    for (auto& ev : ctx->ev) CUDA_TRY(cudaEventCreate(&ev));
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_context_destroy(rt_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->wf) rtd::wavefront_destroy(ctx->wf);
+    if (ctx->accum) cudaFree(ctx->accum);
+    if (ctx->out_rgb) cudaFree(ctx->out_rgb);
+    if (ctx->d_ray_counter) cudaFree(ctx->d_ray_counter);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+rt_status rt_context_set_stream(rt_context* ctx, void* cuda_stream) {
+    ARG_CHECK(ctx != nullptr, "ctx is NULL");
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return RT_OK;
+}
+
+rt_status rt_context_synchronize(rt_context* ctx) {
+    ARG_CHECK(ctx != nullptr, "ctx is NULL");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out) {
+    ARG_CHECK(ctx != nullptr && out != nullptr, "ctx/out is NULL");
+    *out = nullptr;
+    rt_status st = validate_desc(desc);
+    if (st != RT_OK) return st;
+    st = make_current(ctx);
+    if (st != RT_OK) return st;
+
+    rt_scene* s = new (std::nothrow) rt_scene();
+    if (!s) return RT_ERR_OOM;
+    s->ctx = ctx;
+    struct Guard {
+        rt_scene* s;
+        ~Guard() {
+            if (s) rt_scene_destroy(s);
+        }
+    } guard{s};
+
+    const auto t_begin = std::chrono::steady_clock::now();
+    const uint32_t n = desc->n_spheres;
+
+    // ---- primitives: static spheres first (stable), SoA float4 arrays ----
+    std::vector<uint32_t> order;
+    order.reserve(n);
+    for (uint32_t i = 0; i < n; ++i)
+        if (!(desc->spheres[i].flags & RT_SPHERE_MOVING)) order.push_back(i);
+    const uint32_t n_static = uint32_t(order.size());
+    for (uint32_t i = 0; i < n; ++i)
+        if (desc->spheres[i].flags & RT_SPHERE_MOVING) order.push_back(i);
+
+    std::vector<float4> ha(n), hb(n);
+    std::vector<uint4> hc(n);
+    std::vector<rth::Box> boxes(n);
+    for (uint32_t k = 0; k < n; ++k) {
+        const rt_sphere& sp = desc->spheres[order[k]];
+        ha[k] = make_float4(sp.center0[0], sp.center0[1], sp.center0[2], sp.radius);
+        hb[k] = make_float4(host_sub_rz(sp.center1[0], sp.center0[0]), host_sub_rz(sp.center1[1], sp.center0[1]),
+                            host_sub_rz(sp.center1[2], sp.center0[2]), sp.time0);
+        float dt = sp.time1 - sp.time0; // FADD(RN) in the reference's SASS (sphere.h:51)
+        uint32_t dt_bits;
+        memcpy(&dt_bits, &dt, 4);
+        hc[k] = make_uint4(dt_bits, sp.material, sp.id, order[k]);
+        const bool moving = (sp.flags & RT_SPHERE_MOVING) != 0;
+        boxes[k] = rth::sphere_box(sp.center0, moving ? sp.center1 : sp.center0, sp.radius);
+    }
+
+    // ---- acceleration structure ----
+    uint32_t mode = desc->bvh_mode;
+    if (mode == RT_BVH_AUTO) mode = n <= 12 ? RT_BVH_NONE : (n <= 200000 ? RT_BVH_HOST_SAH : RT_BVH_GPU_LBVH);
+    if (n < 2) mode = RT_BVH_NONE;
+    std::vector<rth::NodeHost> nodes;
+    rth::BvhStats bstats;
+    const auto t_build0 = std::chrono::steady_clock::now();
+    if (mode == RT_BVH_HOST_SAH) rth::build_bvh_sah(boxes, nodes, &bstats);
+    const auto t_build1 = std::chrono::steady_clock::now();
+
+    // ---- upload ----
+    float4 *da = nullptr, *db = nullptr;
+    uint4* dc = nullptr;
+    rtd::BvhNode* dnodes = nullptr;
+    rtd::DMaterial* dmats = nullptr;
+    rtd::DTexture* dtexs = nullptr;
+    if ((st = dev_alloc(s, &da, n)) != RT_OK) return st;
+    if ((st = dev_alloc(s, &db, n)) != RT_OK) return st;
+    if ((st = dev_alloc(s, &dc, n)) != RT_OK) return st;
+    cudaStream_t stream = ctx->stream;
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(da, ha.data(), n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(db, hb.data(), n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(dc, hc.data(), n * sizeof(uint4), cudaMemcpyHostToDevice, stream));
+    }
+    float lbvh_ms = 0.f;
+    uint32_t n_nodes = 0;
+    if (mode == RT_BVH_HOST_SAH) {
+        n_nodes = uint32_t(nodes.size());
+        if ((st = dev_alloc(s, &dnodes, n_nodes)) != RT_OK) return st;
+        CUDA_TRY(cudaMemcpyAsync(dnodes, nodes.data(), n_nodes * sizeof(rtd::BvhNode), cudaMemcpyHostToDevice, stream));
+    } else if (mode == RT_BVH_GPU_LBVH) {
+        n_nodes = n - 1;
+        if ((st = dev_alloc(s, &dnodes, n_nodes)) != RT_OK) return st;
+        rth::Box* dboxes = nullptr;
+        CUDA_TRY(cudaMalloc(&dboxes, n * sizeof(rth::Box)));
+        cudaError_t e = cudaMemcpyAsync(dboxes, boxes.data(), n * sizeof(rth::Box), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) e = rtd::lbvh_build(reinterpret_cast<const float*>(dboxes), n, dnodes, stream, &lbvh_ms, &bstats.depth);
+        cudaFree(dboxes);
+        if (e != cudaSuccess) {
+            set_error("GPU LBVH build failed: %s", cudaGetErrorString(e));
+            return RT_ERR_CUDA;
+        }
+    }
+
+    std::vector<rtd::DMaterial> hm(desc->n_materials);
+    for (uint32_t i = 0; i < desc->n_materials; ++i) {
+        const rt_material& m = desc->materials[i];
+        hm[i] = rtd::DMaterial{m.kind, m.texture, m.albedo[0], m.albedo[1], m.albedo[2], m.param, 0.f, 0.f};
+    }
+    std::vector<rtd::DTexture> ht(desc->n_textures);
+    for (uint32_t i = 0; i < desc->n_textures; ++i) {
+        const rt_texture& t = desc->textures[i];
+        ht[i] = rtd::DTexture{t.kind,      t.even,      t.odd,       t.image,   t.color1[0], t.color1[1],
+                              t.color1[2], t.density,   t.color2[0], t.color2[1], t.color2[2], t.hardness};
+    }
+    if ((st = dev_alloc(s, &dmats, hm.size())) != RT_OK) return st;
+    if ((st = dev_alloc(s, &dtexs, ht.size())) != RT_OK) return st;
+    if (!hm.empty()) CUDA_TRY(cudaMemcpyAsync(dmats, hm.data(), hm.size() * sizeof(rtd::DMaterial), cudaMemcpyHostToDevice, stream));
+    if (!ht.empty()) CUDA_TRY(cudaMemcpyAsync(dtexs, ht.data(), ht.size() * sizeof(rtd::DTexture), cudaMemcpyHostToDevice, stream));
+
+    // ---- image textures: float RGB -> float4 cudaArray + point-sampled texture object ----
+    for (uint32_t i = 0; i < desc->n_images; ++i) {
+        const rt_image& im = desc->images[i];
+        const size_t texels = size_t(im.width) * size_t(im.height);
+        float* d_rgb = nullptr;
+        float4* d_rgba = nullptr;
+        CUDA_TRY(cudaMalloc(&d_rgb, texels * 3 * sizeof(float)));
+        cudaError_t e = cudaMalloc(&d_rgba, texels * sizeof(float4));
+        if (e != cudaSuccess) {
+            cudaFree(d_rgb);
+            set_error("cudaMalloc(image staging) failed: %s", cudaGetErrorString(e));
+            return RT_ERR_OOM;
+        }
+        cudaArray_t arr = nullptr;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<float4>();
+        e = cudaMemcpyAsync(d_rgb, im.rgb, texels * 3 * sizeof(float), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess) {
+            rtd::launch_rgb_to_rgba(d_rgb, d_rgba, texels, stream);
+            e = cudaMallocArray(&arr, &cd, size_t(im.width), size_t(im.height));
+        }
+        if (e == cudaSuccess) {
+            s->arrays.push_back(arr);
+            e = cudaMemcpy2DToArrayAsync(arr, 0, 0, d_rgba, size_t(im.width) * sizeof(float4), size_t(im.width) * sizeof(float4),
+                                         size_t(im.height), cudaMemcpyDeviceToDevice, stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(d_rgb);
+        cudaFree(d_rgba);
+        if (e != cudaSuccess) {
+            set_error("image texture upload failed: %s", cudaGetErrorString(e));
+            return RT_ERR_CUDA;
+        }
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t tex = 0;
+        CUDA_TRY(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        s->texobjs.push_back(tex);
+        s->d.images[i] = rtd::DImage{tex, im.width, im.height};
+        s->info.device_bytes += texels * sizeof(float4);
+    }
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+
+    s->d.sph_a = da;
+    s->d.sph_b = db;
+    s->d.sph_c = dc;
+    s->d.n_spheres = n;
+    s->d.n_static = n_static;
+    s->d.nodes = dnodes;
+    s->d.n_nodes = n_nodes;
+    s->d.mats = dmats;
+    s->d.texs = dtexs;
+    make_camera(desc->camera, s->d.cam);
+
+    const auto t_end = std::chrono::steady_clock::now();
+    s->info.n_spheres = n;
+    s->info.n_nodes = n_nodes;
+    s->info.bvh_mode = mode;
+    s->info.bvh_depth = bstats.depth;
+    s->info.sah_cost = bstats.sah_cost;
+    s->info.ms_build = mode == RT_BVH_GPU_LBVH ? lbvh_ms
+                                               : std::chrono::duration<float, std::milli>(t_build1 - t_build0).count();
+    s->info.ms_upload = std::chrono::duration<float, std::milli>(t_end - t_begin).count() -
+                        std::chrono::duration<float, std::milli>(t_build1 - t_build0).count();
+    guard.s = nullptr;
+    *out = s;
+    return RT_OK;
+}
+
+void rt_scene_destroy(rt_scene* scene) {
+    if (!scene) return;
+    if (scene->ctx) cudaSetDevice(scene->ctx->device);
+    for (auto t : scene->texobjs) cudaDestroyTextureObject(t);
+    for (auto a : scene->arrays) cudaFreeArray(a);
+    for (auto p : scene->allocs) cudaFree(p);
+    delete scene;
+}
+
+rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info) {
+    ARG_CHECK(scene && info, "scene/info is NULL");
+    *info = scene->info;
+    return RT_OK;
+}
+
+rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n, float tmin, int use_bvh,
+                           rt_hit* hits) {
+    ARG_CHECK(ctx && scene, "ctx/scene is NULL");
+    ARG_CHECK(n == 0 || (rays && hits), "rays/hits is NULL");
+    if (n == 0) return RT_OK;
+    rt_status st = make_current(ctx);
+    if (st != RT_OK) return st;
+    rt_ray* d_rays = nullptr;
+    rt_hit* d_hits = nullptr;
+    CUDA_TRY(cudaMalloc(&d_rays, n * sizeof(rt_ray)));
+    cudaError_t e = cudaMalloc(&d_hits, n * sizeof(rt_hit));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        rtd::launch_trace_primary(scene->d, d_rays, n, tmin, use_bvh != 0, d_hits, ctx->stream);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_hits, n * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_rays);
+    if (d_hits) cudaFree(d_hits);
+    if (e != cudaSuccess) {
+        set_error("rt_trace_primary: %s", cudaGetErrorString(e));
+        return RT_ERR_CUDA;
+    }
+    return RT_OK;
+}
+
+rt_status rt_render_accum_device(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, void* accum_dev,
+                                 rt_stats* stats) {
+    ARG_CHECK(ctx && scene && accum_dev, "ctx/scene/accum_dev is NULL");
+    rt_status st = check_params(p);
+    if (st != RT_OK) return st;
+    if ((st = make_current(ctx)) != RT_OK) return st;
+    return render_into(ctx, scene, p, static_cast<float4*>(accum_dev), stats);
+}
+
+rt_status rt_render_accum(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, float* out_accum, rt_stats* stats) {
+    ARG_CHECK(ctx && scene && out_accum, "ctx/scene/out_accum is NULL");
+    rt_status st = check_params(p);
+    if (st != RT_OK) return st;
+    if ((st = make_current(ctx)) != RT_OK) return st;
+    const size_t npix = size_t(p->width) * size_t(p->height);
+    if ((st = ensure_accum(ctx, npix)) != RT_OK) return st;
+    CUDA_TRY(cudaMemsetAsync(ctx->accum, 0, npix * sizeof(float4), ctx->stream));
+    rt_stats local;
+    if ((st = render_into(ctx, scene, p, ctx->accum, &local)) != RT_OK) return st;
+    CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_accum, ctx->accum, npix * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaEventElapsedTime(&local.ms_d2h, ctx->ev[2], ctx->ev[3]));
+    if (stats) *stats = local;
+    return RT_OK;
+}
+
+rt_status rt_tonemap_device(rt_context* ctx, const void* accum_dev, int32_t width, int32_t height, void* out_rgb_dev,
+                            void* out_rgb8_dev) {
+    ARG_CHECK(ctx && accum_dev, "ctx/accum_dev is NULL");
+    ARG_CHECK(width > 0 && height > 0, "width/height must be positive");
+    ARG_CHECK(out_rgb_dev || out_rgb8_dev, "no output buffer");
+    rt_status st = make_current(ctx);
+    if (st != RT_OK) return st;
+    rtd::launch_tonemap(static_cast<const float4*>(accum_dev), width, height, static_cast<float*>(out_rgb_dev),
+                        static_cast<uint8_t*>(out_rgb8_dev), ctx->stream);
+    CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+rt_status rt_render(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, float* out_rgb, rt_stats* stats) {
+    ARG_CHECK(ctx && scene && out_rgb, "ctx/scene/out_rgb is NULL");
+    rt_status st = check_params(p);
+    if (st != RT_OK) return st;
+    if ((st = make_current(ctx)) != RT_OK) return st;
+    const size_t npix = size_t(p->width) * size_t(p->height);
+    if ((st = ensure_accum(ctx, npix)) != RT_OK) return st;
+    if ((st = ensure_out(ctx, npix)) != RT_OK) return st;
+    CUDA_TRY(cudaMemsetAsync(ctx->accum, 0, npix * sizeof(float4), ctx->stream));
+    rt_stats local;
+    if ((st = render_into(ctx, scene, p, ctx->accum, &local)) != RT_OK) return st;
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    rtd::launch_tonemap(ctx->accum, p->width, p->height, ctx->out_rgb, nullptr, ctx->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_rgb, ctx->out_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaEventElapsedTime(&local.ms_tonemap, ctx->ev[1], ctx->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&local.ms_d2h, ctx->ev[2], ctx->ev[3]));
+    local.launches += 1;
+    if (stats) *stats = local;
+    return RT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,167 @@
+// rt_device.cuh — device-side POD scene, reference-faithful vector arithmetic and
+// the counter-based RNG shared by every kernel of the render path.
+//
+// Arithmetic convention (SURVEY.md §8a "Q17"): the reference's vec3 operators are
+// explicit round-toward-zero intrinsics on the device (vec3.h:73-151,258-347), so
+// nothing inside vector math is FMA-contracted; dot()/sq_length() are RZ multiplies
+// summed left-to-right with round-to-nearest adds (vec3.h:168-179,208-219).  The
+// geometric part of this renderer (intersection, hit point, normal, scattered ray)
+// reproduces those roundings with the same intrinsics so closest-hit results are
+// bit-identical to the reference kernel; colour math is ordinary FP32.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rt_api.h"
+
+namespace rtd {
+
+#define RT_DEV __device__ __forceinline__
+
+// ---------------------------------------------------------------- vec3 (RZ) ----
+struct V3 {
+    float x, y, z;
+};
+RT_DEV V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+RT_DEV V3 operator+(V3 a, V3 b) { return V3{__fadd_rz(a.x, b.x), __fadd_rz(a.y, b.y), __fadd_rz(a.z, b.z)}; }
+RT_DEV V3 operator-(V3 a, V3 b) { return V3{__fsub_rz(a.x, b.x), __fsub_rz(a.y, b.y), __fsub_rz(a.z, b.z)}; }
+RT_DEV V3 operator*(V3 a, V3 b) { return V3{__fmul_rz(a.x, b.x), __fmul_rz(a.y, b.y), __fmul_rz(a.z, b.z)}; }
+RT_DEV V3 operator*(V3 a, float t) { return V3{__fmul_rz(a.x, t), __fmul_rz(a.y, t), __fmul_rz(a.z, t)}; }
+RT_DEV V3 operator*(float t, V3 a) { return V3{__fmul_rz(a.x, t), __fmul_rz(a.y, t), __fmul_rz(a.z, t)}; }
+RT_DEV V3 operator/(V3 a, float t) { return V3{__fdiv_rz(a.x, t), __fdiv_rz(a.y, t), __fdiv_rz(a.z, t)}; } // vec3.h:334-347
+RT_DEV V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+// vec3::dot (vec3.h:208-219): RZ products, RN sums, left to right
+RT_DEV float dot(V3 a, V3 b) {
+    return __fadd_rn(__fadd_rn(__fmul_rz(a.x, b.x), __fmul_rz(a.y, b.y)), __fmul_rz(a.z, b.z));
+}
+RT_DEV float length(V3 a) { return __fsqrt_rz(dot(a, a)); } // vec3.h:153-166
+RT_DEV V3 normalize(V3 a) {                                  // vec3.h:199-205
+    if (a.x == 0.f && a.y == 0.f && a.z == 0.f) return a;
+    return a / length(a);
+}
+
+// ---------------------------------------------------------------- scene PODs ----
+struct DCamera { // camera.h:40-47, filled on the host by rt_scene_create
+    V3 origin, lower_left, horizontal, vertical, u, v;
+    float lens_radius, t0, t1;
+};
+
+struct DMaterial { // 32 B, read as 2 x float4
+    uint32_t kind;
+    int32_t tex;
+    float ax, ay, az; // metal albedo / dielectric tint
+    float param;      // roughness / ri / intensity
+    float pad0, pad1;
+};
+
+struct DTexture { // 48 B, read as 3 x float4
+    uint32_t kind;
+    int32_t even, odd, image;
+    float c1x, c1y, c1z, density;
+    float c2x, c2y, c2z, hardness;
+};
+
+struct DImage {
+    cudaTextureObject_t tex;
+    int32_t width, height;
+};
+
+// 64-byte BVH node holding the boxes of BOTH children, so one node visit is four
+// float4 read-only loads and decides both subtrees.  child >= 0: inner node index;
+// child < 0: leaf, primitive index = ~child (one sphere per leaf).
+struct BvhNode {
+    float4 lmin; // (L.min.xyz, as_float(left child))
+    float4 lmax; // (L.max.xyz, as_float(right child))
+    float4 rmin; // (R.min.xyz, unused)
+    float4 rmax; // (R.max.xyz, unused)
+};
+
+#define RT_MAX_IMAGES 8
+
+struct DScene {
+    // primitives, static spheres first: [0, n_static) static, [n_static, n) moving
+    const float4* sph_a;  // (c0.xyz, r)
+    const float4* sph_b;  // (rz(c1-c0).xyz, t0)       — moving spheres only
+    const uint4* sph_c;   // (as_uint(t1-t0), material, id, ordinal in the caller's list)
+    uint32_t n_spheres;
+    uint32_t n_static;
+    const BvhNode* nodes; // nullptr => brute force
+    uint32_t n_nodes;
+    const DMaterial* mats;
+    const DTexture* texs;
+    DImage images[RT_MAX_IMAGES];
+    DCamera cam;
+};
+
+struct DRenderParams {
+    int32_t width, height;
+    int32_t spp, sample_offset;
+    int32_t max_depth;
+    uint32_t seed;
+    float tmin;
+    float world_r, world_g, world_b;
+    float bloom;
+};
+
+struct Ray {
+    V3 o, d;
+    float time;
+};
+
+struct Hit {
+    float t;
+    uint32_t prim; // index into sph_* (RT_INVALID_ID on miss)
+};
+
+// ---------------------------------------------------------------- Philox4x32-10 ----
+// Counter-based RNG keyed on (pixel, sample, bounce): the stream a path sees does
+// not depend on which thread, kernel or GPU evaluates it.  (The reference carries a
+// per-pixel XORWOW state, main.cu:76-95,111 — per-sample parity with it is impossible
+// by construction; parity is distributional.)
+struct U4 {
+    uint32_t x, y, z, w;
+};
+RT_DEV U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return U4{c0, c1, c2, c3};
+}
+// draw block `blk` of (pixel, sample, bounce); bounce 0 = camera
+RT_DEV U4 rng_block(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t blk) {
+    return philox4x32_10(pixel, sample, (bounce << 8) | blk, 0x52544232u, seed, 0x42323030u);
+}
+// curand_uniform's mapping, (0,1]  (reference draws: main.cu:116-117, utils.h:69-72,84-85)
+RT_DEV float u01(uint32_t x) { return __fmaf_rn((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+// Uniform point in the open unit ball.  The reference rejects points of the cube
+// (utils.h:61-77, mean 1.91 tries of 3 uniforms); this draws the same distribution
+// directly (uniform direction x cbrt radius) so every lane does the same work.
+RT_DEV V3 sample_unit_ball(float u1, float u2, float u3) {
+    float z = __fmaf_rn(-2.f, u1, 1.f);
+    float rxy = sqrtf(fmaxf(0.f, __fmaf_rn(-z, z, 1.f)));
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);
+    float rad = fminf(cbrtf(u3), 0.99999994f);
+    return V3{rad * rxy * c, rad * rxy * s, rad * z};
+}
+// Uniform point in the open unit disk (reference: rejection, utils.h:79-91)
+RT_DEV void sample_unit_disk(float u1, float u2, float& dx, float& dy) {
+    float rad = fminf(sqrtf(u1), 0.99999994f);
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);
+    dx = rad * c;
+    dy = rad * s;
+}
+
+} // namespace rtd

@@ -1,0 +1,205 @@
+// rt_intersect.cuh — ray/sphere tests and closest-hit search (brute-force list and
+// flattened BVH).  The sphere tests reproduce the reference's SASS-level operation
+// order (nvcc 12.9, sm_100, disassembled from the unchanged src/main.cu):
+//   oc    = FADD.RZ                                  (vec3 operator-, vec3.h:272-284)
+//   a,b,. = FMUL.RZ products, FADD(RN) sums          (vec3::dot, vec3.h:208-219)
+//   c     = FFMA(-r, r, dot(oc,oc))                  (sphere.h:96: ptxas fuses `- _r*_r`)
+//   delta = FFMA(b, b, -(FMUL a*c))                  (sphere.h:97)
+//   sqrt.rn, div.rn for the roots                    (sphere.h:106-107)
+// so that (id, t) of every closest hit is bit-identical to the reference kernel.
+#pragma once
+
+#include <float.h>
+
+#include "rt_device.cuh"
+
+namespace rtd {
+
+struct RayQ { // ray + per-ray invariants hoisted out of the primitive loop
+    V3 o, d;
+    float time;
+    float a; // dot(d, d) — recomputed per sphere by the reference (sphere.h:94), same value
+};
+
+RT_DEV RayQ make_rayq(const Ray& r) {
+    RayQ q;
+    q.o = r.o;
+    q.d = r.d;
+    q.time = r.time;
+    q.a = dot(r.d, r.d);
+    return q;
+}
+
+// sphere::hit (sphere.h:86-140) root selection for closest-hit use.  Returns the
+// accepted root (near root if >= tmin, else far root if >= tmin; bounds inclusive) or
+// NaN-free "no hit".  The `root > tmax` tests of the reference are subsumed by the
+// caller's strict `t < closest` (hitable_list.h:72, bvh.h:147), see DESIGN.md.
+RT_DEV bool sphere_root_static(const RayQ& q, float4 s, float tmin, float& t) {
+    V3 oc = q.o - mk(s.x, s.y, s.z);
+    float b = dot(oc, q.d);
+    float c = __fmaf_rn(-s.w, s.w, dot(oc, oc));
+    float delta = __fmaf_rn(b, b, -__fmul_rn(q.a, c));
+    if (!(delta >= 0.f)) return false; // sphere.h:99 (`delta < 0`), NaN never survives `t < closest`
+    float sq = __fsqrt_rn(delta);
+    float root = __fdiv_rn(__fadd_rn(-b, -sq), q.a);
+    if (root < tmin) {
+        root = __fdiv_rn(__fadd_rn(-b, sq), q.a);
+        if (root < tmin) return false;
+    }
+    t = root;
+    return true;
+}
+
+// moving_sphere::center (sphere.h:49-52): c0 + ((time - t0) / (t1 - t0)) * (c1 - c0)
+RT_DEV V3 moving_center(float4 a, float4 b, float dt, float time) {
+    float s = __fdiv_rn(__fsub_rn(time, b.w), dt);
+    return mk(a.x, a.y, a.z) + s * mk(b.x, b.y, b.z);
+}
+
+// moving_sphere::hit (sphere.h:157-190): delta > 0 strictly, roots exclusive of tmin
+RT_DEV bool sphere_root_moving(const RayQ& q, float4 a, float4 bq, float dt, float tmin, float& t) {
+    V3 oc = q.o - moving_center(a, bq, dt, q.time);
+    float b = dot(oc, q.d);
+    float c = __fmaf_rn(-a.w, a.w, dot(oc, oc));
+    float delta = __fmaf_rn(b, b, -__fmul_rn(q.a, c));
+    if (!(delta > 0.f)) return false;
+    float sq = __fsqrt_rn(delta);
+    float root = __fdiv_rn(__fadd_rn(-b, -sq), q.a);
+    if (!(root > tmin)) {
+        root = __fdiv_rn(__fadd_rn(-b, sq), q.a);
+        if (!(root > tmin)) return false;
+    }
+    t = root;
+    return true;
+}
+
+// Closest-hit bookkeeping: strictly smaller t wins (hitable_list.h:72); an exact tie
+// goes to the object that comes first in the caller's list, which is what the
+// reference's first-found-wins loop does.
+RT_DEV void consider(const DScene& sc, uint32_t prim, float t, Hit& best) {
+    if (t < best.t) {
+        best.t = t;
+        best.prim = prim;
+    } else if (t == best.t && best.prim != RT_INVALID_ID) {
+        if (__ldg(&sc.sph_c[prim]).w < __ldg(&sc.sph_c[best.prim]).w) best.prim = prim;
+    }
+}
+
+RT_DEV void test_prim(const DScene& sc, const RayQ& q, uint32_t prim, float tmin, Hit& best) {
+    float t;
+    float4 a = __ldg(&sc.sph_a[prim]);
+    if (prim < sc.n_static) {
+        if (sphere_root_static(q, a, tmin, t)) consider(sc, prim, t, best);
+    } else {
+        float4 b = __ldg(&sc.sph_b[prim]);
+        float dt = __uint_as_float(__ldg(&sc.sph_c[prim]).x);
+        if (sphere_root_moving(q, a, b, dt, tmin, t)) consider(sc, prim, t, best);
+    }
+}
+
+// hitable_list::hit with bvh == nullptr (hitable_list.h:66-78)
+RT_DEV Hit closest_hit_list(const DScene& sc, const RayQ& q, float tmin) {
+    Hit best{FLT_MAX, RT_INVALID_ID};
+    float t;
+    for (uint32_t i = 0; i < sc.n_static; ++i) {
+        float4 a = __ldg(&sc.sph_a[i]);
+        if (sphere_root_static(q, a, tmin, t)) consider(sc, i, t, best);
+    }
+    for (uint32_t i = sc.n_static; i < sc.n_spheres; ++i) {
+        float4 a = __ldg(&sc.sph_a[i]);
+        float4 b = __ldg(&sc.sph_b[i]);
+        float dt = __uint_as_float(__ldg(&sc.sph_c[i]).x);
+        if (sphere_root_moving(q, a, b, dt, tmin, t)) consider(sc, i, t, best);
+    }
+    return best;
+}
+
+// Conservative slab test (the far bound is widened by 2 ulp so rounding can only
+// add node visits, never remove a leaf the sphere test would accept).
+RT_DEV bool slab(float4 lo, float4 hi, const V3& o, const V3& inv, float tmin, float tmax, float& tnear) {
+    float tx0 = (lo.x - o.x) * inv.x, tx1 = (hi.x - o.x) * inv.x;
+    float ty0 = (lo.y - o.y) * inv.y, ty1 = (hi.y - o.y) * inv.y;
+    float tz0 = (lo.z - o.z) * inv.z, tz1 = (hi.z - o.z) * inv.z;
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
+    tnear = tn;
+    return tn <= tf * 1.0000003f;
+}
+
+#define RT_BVH_STACK 64
+
+// Flattened-BVH closest hit: short per-thread stack, both child boxes fetched with four
+// float4 read-only loads per visited node, near child first, culled by the closest t so far.
+// (Reference: bvh_node::dfs, bvh.h:121-155 — pointer-chasing, unordered, never culls by
+// `closest`, recomputes 1/d for every box: aabb.h:54-68.)
+RT_DEV Hit closest_hit_bvh(const DScene& sc, const RayQ& q, float tmin) {
+    Hit best{FLT_MAX, RT_INVALID_ID};
+    if (sc.n_spheres == 1) {
+        test_prim(sc, q, 0, tmin, best);
+        return best;
+    }
+    V3 inv{1.0f / q.d.x, 1.0f / q.d.y, 1.0f / q.d.z};
+    int stack[RT_BVH_STACK];
+    int sp = 0;
+    int node = 0;
+    while (true) {
+        const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+        float4 lmin = __ldg(np + 0), lmax = __ldg(np + 1), rmin = __ldg(np + 2), rmax = __ldg(np + 3);
+        float tl, tr;
+        bool hl = slab(lmin, lmax, q.o, inv, tmin, best.t, tl);
+        bool hr = slab(rmin, rmax, q.o, inv, tmin, best.t, tr);
+        int cl = __float_as_int(lmin.w), cr = __float_as_int(lmax.w);
+        if (hl && cl < 0) {
+            test_prim(sc, q, uint32_t(~cl), tmin, best);
+            hl = false;
+        }
+        if (hr && cr < 0) {
+            test_prim(sc, q, uint32_t(~cr), tmin, best);
+            hr = false;
+        }
+        if (hl && hr) {
+            bool left_first = tl <= tr;
+            int nearc = left_first ? cl : cr;
+            int farc = left_first ? cr : cl;
+            if (sp < RT_BVH_STACK) stack[sp++] = farc;
+            node = nearc;
+        } else if (hl) {
+            node = cl;
+        } else if (hr) {
+            node = cr;
+        } else {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return best;
+}
+
+RT_DEV Hit closest_hit(const DScene& sc, const RayQ& q, float tmin, bool use_bvh) {
+    return (use_bvh && sc.nodes) ? closest_hit_bvh(sc, q, tmin) : closest_hit_list(sc, q, tmin);
+}
+
+// Surface data of an accepted hit: p = o + t*d (ray.h:28-30), outward normal
+// n = (p - c)/r (sphere.h:123), both in the reference's RZ arithmetic.
+RT_DEV void hit_surface(const DScene& sc, const RayQ& q, Hit h, V3& p, V3& n) {
+    float4 a = __ldg(&sc.sph_a[h.prim]);
+    V3 c = mk(a.x, a.y, a.z);
+    if (h.prim >= sc.n_static) {
+        float4 b = __ldg(&sc.sph_b[h.prim]);
+        float dt = __uint_as_float(__ldg(&sc.sph_c[h.prim]).x);
+        c = moving_center(a, b, dt, q.time);
+    }
+    p = q.o + h.t * q.d;
+    n = (p - c) / a.w;
+}
+
+// sphere::get_sphere_uv (sphere.h:61-83): atan2f/asinf in float, the affine map in double.
+// KAT (sphere.h:71-77): (1,0,0)->(.5,.5) (0,1,0)->(.5,1) (0,0,1)->(.25,.5) (-1,0,0)->(0,.5)
+RT_DEV void sphere_uv(V3 n, float& u, float& v) {
+    float phi = atan2f(n.z, n.x);
+    float theta = asinf(n.y);
+    u = 1 - (phi + 3.14159265358979323846) / (2 * 3.14159265358979323846);
+    v = (theta + 1.57079632679489661923) / 3.14159265358979323846;
+}
+
+} // namespace rtd

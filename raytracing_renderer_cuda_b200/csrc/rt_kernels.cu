@@ -1,0 +1,156 @@
+// rt_kernels.cu — parity hook, per-path megakernel, tonemap.  sm_100a only.
+#include "rt_kernels.cuh"
+#include "rt_shade.cuh"
+
+namespace rtd {
+
+// --------------------------------------------------------------- trace_primary ----
+// scene.hit(r, tmin, FLT_MAX, rec) for caller-supplied rays (hitable_list.h:60-79).
+__global__ void __launch_bounds__(256) k_trace_primary(const __grid_constant__ DScene sc, const rt_ray* __restrict__ rays,
+                                                       size_t n, float tmin, int use_bvh, rt_hit* __restrict__ hits) {
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rt_ray in = rays[i];
+    Ray r;
+    r.o = mk(in.origin[0], in.origin[1], in.origin[2]);
+    r.d = mk(in.direction[0], in.direction[1], in.direction[2]);
+    r.time = in.time;
+    RayQ q = make_rayq(r);
+    Hit h = closest_hit(sc, q, tmin, use_bvh != 0);
+    rt_hit out;
+    if (h.prim == RT_INVALID_ID) {
+        out.t = FLT_MAX;
+        out.id = RT_INVALID_ID;
+        out.p[0] = out.p[1] = out.p[2] = 0.f;
+        out.n[0] = out.n[1] = out.n[2] = 0.f;
+        out.u = out.v = 0.f;
+    } else {
+        V3 p, nn;
+        hit_surface(sc, q, h, p, nn);
+        out.t = h.t;
+        out.id = __ldg(&sc.sph_c[h.prim]).z;
+        out.p[0] = p.x; out.p[1] = p.y; out.p[2] = p.z;
+        out.n[0] = nn.x; out.n[1] = nn.y; out.n[2] = nn.z;
+        sphere_uv(nn, out.u, out.v);
+    }
+    hits[i] = out;
+}
+
+void launch_trace_primary(const DScene& sc, const rt_ray* rays_dev, size_t n, float tmin, bool use_bvh,
+                          rt_hit* hits_dev, cudaStream_t st) {
+    if (n == 0) return;
+    unsigned blocks = unsigned((n + 255) / 256);
+    k_trace_primary<<<blocks, 256, 0, st>>>(sc, rays_dev, n, tmin, use_bvh ? 1 : 0, hits_dev);
+}
+
+// --------------------------------------------------------------- megakernel ----
+// One thread per path, grid-stride over (sample, pixel) with pixel fastest so a warp
+// covers 32 neighbouring pixels of one sample.  This is the reference's structure
+// (render + color(), main.cu:35-74,97-132) on the flat scene; it is kept as the
+// RT_PIPE_MEGAKERNEL pipeline and as the yardstick the wavefront pipeline is measured against.
+__global__ void __launch_bounds__(256) k_render_mega(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp,
+                                                     int use_bvh, float4* __restrict__ accum,
+                                                     unsigned long long* __restrict__ ray_counter) {
+    extern __shared__ uint32_t smem[];
+    perlin_stage(smem, threadIdx.x, blockDim.x);
+    __syncthreads();
+    PerlinTab pt{smem, threadIdx.x & 31u};
+
+    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
+    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long nrays = 0;
+    for (unsigned long long path = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; path < npaths; path += stride) {
+        uint32_t pixel = uint32_t(path % npix);
+        uint32_t sample = uint32_t(path / npix) + uint32_t(rp.sample_offset);
+        Ray r = camera_ray(sc, rp, pixel, sample);
+        V3 A = mk(rp.world_r, rp.world_g, rp.world_b); // main.cu:40
+        V3 result = mk(0.f, 0.f, 0.f);                 // exceeded recursion (main.cu:70)
+        for (int bounce = 1; bounce <= rp.max_depth; ++bounce) {
+            RayQ q = make_rayq(r);
+            Hit h = closest_hit(sc, q, rp.tmin, use_bvh != 0);
+            ++nrays;
+            if (h.prim == RT_INVALID_ID) { // main.cu:66-67: return world colour times nothing: A itself
+                result = A;
+                break;
+            }
+            Ray next;
+            if (!shade_hit(sc, rp, pt, q, h, pixel, sample, uint32_t(bounce), A, next)) {
+                result = A;
+                break;
+            }
+            r = next;
+        }
+        atomicAdd(&accum[pixel], make_float4(result.x, result.y, result.z, 1.f)); // RED.E.ADD.F32x4 (sm_90+)
+    }
+    // one counter update per warp
+    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
+    if ((threadIdx.x & 31) == 0 && nrays) atomicAdd(ray_counter, nrays);
+}
+
+void launch_render_mega(const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
+                        unsigned long long* ray_counter, int sm_count, cudaStream_t st) {
+    unsigned long long npaths = (unsigned long long)rp.width * rp.height * (unsigned long long)rp.spp;
+    if (npaths == 0) return;
+    const size_t smem = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_render_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        attr_set = true;
+    }
+    unsigned long long want = (npaths + 255) / 256;
+    unsigned long long cap = (unsigned long long)sm_count * 32; // several waves of resident CTAs, grid-stride beyond
+    unsigned blocks = unsigned(want < cap ? want : cap);
+    k_render_mega<<<blocks, 256, smem, st>>>(sc, rp, use_bvh ? 1 : 0, accum, ray_counter);
+}
+
+// --------------------------------------------------------------- tonemap ----
+// main.cu:124-127: col /= spp (vec3::operator/=(float): rz(1/f) then RZ multiplies,
+// vec3.h:138-151), saturate (vec3.h:349-356), gamma 2 = __fsqrt_rz (vec3.h:181-187).
+// out_rgb: reference framebuffer layout, index j*W+i with j = 0 the bottom row.
+// out_rgb8: the writer loop main.cu:476-487 — Y flip and int(255.999f*c) & 255.
+__global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accum, int width, int height,
+                                                 float* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8) {
+    size_t npix = size_t(width) * height;
+    for (size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < npix; idx += size_t(gridDim.x) * blockDim.x) {
+        float4 a = __ldg(&accum[idx]);
+        float inv = __fdiv_rz(1.0f, a.w);
+        float r = __fsqrt_rz(__saturatef(__fmul_rz(a.x, inv)));
+        float g = __fsqrt_rz(__saturatef(__fmul_rz(a.y, inv)));
+        float b = __fsqrt_rz(__saturatef(__fmul_rz(a.z, inv)));
+        if (out_rgb) {
+            out_rgb[idx * 3 + 0] = r;
+            out_rgb[idx * 3 + 1] = g;
+            out_rgb[idx * 3 + 2] = b;
+        }
+        if (out_rgb8) {
+            size_t i = idx % size_t(width), j = idx / size_t(width);
+            size_t rev = (size_t(height) - 1 - j) * size_t(width) + i;
+            out_rgb8[rev * 3 + 0] = uint8_t(int(255.999f * r) & 255);
+            out_rgb8[rev * 3 + 1] = uint8_t(int(255.999f * g) & 255);
+            out_rgb8[rev * 3 + 2] = uint8_t(int(255.999f * b) & 255);
+        }
+    }
+}
+
+void launch_tonemap(const float4* accum, int width, int height, float* out_rgb, uint8_t* out_rgb8, cudaStream_t st) {
+    size_t npix = size_t(width) * height;
+    if (npix == 0) return;
+    size_t want = (npix + 255) / 256;
+    unsigned blocks = unsigned(want < 148 * 16 ? want : 148 * 16);
+    k_tonemap<<<blocks, 256, 0, st>>>(accum, width, height, out_rgb, out_rgb8);
+}
+
+__global__ void __launch_bounds__(256) k_rgb_to_rgba(const float* __restrict__ rgb, float4* __restrict__ rgba, size_t n) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+        rgba[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 1.f);
+}
+
+void launch_rgb_to_rgba(const float* rgb, float4* rgba, size_t n_texels, cudaStream_t st) {
+    if (n_texels == 0) return;
+    size_t want = (n_texels + 255) / 256;
+    unsigned blocks = unsigned(want < 148 * 16 ? want : 148 * 16);
+    k_rgb_to_rgba<<<blocks, 256, 0, st>>>(rgb, rgba, n_texels);
+}
+
+} // namespace rtd

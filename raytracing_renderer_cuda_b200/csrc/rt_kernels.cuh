@@ -1,0 +1,34 @@
+// rt_kernels.cuh — host-callable launchers of the sm_100a kernels (defined in the .cu files).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "rt_device.cuh"
+
+namespace rtd {
+
+// parity hook: closest hit for caller-supplied rays
+void launch_trace_primary(const DScene& sc, const rt_ray* rays_dev, size_t n, float tmin, bool use_bvh,
+                          rt_hit* hits_dev, cudaStream_t st);
+
+// one thread runs whole paths (reference structure, main.cu:35-74,97-132)
+void launch_render_mega(const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
+                        unsigned long long* ray_counter, int sm_count, cudaStream_t st);
+
+// pixel finalisation (main.cu:124-127) + optional writer conversion (main.cu:476-487)
+void launch_tonemap(const float4* accum, int width, int height, float* out_rgb, uint8_t* out_rgb8, cudaStream_t st);
+
+// float RGB (w*h*3) -> float4 RGBA staging for the image-texture cudaArray
+void launch_rgb_to_rgba(const float* rgb, float4* rgba, size_t n_texels, cudaStream_t st);
+
+// wavefront pipeline state (rt_wavefront.cu)
+struct WavefrontState;
+WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st);
+void wavefront_destroy(WavefrontState* ws);
+size_t wavefront_pool(const WavefrontState* ws);
+// renders rp.spp samples of every pixel into accum (+=); returns launches/iterations
+void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
+                      unsigned long long* ray_counter, int sm_count, cudaStream_t st, uint32_t* launches,
+                      uint32_t* iterations);
+
+} // namespace rtd

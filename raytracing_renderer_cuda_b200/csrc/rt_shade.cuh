@@ -1,0 +1,311 @@
+// rt_shade.cuh — camera rays, textures (incl. Perlin), materials and the per-hit
+// integrator step.  Semantics follow SURVEY.md §8a / §8a' item by item; every function
+// cites the reference lines it restates.
+#pragma once
+
+#include "rt_intersect.cuh"
+
+namespace rtd {
+
+// ------------------------------------------------------------------ Perlin ----
+// Ken Perlin's 2002 permutation (perlin_noise.h:24-37).  p[512] of the reference is
+// this table twice (perlin_noise.h:43), so p[i] == perm[i & 255] for every index used.
+__device__ const uint8_t k_perlin_perm[256] = {
+    151, 160, 137, 91,  90,  15,  131, 13,  201, 95,  96,  53,  194, 233, 7,   225, 140, 36,  103, 30,  69,  142,
+    8,   99,  37,  240, 21,  10,  23,  190, 6,   148, 247, 120, 234, 75,  0,   26,  197, 62,  94,  252, 219, 203,
+    117, 35,  11,  32,  57,  177, 33,  88,  237, 149, 56,  87,  174, 20,  125, 136, 171, 168, 68,  175, 74,  165,
+    71,  134, 139, 48,  27,  166, 77,  146, 158, 231, 83,  111, 229, 122, 60,  211, 133, 230, 220, 105, 92,  41,
+    55,  46,  245, 40,  244, 102, 143, 54,  65,  25,  63,  161, 1,   216, 80,  73,  209, 76,  132, 187, 208, 89,
+    18,  169, 200, 196, 135, 130, 116, 188, 159, 86,  164, 100, 109, 198, 173, 186, 3,   64,  52,  217, 226, 250,
+    124, 123, 5,   202, 38,  147, 118, 126, 255, 82,  85,  212, 207, 206, 59,  227, 47,  16,  58,  17,  182, 189,
+    28,  42,  223, 183, 170, 213, 119, 248, 152, 2,   44,  154, 163, 70,  221, 153, 101, 155, 167, 43,  172, 9,
+    129, 22,  39,  253, 19,  98,  108, 110, 79,  113, 224, 232, 178, 185, 112, 104, 218, 246, 97,  228, 251, 34,
+    242, 193, 238, 210, 144, 12,  191, 179, 162, 241, 81,  51,  145, 235, 249, 14,  239, 107, 49,  192, 214, 31,
+    181, 199, 106, 157, 184, 84,  204, 176, 115, 121, 50,  45,  127, 4,   150, 254, 138, 236, 205, 93,  222, 114,
+    67,  29,  24,  72,  243, 141, 128, 195, 78,  66,  215, 61,  156, 180};
+
+// Shared-memory staging of the permutation.  Entry i holds the PAIR (perm[i], perm[i+1])
+// so the two neighbouring lookups every hash level needs (perlin_noise.h:67-72) cost one
+// load, and the table is replicated once per bank (word i*32 + lane) so the 32 lanes of a
+// warp never conflict however divergent their lattice cells are.  256 x 32 x 4 B = 32 KB.
+#define RT_PERLIN_SMEM_WORDS (256 * 32)
+struct PerlinTab {
+    const uint32_t* s; // shared memory, RT_PERLIN_SMEM_WORDS words
+    uint32_t lane;
+};
+RT_DEV void perlin_stage(uint32_t* smem, uint32_t tid, uint32_t nthreads) {
+    for (uint32_t w = tid; w < RT_PERLIN_SMEM_WORDS; w += nthreads) {
+        uint32_t i = w >> 5;
+        smem[w] = uint32_t(k_perlin_perm[i]) | (uint32_t(k_perlin_perm[(i + 1) & 255]) << 8);
+    }
+}
+RT_DEV uint32_t perlin_pair(const PerlinTab& pt, uint32_t i) { return pt.s[((i & 255u) << 5) | pt.lane]; }
+
+// perlin_noise::grad (perlin_noise.h:173-181)
+RT_DEV float perlin_grad(uint32_t hash, float x, float y, float z) {
+    uint32_t h = hash & 15u;
+    float u = h < 8u ? x : y;
+    float v = h < 4u ? y : ((h == 12u || h == 14u) ? x : z);
+    return ((h & 1u) == 0u ? u : -u) + ((h & 2u) == 0u ? v : -v);
+}
+RT_DEV float perlin_ease(float t) { return t * t * t * (t * (t * 6.f - 15.f) + 10.f); } // :156-165
+RT_DEV float perlin_lerp(float t, float a, float b) { return a + t * (b - a); }         // :167-171
+
+// perlin_noise::noise (perlin_noise.h:46-105)
+RT_DEV float perlin_noise(const PerlinTab& pt, V3 p) {
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    uint32_t xi = uint32_t(int(fx)) & 255u, yi = uint32_t(int(fy)) & 255u, zi = uint32_t(int(fz)) & 255u;
+    float xf = p.x - fx, yf = p.y - fy, zf = p.z - fz;
+    float u = perlin_ease(xf), v = perlin_ease(yf), w = perlin_ease(zf);
+    uint32_t px = perlin_pair(pt, xi);        // (p[xi], p[xi+1])
+    uint32_t A = (px & 255u) + yi;            // p[xi] + yi
+    uint32_t B = ((px >> 8) & 255u) + yi;     // p[xi+1] + yi
+    uint32_t pa = perlin_pair(pt, A);         // (p[A], p[A+1])
+    uint32_t pb = perlin_pair(pt, B);         // (p[B], p[B+1])
+    uint32_t AA = (pa & 255u) + zi, AB = ((pa >> 8) & 255u) + zi;
+    uint32_t BA = (pb & 255u) + zi, BB = ((pb >> 8) & 255u) + zi;
+    uint32_t gaa = perlin_pair(pt, AA), gba = perlin_pair(pt, BA); // (p[AA], p[AA+1]) ...
+    uint32_t gab = perlin_pair(pt, AB), gbb = perlin_pair(pt, BB);
+    float x1 = xf - 1.f, y1 = yf - 1.f, z1 = zf - 1.f;
+    float res = perlin_lerp(
+        w,
+        perlin_lerp(v, perlin_lerp(u, perlin_grad(gaa, xf, yf, zf), perlin_grad(gba, x1, yf, zf)),
+                    perlin_lerp(u, perlin_grad(gab, xf, y1, zf), perlin_grad(gbb, x1, y1, zf))),
+        perlin_lerp(v, perlin_lerp(u, perlin_grad(gaa >> 8, xf, yf, z1), perlin_grad(gba >> 8, x1, yf, z1)),
+                    perlin_lerp(u, perlin_grad(gab >> 8, xf, y1, z1), perlin_grad(gbb >> 8, x1, y1, z1))));
+    return (res + 1.0f) / 2.0f;
+}
+
+// perlin_noise::turbulance_noise, implementation 3 (perlin_noise.h:142-153), defaults
+// lacunacity 2, gain .5, 6 octaves (perlin_noise.h:13-17)
+RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
+    float frequency = 1.f, sum = 0.f, amplitude = 1.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        float r = perlin_noise(pt, p * frequency);
+        sum += fabsf(r * 2.f - 1.f) * amplitude;
+        frequency *= 2.f;
+        amplitude *= 0.5f;
+    }
+    return sum;
+}
+
+// ------------------------------------------------------------------ textures ----
+RT_DEV DTexture load_tex(const DScene& sc, int32_t ix) {
+    const float4* tp = reinterpret_cast<const float4*>(sc.texs + ix);
+    float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    DTexture t;
+    t.kind = __float_as_uint(a.x);
+    t.even = __float_as_int(a.y);
+    t.odd = __float_as_int(a.z);
+    t.image = __float_as_int(a.w);
+    t.c1x = b.x; t.c1y = b.y; t.c1z = b.z; t.density = b.w;
+    t.c2x = c.x; t.c2y = c.y; t.c2z = c.z; t.hardness = c.w;
+    return t;
+}
+
+// checker_texture::value (texture.h:41-48) only selects a child from p; children may be
+// checkers themselves.  Returns the index of the leaf texture and loads it into `t`.
+RT_DEV int32_t resolve_texture(const DScene& sc, int32_t ix, V3 p, DTexture& t) {
+    t = load_tex(sc, ix);
+    for (int guard = 0; guard < 8 && t.kind == RT_TEX_CHECKER; ++guard) {
+        float sines = __sinf(10 * p.x) * __sinf(10 * p.y) * __sinf(10 * p.z);
+        ix = sines < 0.f ? t.odd : t.even;
+        t = load_tex(sc, ix);
+    }
+    return ix;
+}
+
+RT_DEV V3 tex_constant(const DTexture& t) { return mk(t.c1x, t.c1y, t.c1z); } // texture.h:22-24
+RT_DEV V3 tex_perlin(const PerlinTab& pt, const DTexture& t, V3 p) {         // texture.h:58-59
+    float v = perlin_noise(pt, p * t.density);
+    return mk(v, v, v);
+}
+RT_DEV V3 tex_turbulence(const PerlinTab& pt, const DTexture& t, V3 p) { // texture.h:60-63: vec3(1) * 0.5 * turb(p * density)
+    float v = __fmul_rz(0.5f, perlin_turbulence(pt, p * t.density));
+    return mk(v, v, v);
+}
+RT_DEV V3 tex_marble(const PerlinTab& pt, const DTexture& t, V3 p) { // texture.h:65-75: turbulence of the UNSCALED p
+    float value = 0.5f * (1 + __sinf((p.z * t.density + 7 * perlin_turbulence(pt, p))));
+    V3 color1 = mk(0.925f, 0.816f, 0.78f);
+    V3 color2 = mk(float(0.349 / 2), float(0.431 / 2), float(0.498 / 2));
+    return color1 * value + color2 * (1 - value);
+}
+RT_DEV V3 tex_wood(const PerlinTab& pt, const DTexture& t, V3 p) { // texture.h:99-104
+    float nn = t.hardness * perlin_noise(pt, p / t.density);
+    nn -= floorf(nn);
+    return (mk(t.c1x, t.c1y, t.c1z) * nn) + (mk(t.c2x, t.c2y, t.c2z) * (1.f - nn));
+}
+RT_DEV V3 tex_image(const DScene& sc, const DTexture& t, V3 n) { // image_texture::value (texture.h:118-132)
+    float u, v;
+    sphere_uv(n, u, v);
+    const DImage& im = sc.images[t.image];
+    int i = u * im.width;
+    int j = (1 - v) * im.height - 0.001;
+    if (i < 0) i = 0;
+    if (j < 0) j = 0;
+    if (i > im.width - 1) i = im.width - 1;
+    if (j > im.height - 1) j = im.height - 1;
+    float4 c = tex2D<float4>(im.tex, i + 0.5f, j + 0.5f); // nearest texel, row 0 = top
+    return mk(c.x, c.y, c.z);
+}
+
+// text::value(u, v, p) of a non-checker texture.  (u,v) are only needed by image textures
+// and are derived from the outward normal there (sphere.h:123-128).
+RT_DEV V3 texture_leaf_value(const DScene& sc, const PerlinTab& pt, const DTexture& t, V3 n, V3 p) {
+    switch (t.kind) {
+    case RT_TEX_CONSTANT: return tex_constant(t);
+    case RT_TEX_NOISE_PERLIN: return tex_perlin(pt, t, p);
+    case RT_TEX_NOISE_TURBULANCE: return tex_turbulence(pt, t, p);
+    case RT_TEX_NOISE_MARBLE: return tex_marble(pt, t, p);
+    case RT_TEX_WOOD: return tex_wood(pt, t, p);
+    case RT_TEX_IMAGE: return tex_image(sc, t, n);
+    default: return mk(1.f, 1.f, 1.f);
+    }
+}
+
+RT_DEV V3 texture_value(const DScene& sc, const PerlinTab& pt, int32_t ix, V3 n, V3 p) {
+    DTexture t;
+    resolve_texture(sc, ix, p, t);
+    return texture_leaf_value(sc, pt, t, n, p);
+}
+
+// ------------------------------------------------------------------ camera ----
+// render()'s per-sample set-up (main.cu:116-118) + camera::get_ray (camera.h:33-38).
+// Draw order of the reference: jitter x, jitter y, lens disk, shutter time.
+RT_DEV Ray camera_ray(const DScene& sc, const DRenderParams& rp, uint32_t pixel, uint32_t sample) {
+    const DCamera& cam = sc.cam;
+    uint32_t i = pixel % uint32_t(rp.width), j = pixel / uint32_t(rp.width);
+    U4 r0 = rng_block(rp.seed, pixel, sample, 0, 0);
+    float s = float(i + u01(r0.x)) / float(rp.width);
+    float t = float(j + u01(r0.y)) / float(rp.height);
+    float dx, dy;
+    sample_unit_disk(u01(r0.z), u01(r0.w), dx, dy);
+    V3 rd = cam.lens_radius * mk(dx, dy, 0.f);
+    V3 offset = cam.u * rd.x + cam.v * rd.y;
+    float time = cam.t0;
+    if (cam.t1 != cam.t0) {
+        U4 r1 = rng_block(rp.seed, pixel, sample, 0, 1);
+        time = cam.t0 + u01(r1.x) * (cam.t1 - cam.t0);
+    }
+    Ray r;
+    r.o = cam.origin + offset;
+    r.d = cam.lower_left + s * cam.horizontal + t * cam.vertical - cam.origin - offset;
+    r.time = time;
+    return r;
+}
+
+// ------------------------------------------------------------------ materials ----
+RT_DEV DMaterial load_mat(const DScene& sc, uint32_t ix) {
+    const float4* mp = reinterpret_cast<const float4*>(sc.mats + ix);
+    float4 a = __ldg(mp), b = __ldg(mp + 1);
+    DMaterial m;
+    m.kind = __float_as_uint(a.x);
+    m.tex = __float_as_int(a.y);
+    m.ax = a.z; m.ay = a.w; m.az = b.x; m.param = b.y;
+    m.pad0 = m.pad1 = 0.f;
+    return m;
+}
+
+RT_DEV V3 reflect(V3 v, V3 n) { return v - 2.f * dot(v, n) * n; } // utils.h:93-97
+
+// utils::refract (utils.h:107-122)
+RT_DEV bool refract(V3 v, V3 n, float mu, V3& refracted) {
+    V3 i = normalize(v);
+    float in = dot(i, n);
+    float delta = 1.f - mu * mu * (1 - in * in);
+    if (delta > 0) {
+        refracted = mu * (i - n * in) - n * sqrtf(delta);
+        return true;
+    }
+    return false;
+}
+
+// utils::shlick (utils.h:124-137)
+RT_DEV float shlick(float cosine, float ref_id) {
+    float r0 = __fdiv_rz((1.f - ref_id), (1.f + ref_id));
+    r0 = __fmul_rz(r0, r0);
+    return r0 + __fmul_rz((1.f - r0), __powf(1.f - cosine, 5.f));
+}
+
+// lambertian::scatter (material.h:105-116): target = p + n + ball; ray keeps rin's time
+RT_DEV void scatter_lambertian(const RayQ& q, V3 p, V3 n, U4 r, Ray& out) {
+    V3 target = p + n + sample_unit_ball(u01(r.x), u01(r.y), u01(r.z));
+    out.o = p;
+    out.d = target - p;
+    out.time = q.time;
+}
+
+// metal::scatter (material.h:118-131): draws the ball sample even at roughness 0, ray time
+// resets to 0 (ray.h:12 default), absorbed when dot(out, n) <= 0
+RT_DEV bool scatter_metal(const RayQ& q, V3 p, V3 n, float roughness, U4 r, Ray& out) {
+    V3 reflection = reflect(normalize(q.d), n);
+    out.o = p;
+    out.d = reflection + roughness * sample_unit_ball(u01(r.x), u01(r.y), u01(r.z));
+    out.time = 0.f;
+    return dot(out.d, n) > 0.f;
+}
+
+// dielectric::scatter (material.h:133-184); ray time resets to 0
+RT_DEV void scatter_dielectric(const RayQ& q, V3 p, V3 n, float ri, U4 r, Ray& out) {
+    V3 refraction_normal;
+    V3 reflected = reflect(q.d, n);
+    float mu, cosine;
+    float ddn = dot(q.d, n);
+    if (ddn > 0.f) {
+        refraction_normal = -n;
+        mu = ri;
+        cosine = ddn / length(q.d);
+        cosine = __fsqrt_rz(1.f - ri * ri * (1 - cosine * cosine));
+    } else {
+        refraction_normal = n;
+        mu = 1.f / ri;
+        cosine = -ddn / length(q.d);
+    }
+    float reflect_prob;
+    V3 refracted = mk(0.f, 0.f, 0.f);
+    if (refract(q.d, refraction_normal, mu, refracted)) {
+        reflect_prob = shlick(cosine, ri);
+    } else {
+        reflect_prob = 1.f;
+    }
+    out.o = p;
+    out.d = (u01(r.w) < reflect_prob) ? reflected : refracted;
+    out.time = 0.f;
+}
+
+// One integrator step at an accepted hit — the body of color()'s loop (main.cu:45-55):
+//   E = m.emit(h) + bloom;  if m.scatter(...)  A = E + att*A, continue with `out`
+//                           else               the path's value is E (A is dropped).
+// Returns true if the path continues.  `bounce` counts from 1 for the RNG key.
+RT_DEV bool shade_hit(const DScene& sc, const DRenderParams& rp, const PerlinTab& pt, const RayQ& q, Hit h,
+                      uint32_t pixel, uint32_t sample, uint32_t bounce, V3& A, Ray& out) {
+    V3 p, n;
+    hit_surface(sc, q, h, p, n);
+    DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
+    V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
+    if (m.kind == RT_MAT_EMITTER) { // emitter::emit / scatter (material.h:42-52)
+        A = texture_value(sc, pt, m.tex, n, p) * m.param + bloom;
+        return false;
+    }
+    V3 E = mk(0.f, 0.f, 0.f) + bloom; // material::emit (material.h:14-16)
+    U4 r = rng_block(rp.seed, pixel, sample, bounce, 0);
+    V3 att;
+    if (m.kind == RT_MAT_LAMBERTIAN) {
+        scatter_lambertian(q, p, n, r, out);
+        att = texture_value(sc, pt, m.tex, n, p);
+    } else if (m.kind == RT_MAT_METAL) {
+        att = mk(m.ax, m.ay, m.az);
+        if (!scatter_metal(q, p, n, m.param, r, out)) { // absorbed: the path's value is E
+            A = E;
+            return false;
+        }
+    } else {
+        att = mk(m.ax, m.ay, m.az);
+        scatter_dielectric(q, p, n, m.param, r, out);
+    }
+    A = E + att * A; // main.cu:51
+    return true;
+}
+
+} // namespace rtd

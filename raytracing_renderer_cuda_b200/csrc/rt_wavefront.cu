@@ -1,0 +1,390 @@
+// rt_wavefront.cu — the wavefront pipeline (BASELINE.json north_star (2)).
+//
+// A pool of P path slots lives in device memory as 64-byte records; every iteration ONE
+// kernel launch advances every live path by one bounce.  Work is organised as queues of
+// slot indices, one queue per shading class:
+//
+//   Q_NEW         free slots: ray-gen (camera + jitter + Philox) for the next path id
+//   Q_LAMB_CONST  lambertian, constant albedo
+//   Q_LAMB_NOISE1 lambertian, one-octave Perlin (noise PERLIN, wood)
+//   Q_LAMB_NOISE6 lambertian, six-octave turbulence (noise TURBULANCE / MARBLE)
+//   Q_LAMB_IMAGE  lambertian, image texture
+//   Q_METAL, Q_DIEL
+//   Q_EMIT        emitter with a non-constant texture (constant emitters and misses
+//                 terminate inside the extend step: "shadow/emission")
+//
+// A CTA takes a 256-entry chunk of ONE queue, so every warp runs one shader with all lanes
+// doing the same thing (the reference's megakernel mixes all of them in every warp).  The
+// shade step produces the scattered ray, the same thread extends it (closest hit), classifies
+// the hit and pushes its slot into the matching queue of the next iteration.  Pushes are
+// compacted with __match_any_sync ballots, aggregated per warp into shared-memory counters
+// and then into ONE global atomic per (CTA chunk, queue).  Terminated paths add their value
+// to the float4 accumulator with a single vector reduction (RED.ADD.F32x4) and hand their
+// slot to Q_NEW, so the pool stays full until the frame's paths run out (path regeneration).
+//
+// The pool is sized to stay resident in B200's 126 MB L2 (default 1 Mi slots = 64 MiB of
+// records), so queue and record traffic is L2 traffic, not HBM traffic.
+#include <cstdio>
+#include <cstdlib>
+
+#include "rt_kernels.cuh"
+#include "rt_shade.cuh"
+
+namespace rtd {
+
+enum : int { Q_NEW = 0, Q_LAMB_CONST, Q_LAMB_NOISE1, Q_LAMB_NOISE6, Q_LAMB_IMAGE, Q_METAL, Q_DIEL, Q_EMIT, NQ };
+#define Q_NONE (-1)
+#define WF_THREADS 256
+
+struct WfRecord { // 64 B, one per slot
+    float4 o;     // origin.xyz, ray time
+    float4 d;     // direction.xyz, t of the pending hit
+    float4 a;     // attenuation A.rgb (main.cu:40,51), as_float(prim of the pending hit)
+    uint4 ids;    // pixel, sample, bounce (= traces done), leaf texture of the pending hit
+};
+
+struct WfBuffers {
+    WfRecord* rec;               // [pool]
+    uint32_t* queue;             // [2][NQ][pool]
+    uint32_t* counts;            // [3][NQ] queue sizes, rotating: cur / next / being-zeroed
+    unsigned long long* next_path; // next path id to generate
+    uint32_t pool;
+};
+
+struct WavefrontState {
+    WfBuffers b{};
+    unsigned long long* h_status = nullptr; // pinned: [0] next_path, [1..NQ] counts of the polled buffer
+    uint32_t* h_counts = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+RT_DEV uint32_t* wf_queue(const WfBuffers& b, int parity, int q) { return b.queue + (size_t(parity) * NQ + size_t(q)) * b.pool; }
+
+// Shading class of a hit: material kind x cost class of its (checker-resolved) leaf texture.
+// Returns Q_NONE when the path terminates right here (constant emitter): `value` is set.
+RT_DEV int classify_hit(const DScene& sc, const DRenderParams& rp, const RayQ& q, Hit h, int32_t& leaf, V3& value) {
+    uint32_t mat_ix = __ldg(&sc.sph_c[h.prim]).y;
+    float4 m0 = __ldg(reinterpret_cast<const float4*>(sc.mats + mat_ix));
+    uint32_t kind = __float_as_uint(m0.x);
+    leaf = -1;
+    if (kind == RT_MAT_METAL) return Q_METAL;
+    if (kind == RT_MAT_DIELECTRIC) return Q_DIEL;
+    int32_t tex = __float_as_int(m0.y);
+    DTexture t = load_tex(sc, tex);
+    leaf = tex;
+    if (t.kind == RT_TEX_CHECKER) { // the checker only needs p (texture.h:41-48)
+        V3 p = q.o + h.t * q.d;
+        leaf = resolve_texture(sc, tex, p, t);
+    }
+    if (kind == RT_MAT_EMITTER) {
+        if (t.kind == RT_TEX_CONSTANT) { // emitter::emit (material.h:50-52) + bloom (main.cu:49)
+            float intensity = __ldg(reinterpret_cast<const float4*>(sc.mats + mat_ix) + 1).y;
+            value = tex_constant(t) * intensity + mk(rp.bloom, rp.bloom, rp.bloom);
+            return Q_NONE;
+        }
+        return Q_EMIT;
+    }
+    switch (t.kind) {
+    case RT_TEX_CONSTANT: return Q_LAMB_CONST;
+    case RT_TEX_NOISE_PERLIN:
+    case RT_TEX_WOOD: return Q_LAMB_NOISE1;
+    case RT_TEX_NOISE_TURBULANCE:
+    case RT_TEX_NOISE_MARBLE: return Q_LAMB_NOISE6;
+    case RT_TEX_IMAGE: return Q_LAMB_IMAGE;
+    default: return Q_LAMB_CONST;
+    }
+}
+
+template <bool USE_BVH>
+__global__ void __launch_bounds__(WF_THREADS, 2)
+    k_wf_step(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
+              int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
+    extern __shared__ uint32_t smem[];
+    __shared__ uint32_t s_count[NQ];
+    __shared__ uint32_t s_base[NQ];
+    __shared__ unsigned long long s_path_base;
+
+    perlin_stage(smem, threadIdx.x, blockDim.x);
+    const PerlinTab pt{smem, threadIdx.x & 31u};
+    const uint32_t lane = threadIdx.x & 31u;
+
+    const uint32_t* cnt_cur = wb.counts + (it % 3) * NQ;
+    uint32_t* cnt_next = wb.counts + ((it + 1) % 3) * NQ;
+    if (blockIdx.x == 0 && threadIdx.x < NQ) wb.counts[((it + 2) % 3) * NQ + threadIdx.x] = 0; // next iteration's target
+    const int par_cur = it & 1, par_next = par_cur ^ 1;
+
+    uint32_t n_q[NQ], chunk_end[NQ];
+    uint32_t total_chunks = 0;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        // most expensive classes first so the long chunks start early
+        n_q[k] = __ldg(cnt_cur + k);
+    }
+    // chunk order: NOISE6, NOISE1, IMAGE, EMIT, DIEL, METAL, LAMB_CONST, NEW
+    const int order[NQ] = {Q_LAMB_NOISE6, Q_LAMB_NOISE1, Q_LAMB_IMAGE, Q_EMIT, Q_DIEL, Q_METAL, Q_LAMB_CONST, Q_NEW};
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        total_chunks += (n_q[order[k]] + WF_THREADS - 1) / WF_THREADS;
+        chunk_end[k] = total_chunks;
+    }
+
+    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
+    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+    const V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
+    unsigned long long nrays = 0;
+
+    for (uint32_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+        int kpos = 0;
+#pragma unroll
+        for (int k = 0; k < NQ - 1; ++k) kpos += (chunk >= chunk_end[k]) ? 1 : 0;
+        const int kind = order[kpos];
+        const uint32_t first = (chunk - (kpos ? chunk_end[kpos - 1] : 0u)) * WF_THREADS;
+        const uint32_t idx = first + threadIdx.x;
+        const bool valid = idx < n_q[kind];
+
+        __syncthreads(); // previous chunk's pushes are done with s_count/s_base; perlin table staged
+        if (threadIdx.x < NQ) s_count[threadIdx.x] = 0;
+        if (kind == Q_NEW && threadIdx.x == 0) {
+            uint32_t want = min(uint32_t(WF_THREADS), n_q[Q_NEW] - first);
+            s_path_base = atomicAdd(wb.next_path, (unsigned long long)want);
+        }
+        __syncthreads();
+
+        uint32_t slot = valid ? __ldg(wf_queue(wb, par_cur, kind) + idx) : 0u;
+        WfRecord* rec = wb.rec + slot;
+
+        bool has_ray = false;   // a ray to extend
+        bool finished = false;  // path ended: add `A` to the pixel
+        bool slot_free = false; // hand the slot to Q_NEW
+        Ray r;
+        V3 A = mk(0.f, 0.f, 0.f);
+        uint32_t pixel = 0, sample = 0, bounce = 0;
+
+        if (valid) {
+            if (kind == Q_NEW) {
+                unsigned long long path = s_path_base + threadIdx.x;
+                if (path < npaths) {
+                    pixel = uint32_t(path % npix);
+                    sample = uint32_t(path / npix) + uint32_t(rp.sample_offset);
+                    A = mk(rp.world_r, rp.world_g, rp.world_b);
+                    if (rp.max_depth > 0) {
+                        r = camera_ray(sc, rp, pixel, sample);
+                        has_ray = true;
+                    } else { // exceeded recursion before the first hit test (main.cu:42,70)
+                        A = mk(0.f, 0.f, 0.f);
+                        finished = true;
+                        slot_free = true;
+                    }
+                } // else: no paths left; the slot retires
+            } else {
+                const float4 ro = rec->o, rd = rec->d, ra = rec->a;
+                const uint4 ids = rec->ids;
+                pixel = ids.x;
+                sample = ids.y;
+                bounce = ids.z;
+                RayQ q;
+                q.o = mk(ro.x, ro.y, ro.z);
+                q.d = mk(rd.x, rd.y, rd.z);
+                q.time = ro.w;
+                q.a = 0.f; // not needed for shading
+                Hit h{rd.w, __float_as_uint(ra.w)};
+                A = mk(ra.x, ra.y, ra.z);
+                V3 p, n;
+                hit_surface(sc, q, h, p, n);
+                if (kind == Q_EMIT) { // emitter::emit (material.h:50-52): value = tex * intensity + bloom; A is dropped
+                    DTexture t = load_tex(sc, int32_t(ids.w));
+                    float intensity = __ldg(reinterpret_cast<const float4*>(sc.mats + __ldg(&sc.sph_c[h.prim]).y) + 1).y;
+                    A = texture_leaf_value(sc, pt, t, n, p) * intensity + bloom;
+                    finished = true;
+                    slot_free = true;
+                } else {
+                    const V3 E = mk(0.f, 0.f, 0.f) + bloom; // material::emit (material.h:14-16) + bloom
+                    const U4 rn = rng_block(rp.seed, pixel, sample, bounce, 0);
+                    V3 att;
+                    bool scattered = true;
+                    if (kind == Q_METAL) {
+                        DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
+                        att = mk(m.ax, m.ay, m.az);
+                        scattered = scatter_metal(q, p, n, m.param, rn, r);
+                    } else if (kind == Q_DIEL) {
+                        DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
+                        att = mk(m.ax, m.ay, m.az);
+                        scatter_dielectric(q, p, n, m.param, rn, r);
+                    } else {
+                        DTexture t = load_tex(sc, int32_t(ids.w));
+                        if (kind == Q_LAMB_CONST) att = tex_constant(t);
+                        else if (kind == Q_LAMB_NOISE1) att = t.kind == RT_TEX_WOOD ? tex_wood(pt, t, p) : tex_perlin(pt, t, p);
+                        else if (kind == Q_LAMB_NOISE6) att = t.kind == RT_TEX_NOISE_MARBLE ? tex_marble(pt, t, p) : tex_turbulence(pt, t, p);
+                        else att = tex_image(sc, t, n);
+                        scatter_lambertian(q, p, n, rn, r);
+                    }
+                    if (!scattered) { // absorbed (material.h:129-130): the path's value is E (main.cu:53-54)
+                        A = E;
+                        finished = true;
+                        slot_free = true;
+                    } else {
+                        A = E + att * A; // main.cu:51
+                        if (int(bounce) >= rp.max_depth) { // exceeded recursion (main.cu:70)
+                            A = mk(0.f, 0.f, 0.f);
+                            finished = true;
+                            slot_free = true;
+                        } else {
+                            has_ray = true;
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- extend: closest hit of the new ray, classification into the next queues ----
+        int out_q = Q_NONE;
+        if (has_ray) {
+            RayQ q = make_rayq(r);
+            Hit h = USE_BVH ? closest_hit_bvh(sc, q, rp.tmin) : closest_hit_list(sc, q, rp.tmin);
+            ++nrays;
+            ++bounce;
+            if (h.prim == RT_INVALID_ID) { // miss: the path's value is A (main.cu:66-67)
+                finished = true;
+                slot_free = true;
+            } else {
+                int32_t leaf;
+                V3 value;
+                out_q = classify_hit(sc, rp, q, h, leaf, value);
+                if (out_q == Q_NONE) { // constant emitter: terminate here
+                    A = value;
+                    finished = true;
+                    slot_free = true;
+                } else {
+                    rec->o = make_float4(r.o.x, r.o.y, r.o.z, r.time);
+                    rec->d = make_float4(r.d.x, r.d.y, r.d.z, h.t);
+                    rec->a = make_float4(A.x, A.y, A.z, __uint_as_float(h.prim));
+                    rec->ids = make_uint4(pixel, sample, bounce, uint32_t(leaf));
+                }
+            }
+        }
+        if (finished) atomicAdd(&accum[pixel], make_float4(A.x, A.y, A.z, 1.f));
+        if (slot_free) out_q = Q_NEW;
+
+        // ---- queue push: warp ballot -> shared counters -> one global atomic per queue ----
+        uint32_t local = 0;
+        {
+            const unsigned peers = __match_any_sync(0xffffffffu, out_q);
+            if (out_q != Q_NONE) {
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (int(lane) == leader) base = atomicAdd(&s_count[out_q], uint32_t(__popc(peers)));
+                base = __shfl_sync(peers, base, leader);
+                local = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < NQ) {
+            uint32_t c = s_count[threadIdx.x];
+            s_base[threadIdx.x] = c ? atomicAdd(cnt_next + threadIdx.x, c) : 0u;
+        }
+        __syncthreads();
+        if (out_q != Q_NONE) wf_queue(wb, par_next, out_q)[s_base[out_q] + local] = slot;
+    }
+
+    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
+    if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
+}
+
+// fills Q_NEW of iteration 0 with every slot and resets the path counter
+__global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_slots) wf_queue(wb, 0, Q_NEW)[i] = i;
+    if (i < 3 * NQ) wb.counts[i] = (i == Q_NEW) ? n_slots : 0u;
+    if (i == 0) *wb.next_path = 0ull;
+}
+
+WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st) {
+    WavefrontState* ws = new WavefrontState();
+    ws->stream = st;
+    ws->b.pool = uint32_t(pool_paths);
+    bool ok = cudaMalloc(&ws->b.rec, pool_paths * sizeof(WfRecord)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ws->b.queue, size_t(2) * NQ * pool_paths * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ws->b.counts, 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ws->b.next_path, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ws->h_status, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ws->h_counts, 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
+    if (!ok) {
+        wavefront_destroy(ws);
+        return nullptr;
+    }
+    return ws;
+}
+
+void wavefront_destroy(WavefrontState* ws) {
+    if (!ws) return;
+    if (ws->b.rec) cudaFree(ws->b.rec);
+    if (ws->b.queue) cudaFree(ws->b.queue);
+    if (ws->b.counts) cudaFree(ws->b.counts);
+    if (ws->b.next_path) cudaFree(ws->b.next_path);
+    if (ws->h_status) cudaFreeHost(ws->h_status);
+    if (ws->h_counts) cudaFreeHost(ws->h_counts);
+    delete ws;
+}
+
+size_t wavefront_pool(const WavefrontState* ws) { return ws ? ws->b.pool : 0; }
+
+void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
+                      unsigned long long* ray_counter, int sm_count, cudaStream_t st, uint32_t* launches,
+                      uint32_t* iterations) {
+    const unsigned long long npaths = (unsigned long long)rp.width * rp.height * (unsigned long long)rp.spp;
+    *launches = 0;
+    *iterations = 0;
+    if (npaths == 0) return;
+    static bool attr_set = false;
+    const size_t smem = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_wf_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaFuncSetAttribute(k_wf_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        attr_set = true;
+    }
+    // slots in use: never more than there are paths
+    WfBuffers wb = ws->b;
+    const uint32_t slots = uint32_t(npaths < wb.pool ? npaths : wb.pool);
+    k_wf_init<<<(slots + 255) / 256 > 0 ? (slots + 255) / 256 : 1, 256, 0, st>>>(wb, slots);
+    ++*launches;
+
+    const unsigned grid_cap = unsigned(sm_count) * 8u;
+    const unsigned grid_need = (slots + WF_THREADS - 1) / WF_THREADS + NQ;
+    const unsigned grid = grid_need < grid_cap ? grid_need : grid_cap;
+
+    uint32_t it = 0;
+    // Iterations are enqueued in batches; between batches the host reads back the queue
+    // sizes and the path counter (two small async copies) to decide whether to go on.
+    uint32_t batch = uint32_t((npaths + slots - 1) / slots) + 2; // at least this many are needed
+    const uint32_t max_iters = 4u * (uint32_t(rp.max_depth) + 2u) + 64u * uint32_t((npaths + slots - 1) / slots);
+    while (true) {
+        for (uint32_t k = 0; k < batch; ++k, ++it) {
+            if (use_bvh)
+                k_wf_step<true><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
+            else
+                k_wf_step<false><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
+            ++*launches;
+        }
+        cudaMemcpyAsync(ws->h_counts, wb.counts, 3 * NQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(ws->h_status, wb.next_path, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        const uint32_t* c = ws->h_counts + (it % 3) * NQ; // queues the NEXT iteration would read
+        uint64_t live = 0;
+        for (int k = 0; k < NQ; ++k)
+            if (k != Q_NEW) live += c[k];
+        const unsigned long long started = *ws->h_status;
+        if (live == 0 && (started >= npaths || c[Q_NEW] == 0)) break;
+        if (it >= max_iters) break; // safety net; cannot trigger for max_depth-bounded paths
+        if (started < npaths) {
+            // paths started per iteration so far -> iterations still needed to start the rest
+            double per_it = double(started) / double(it ? it : 1);
+            double need = per_it > 0 ? double(npaths - started) / per_it : 8.0;
+            batch = uint32_t(need < 4.0 ? 4.0 : (need > 256.0 ? 256.0 : need)) + 1;
+        } else {
+            batch = 6; // tail: at most max_depth more
+        }
+    }
+    *iterations = it;
+}
+
+} // namespace rtd
