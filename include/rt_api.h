@@ -204,6 +204,9 @@ typedef struct rt_scene rt_scene;
 /* ---- entry points -------------------------------------------------------- */
 
 int rt_api_version(void);
+/* sizeof() of a structure of this header by name ("rt_sphere", ...), 0 if unknown: lets a
+ * foreign-language binding verify its layout before passing memory across the boundary. */
+size_t rt_abi_sizeof(const char* struct_name);
 const char* rt_last_error(void);
 void rt_default_render_params(rt_render_params* p); /* reference constants, 1200x600x100 */
 

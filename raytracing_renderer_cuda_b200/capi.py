@@ -1,0 +1,338 @@
+"""ctypes binding of include/rt_api.h (librt_b200.so).
+
+Test / bench orchestration only: the product is the shared library and the C++
+facade in include/rt/.  Every structure below mirrors the C declaration of the
+same name field by field; `check_layout()` compares sizes with the library's
+own `rt_abi_sizeof` so a drifted binding fails loudly instead of corrupting memory.
+
+There is no fallback: if the library is missing, or no sm_100 device is usable,
+the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "librt_b200.so"
+
+RT_INVALID_ID = 0xFFFFFFFF
+RT_OK = 0
+STATUS_NAMES = {0: "RT_OK", 1: "RT_ERR_INVALID_ARG", 2: "RT_ERR_CUDA", 3: "RT_ERR_OOM", 4: "RT_ERR_UNSUPPORTED",
+                5: "RT_ERR_NO_DEVICE", 6: "RT_ERR_IO"}
+
+RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_EMITTER = 0, 1, 2, 3
+(RT_TEX_CONSTANT, RT_TEX_CHECKER, RT_TEX_NOISE_PERLIN, RT_TEX_NOISE_TURBULANCE, RT_TEX_NOISE_MARBLE, RT_TEX_WOOD,
+ RT_TEX_IMAGE) = range(7)
+RT_BVH_AUTO, RT_BVH_NONE, RT_BVH_HOST_SAH, RT_BVH_GPU_LBVH = 0, 1, 2, 3
+RT_PIPE_AUTO, RT_PIPE_WAVEFRONT, RT_PIPE_MEGAKERNEL = 0, 1, 2
+RT_SPHERE_MOVING, RT_SPHERE_INSIDE = 1, 2
+
+
+class RtError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {msg}")
+        self.status = status
+
+
+class rt_sphere(C.Structure):
+    _fields_ = [("center0", C.c_float * 3), ("radius", C.c_float), ("center1", C.c_float * 3), ("time0", C.c_float),
+                ("time1", C.c_float), ("material", C.c_uint32), ("id", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class rt_material(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("texture", C.c_int32), ("albedo", C.c_float * 3), ("param", C.c_float)]
+
+
+class rt_texture(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("even", C.c_int32), ("odd", C.c_int32), ("image", C.c_int32),
+                ("color1", C.c_float * 3), ("color2", C.c_float * 3), ("density", C.c_float), ("hardness", C.c_float)]
+
+
+class rt_image(C.Structure):
+    _fields_ = [("rgb", C.POINTER(C.c_float)), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class rt_camera(C.Structure):
+    _fields_ = [("lookfrom", C.c_float * 3), ("lookat", C.c_float * 3), ("up", C.c_float * 3), ("vfov", C.c_float),
+                ("aspect", C.c_float), ("aperture", C.c_float), ("focus_dist", C.c_float), ("time0", C.c_float),
+                ("time1", C.c_float)]
+
+
+class rt_scene_desc(C.Structure):
+    _fields_ = [("spheres", C.POINTER(rt_sphere)), ("n_spheres", C.c_uint32),
+                ("materials", C.POINTER(rt_material)), ("n_materials", C.c_uint32),
+                ("textures", C.POINTER(rt_texture)), ("n_textures", C.c_uint32),
+                ("images", C.POINTER(rt_image)), ("n_images", C.c_uint32),
+                ("camera", rt_camera), ("bvh_mode", C.c_uint32)]
+
+
+class rt_render_params(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("sample_offset", C.c_int32),
+                ("max_depth", C.c_int32), ("seed", C.c_uint32), ("tmin", C.c_float), ("world", C.c_float * 3),
+                ("bloom", C.c_float), ("pipeline", C.c_uint32)]
+
+
+class rt_stats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("ms_total", C.c_float), ("ms_tonemap", C.c_float),
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("launches", C.c_uint32), ("iterations", C.c_uint32)]
+
+
+class rt_scene_info(C.Structure):
+    _fields_ = [("n_spheres", C.c_uint32), ("n_nodes", C.c_uint32), ("bvh_mode", C.c_uint32), ("bvh_depth", C.c_uint32),
+                ("ms_build", C.c_float), ("ms_upload", C.c_float), ("sah_cost", C.c_float),
+                ("device_bytes", C.c_uint64)]
+
+
+class rt_ray(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("direction", C.c_float * 3), ("time", C.c_float)]
+
+
+class rt_hit(C.Structure):
+    _fields_ = [("t", C.c_float), ("id", C.c_uint32), ("p", C.c_float * 3), ("n", C.c_float * 3), ("u", C.c_float),
+                ("v", C.c_float)]
+
+
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("time", "<f4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("id", "<u4"), ("p", "<f4", 3), ("n", "<f4", 3), ("u", "<f4"), ("v", "<f4")])
+assert RAY_DTYPE.itemsize == C.sizeof(rt_ray) and HIT_DTYPE.itemsize == C.sizeof(rt_hit)
+
+# every symbol include/rt_api.h declares: name -> (restype, argtypes)
+_VP = C.c_void_p
+_SIGNATURES = {
+    "rt_api_version": (C.c_int, []),
+    "rt_abi_sizeof": (C.c_size_t, [C.c_char_p]),
+    "rt_last_error": (C.c_char_p, []),
+    "rt_default_render_params": (None, [C.POINTER(rt_render_params)]),
+    "rt_context_create": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "rt_context_destroy": (None, [_VP]),
+    "rt_context_set_stream": (C.c_int, [_VP, _VP]),
+    "rt_context_synchronize": (C.c_int, [_VP]),
+    "rt_scene_create": (C.c_int, [_VP, C.POINTER(rt_scene_desc), C.POINTER(_VP)]),
+    "rt_scene_destroy": (None, [_VP]),
+    "rt_scene_get_info": (C.c_int, [_VP, C.POINTER(rt_scene_info)]),
+    "rt_trace_primary": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_float, C.c_int, _VP]),
+    "rt_render": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
+    "rt_render_accum": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
+    "rt_render_accum_device": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
+    "rt_tonemap_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
+    "rt_quantize_rgb8": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP]),
+    "rt_write_ppm": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _VP]),
+    "rt_read_ppm_f32": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
+                                  C.POINTER(C.c_int32)]),
+    "rt_free": (None, [_VP]),
+    "rt_builtin_scene": (C.c_int, [C.c_char_p, _VP, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32,
+                                   C.POINTER(C.POINTER(rt_scene_desc))]),
+    "rt_scene_desc_free": (None, [C.POINTER(rt_scene_desc)]),
+    "rt_scene_desc_save": (C.c_int, [C.POINTER(rt_scene_desc), C.c_char_p]),
+    "rt_scene_desc_load": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(rt_scene_desc))]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load_library(path: os.PathLike | None = None) -> C.CDLL:
+    """dlopen librt_b200.so (built in-tree by `make lib` / __graft_entry__.build()).  No fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise FileNotFoundError(f"{p} not found: build it with `make lib` (there is no CPU fallback)")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    check_layout(lib)
+    return lib
+
+
+def check_layout(lib: C.CDLL) -> None:
+    for cls in (rt_sphere, rt_material, rt_texture, rt_image, rt_camera, rt_scene_desc, rt_render_params, rt_stats,
+                rt_scene_info, rt_ray, rt_hit):
+        want = lib.rt_abi_sizeof(cls.__name__.encode())
+        if want != C.sizeof(cls):
+            raise RuntimeError(f"ABI drift: sizeof({cls.__name__}) is {want} in the library, {C.sizeof(cls)} here")
+
+
+def _check(lib: C.CDLL, status: int) -> None:
+    if status != RT_OK:
+        raise RtError(status, (lib.rt_last_error() or b"").decode(errors="replace"))
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class SceneDesc:
+    """Owns (or borrows) a rt_scene_desc.  Built-in scenes come from the C++ facade via rt_builtin_scene."""
+
+    def __init__(self, ptr, lib, keepalive=None):
+        self._ptr = ptr
+        self._lib = lib
+        self._keep = keepalive
+
+    @classmethod
+    def builtin(cls, name: str, image: np.ndarray | None = None, n: int = 0, bvh_mode: int = RT_BVH_AUTO) -> "SceneDesc":
+        lib = load_library()
+        out = C.POINTER(rt_scene_desc)()
+        if image is not None:
+            image = _f32(image)
+            h, w = image.shape[:2]
+            st = lib.rt_builtin_scene(name.encode(), image.ctypes.data, w, h, n, bvh_mode, C.byref(out))
+        else:
+            st = lib.rt_builtin_scene(name.encode(), None, 0, 0, n, bvh_mode, C.byref(out))
+        _check(lib, st)
+        return cls(out, lib)
+
+    @classmethod
+    def load(cls, path: str) -> "SceneDesc":
+        lib = load_library()
+        out = C.POINTER(rt_scene_desc)()
+        _check(lib, lib.rt_scene_desc_load(str(path).encode(), C.byref(out)))
+        return cls(out, lib)
+
+    def save(self, path: str) -> None:
+        _check(self._lib, self._lib.rt_scene_desc_save(self._ptr, str(path).encode()))
+
+    @property
+    def desc(self) -> rt_scene_desc:
+        return self._ptr.contents
+
+    def set_bvh_mode(self, mode: int) -> None:
+        self._ptr.contents.bvh_mode = mode
+
+    def spheres(self) -> np.ndarray:
+        d = self.desc
+        return np.ctypeslib.as_array(C.cast(d.spheres, C.POINTER(C.c_uint8)), (d.n_spheres * C.sizeof(rt_sphere),)).view(
+            SPHERE_DTYPE).copy() if d.n_spheres else np.zeros(0, SPHERE_DTYPE)
+
+    def __del__(self):
+        if getattr(self, "_ptr", None) and self._keep is None:
+            try:
+                self._lib.rt_scene_desc_free(self._ptr)
+            except Exception:
+                pass
+            self._ptr = None
+
+
+SPHERE_DTYPE = np.dtype([("center0", "<f4", 3), ("radius", "<f4"), ("center1", "<f4", 3), ("time0", "<f4"),
+                         ("time1", "<f4"), ("material", "<u4"), ("id", "<u4"), ("flags", "<u4")])
+assert SPHERE_DTYPE.itemsize == C.sizeof(rt_sphere)
+
+
+def default_params(**kw) -> rt_render_params:
+    lib = load_library()
+    p = rt_render_params()
+    lib.rt_default_render_params(C.byref(p))
+    for k, v in kw.items():
+        if k == "world":
+            p.world[:] = v
+        else:
+            setattr(p, k, v)
+    return p
+
+
+class Context:
+    """One CUDA device + one stream (one process per GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self._h = _VP()
+        _check(self.lib, self.lib.rt_context_create(device, C.byref(self._h)))
+        self.device = device
+
+    def set_stream(self, cuda_stream: int) -> None:
+        _check(self.lib, self.lib.rt_context_set_stream(self._h, _VP(cuda_stream)))
+
+    def synchronize(self) -> None:
+        _check(self.lib, self.lib.rt_context_synchronize(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.rt_context_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scene:
+    def __init__(self, ctx: Context, desc: SceneDesc):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self._h = _VP()
+        _check(self.lib, self.lib.rt_scene_create(ctx._h, desc._ptr, C.byref(self._h)))
+
+    def info(self) -> rt_scene_info:
+        i = rt_scene_info()
+        _check(self.lib, self.lib.rt_scene_get_info(self._h, C.byref(i)))
+        return i
+
+    def trace_primary(self, rays: np.ndarray, tmin: float = 1e-5, use_bvh: bool = True) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        _check(self.lib, self.lib.rt_trace_primary(self.ctx._h, self._h, rays.ctypes.data, rays.shape[0], tmin,
+                                                   int(use_bvh), hits.ctypes.data))
+        return hits
+
+    def render(self, params: rt_render_params, out: np.ndarray | None = None):
+        """rt_render: HOST float RGB [H, W, 3], reference framebuffer layout (row 0 = bottom)."""
+        if out is None:
+            out = np.empty((params.height, params.width, 3), dtype=np.float32)
+        st = rt_stats()
+        _check(self.lib, self.lib.rt_render(self.ctx._h, self._h, C.byref(params), out.ctypes.data, C.byref(st)))
+        return out, st
+
+    def render_accum(self, params: rt_render_params):
+        out = np.empty((params.height, params.width, 4), dtype=np.float32)
+        st = rt_stats()
+        _check(self.lib, self.lib.rt_render_accum(self.ctx._h, self._h, C.byref(params), out.ctypes.data, C.byref(st)))
+        return out, st
+
+    def render_accum_device(self, params: rt_render_params, accum_ptr: int, want_stats: bool = False):
+        st = rt_stats() if want_stats else None
+        _check(self.lib, self.lib.rt_render_accum_device(self.ctx._h, self._h, C.byref(params), _VP(accum_ptr),
+                                                         C.byref(st) if st is not None else None))
+        return st
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.rt_scene_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def tonemap_device(ctx: Context, accum_ptr: int, width: int, height: int, out_rgb_ptr: int = 0, out_rgb8_ptr: int = 0):
+    _check(ctx.lib, ctx.lib.rt_tonemap_device(ctx._h, _VP(accum_ptr), width, height, _VP(out_rgb_ptr or None),
+                                              _VP(out_rgb8_ptr or None)))
+
+
+def quantize_rgb8(rgb: np.ndarray) -> np.ndarray:
+    """main.cu:475-488 on the host: Y flip + int(255.999f*c) & 255."""
+    lib = load_library()
+    rgb = _f32(rgb)
+    h, w = rgb.shape[:2]
+    out = np.empty((h, w, 3), dtype=np.uint8)
+    _check(lib, lib.rt_quantize_rgb8(rgb.ctypes.data, w, h, out.ctypes.data))
+    return out
+
+
+def psnr(a: np.ndarray, b: np.ndarray, peak: float = 1.0) -> float:
+    mse = float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
+    return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
