@@ -1,0 +1,208 @@
+"""Parity of the CUDA path (through the C-ABI of librt_b200.so) with the oracle and with golden outputs
+of the reference's own CUDA kernels.  Bars (BASELINE.json north_star): closest-hit object id bit-exact,
+t within 1e-5 relative (asserted bit-exact here), BVH == brute force, converged 4096-spp images
+PSNR >= 40 dB against the reference render."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import raytracing_renderer_cuda_b200 as rt
+from raytracing_renderer_cuda_b200 import capi
+from tests.conftest import ROOT, SCENES
+from tests.oracle_api import camera_rays, secondary_rays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return rt.Context(0)
+
+
+@pytest.fixture(scope="module")
+def gpu_golden():
+    return np.load(ROOT / "tests" / "golden" / "ref_gpu_golden.npz")
+
+
+def _scene(ctx, desc, mode):
+    desc.set_bvh_mode(mode)
+    try:
+        return rt.Scene(ctx, desc)
+    finally:
+        desc.set_bvh_mode(capi.RT_BVH_AUTO)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_trace_matches_reference_gpu_golden(ctx, cpu_golden, gpu_golden, scene_descs, name):
+    rays = np.ascontiguousarray(cpu_golden[f"{name}_rays"]).view(capi.RAY_DTYPE).reshape(-1)
+    want = gpu_golden[f"{name}_hits_bvh1"]
+    for mode in (capi.RT_BVH_NONE, capi.RT_BVH_HOST_SAH, capi.RT_BVH_GPU_LBVH):
+        sc = _scene(ctx, scene_descs[name], mode)
+        got = sc.trace_primary(rays, use_bvh=mode != capi.RT_BVH_NONE)
+        assert np.array_equal(got["id"], want["id"]), mode
+        assert np.array_equal(got["t"], want["t"]), mode
+        assert np.array_equal(got["p"], want["p"]) and np.array_equal(got["n"], want["n"]), mode
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_trace_matches_oracle_on_seeded_rays(ctx, oracle, scene_descs, name):
+    d = scene_descs[name]
+    rays = camera_rays(d, 200_000, seed=21)
+    want = oracle.scene(d).trace(rays, arith=1)
+    sec = secondary_rays(d, want, seed=22)
+    want2 = oracle.scene(d).trace(sec, arith=1)
+    for mode in (capi.RT_BVH_NONE, capi.RT_BVH_HOST_SAH, capi.RT_BVH_GPU_LBVH):
+        sc = _scene(ctx, d, mode)
+        for r, w in ((rays, want), (sec, want2)):
+            got = sc.trace_primary(r, use_bvh=mode != capi.RT_BVH_NONE)
+            assert np.array_equal(got["id"], w["id"]), mode          # bit-exact ids
+            hit = w["id"] != capi.RT_INVALID_ID
+            rel = np.abs(got["t"][hit] - w["t"][hit]) / np.abs(w["t"][hit])
+            assert rel.max() <= 1e-5                                   # the stated tolerance ...
+            assert np.array_equal(got["t"], w["t"])                    # ... and in fact bit-exact
+            assert np.array_equal(got["p"], w["p"]) and np.array_equal(got["n"], w["n"])
+            du = np.abs(got["u"][hit] - w["u"][hit])
+            spheres = d.spheres()
+            static = ~np.isin(w["id"][hit], spheres["id"][(spheres["flags"] & capi.RT_SPHERE_MOVING) != 0])
+            du = np.minimum(du, 1 - du)
+            assert du[static].max() < 2e-6 and np.abs(got["v"][hit] - w["v"][hit])[static].max() < 2e-6
+
+
+def test_bvh_equals_brute_force_on_many_spheres(ctx):
+    """BVH == all-spheres test on a scene far larger than the oracle can brute-force in seconds:
+    20 000 random spheres, 5 % moving; both BVH builders against the GPU's own linear list."""
+    d = rt.SceneDesc.builtin("random_spheres", n=20_000)
+    rays = camera_rays(d, 100_000, seed=31)
+    lst = _scene(ctx, d, capi.RT_BVH_NONE).trace_primary(rays, use_bvh=False)
+    assert (lst["id"] != capi.RT_INVALID_ID).mean() > 0.9
+    sec = secondary_rays(d, lst, seed=32)
+    lst2 = _scene(ctx, d, capi.RT_BVH_NONE).trace_primary(sec, use_bvh=False)
+    for mode in (capi.RT_BVH_HOST_SAH, capi.RT_BVH_GPU_LBVH):
+        sc = _scene(ctx, d, mode)
+        assert sc.info().bvh_mode == mode and sc.info().n_nodes == 20_000
+        for r, w in ((rays, lst), (sec, lst2)):
+            got = sc.trace_primary(r, use_bvh=True)
+            assert got.tobytes() == w.tobytes(), mode
+
+
+@pytest.mark.parametrize("name,size", [("earth_emitter", (96, 48, 16)), ("book1_final", (64, 36, 8)), ("perlin_motion", (80, 40, 8))])
+@pytest.mark.parametrize("pipe", [capi.RT_PIPE_WAVEFRONT, capi.RT_PIPE_MEGAKERNEL])
+def test_render_matches_oracle_same_random_numbers(ctx, oracle, scene_descs, name, size, pipe):
+    """Same Philox keys, same direct samplers: CUDA and the oracle follow the same paths, so per-pixel sums
+    agree up to SFU approximations (__sinf/__powf/sincos/cbrt) and accumulation order.  A handful of
+    pixels may diverge where an approximation flips a hit/miss or a reflect/refract decision."""
+    w, h, spp = size
+    d = scene_descs[name]
+    p = rt.default_params(width=w, height=h, spp=spp, pipeline=pipe)
+    got, st = rt.Scene(ctx, d).render_accum(p)
+    want, nrays = oracle.scene(d).render(p, sampler=1, arith=1)
+    assert st.paths == w * h * spp
+    assert np.array_equal(got[..., 3], np.full((h, w), spp, np.float32))
+    assert abs(int(st.rays) - int(nrays)) <= max(8, nrays // 2000)
+    diff = np.abs(got[..., :3] - want[..., :3]).max(axis=2) / spp
+    assert np.median(diff) < 1e-5
+    assert (diff > 1e-3).mean() < 0.01, float((diff > 1e-3).mean())
+    assert rt.psnr(oracle.tonemap(got), oracle.tonemap(want)) > 45.0
+
+
+@pytest.mark.parametrize("name,size", [("earth_emitter", (400, 200, 4096)), ("book1_final", (320, 180, 4096)),
+                                       ("perlin_motion", (300, 150, 4096))])
+def test_converged_render_psnr_vs_reference_kernel(ctx, gpu_golden, scene_descs, name, size):
+    w, h, spp = size
+    ref_fb = gpu_golden[f"{name}_fb_{w}x{h}x{spp}"]
+    img, st = rt.Scene(ctx, scene_descs[name]).render(rt.default_params(width=w, height=h, spp=spp))
+    psnr = rt.psnr(img, ref_fb)
+    assert psnr >= 40.0, psnr  # north_star: PSNR >= 40 dB at 4096 spp against the reference's render
+
+
+def test_wavefront_equals_megakernel_and_is_schedule_independent(ctx, scene_descs, monkeypatch):
+    d = scene_descs["perlin_motion"]
+    sc = rt.Scene(ctx, d)
+    p = rt.default_params(width=160, height=80, spp=8, pipeline=capi.RT_PIPE_WAVEFRONT)
+    a, sa = sc.render_accum(p)
+    p2 = rt.default_params(width=160, height=80, spp=8, pipeline=capi.RT_PIPE_MEGAKERNEL)
+    b, sb = sc.render_accum(p2)
+    assert sa.rays == sb.rays  # identical paths: the RNG is keyed on (pixel, sample, bounce), not on the schedule
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-5)  # float atomics commute only up to rounding
+
+
+def test_sample_sharding_is_additive(ctx, scene_descs):
+    """Multi-GPU contract: ranks render disjoint sample ranges (sample_offset) and the float4 accumulators are
+    summed.  Two half renders must equal the full render."""
+    sc = rt.Scene(ctx, scene_descs["earth_emitter"])
+    full, sf = sc.render_accum(rt.default_params(width=120, height=60, spp=16))
+    a, s0 = sc.render_accum(rt.default_params(width=120, height=60, spp=8, sample_offset=0))
+    b, s1 = sc.render_accum(rt.default_params(width=120, height=60, spp=8, sample_offset=8))
+    assert s0.rays + s1.rays == sf.rays
+    assert np.allclose(a + b, full, rtol=1e-5, atol=1e-5)
+
+
+def test_tonemap_and_writer_conversion_bit_exact(ctx, oracle, scene_descs):
+    import torch
+
+    sc = rt.Scene(ctx, scene_descs["earth_emitter"])
+    w, h = 64, 32
+    acc, _ = sc.render_accum(rt.default_params(width=w, height=h, spp=4))
+    acc[0, 0, :3] = 1e9   # saturates
+    acc[0, 1, :3] = -1.0  # clamps to 0
+    dev = torch.from_numpy(acc).cuda()
+    rgb = torch.empty((h, w, 3), dtype=torch.float32, device="cuda")
+    rgb8 = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+    rt.tonemap_device(ctx, dev.data_ptr(), w, h, rgb.data_ptr(), rgb8.data_ptr())
+    ctx.synchronize()
+    want = oracle.tonemap(acc)  # main.cu:124-127 with truncating arithmetic
+    assert np.array_equal(rgb.cpu().numpy(), want)
+    assert np.array_equal(rgb8.cpu().numpy(), rt.quantize_rgb8(want))  # main.cu:475-488
+
+
+def test_edge_cases(ctx, scene_descs):
+    # empty scene: every ray misses, every pixel is the world colour (main.cu:66-67)
+    S, M, T = capi.rt_sphere * 1, capi.rt_material * 1, capi.rt_texture * 1
+    desc = capi.rt_scene_desc()
+    desc.camera = scene_descs["book1_final"].desc.camera
+    holder = capi.SceneDesc(C.pointer(desc), capi.load_library(), keepalive=True)
+    sc = rt.Scene(ctx, holder)
+    acc, st = sc.render_accum(rt.default_params(width=33, height=17, spp=3))
+    assert st.rays == 33 * 17 * 3
+    assert np.allclose(acc, np.array([3.0, 2.4, 2.1, 3.0], np.float32), rtol=1e-6)
+    hits = sc.trace_primary(camera_rays(holder, 100))
+    assert (hits["id"] == capi.RT_INVALID_ID).all() and (hits["t"] == np.float32(3.4028234663852886e38)).all()
+    # spp = 0 and max_depth = 0 (color() returns black after exceeding the recursion, main.cu:70)
+    sc1 = rt.Scene(ctx, scene_descs["earth_emitter"])
+    acc, st = sc1.render_accum(rt.default_params(width=16, height=8, spp=0))
+    assert st.paths == 0 and not acc.any()
+    acc, st = sc1.render_accum(rt.default_params(width=16, height=8, spp=2, max_depth=0))
+    assert st.rays == 0 and not acc[..., :3].any() and (acc[..., 3] == 2).all()
+    # one-sphere scene with a BVH request, ragged image size
+    one = capi.rt_scene_desc()
+    sph = S(capi.rt_sphere((0, 0, -1), 0.5, (0, 0, -1), 0, 1, 0, 7, 0))
+    mat = M(capi.rt_material(capi.RT_MAT_LAMBERTIAN, 0, (0, 0, 0), 0))
+    tex = T(capi.rt_texture(capi.RT_TEX_CONSTANT, -1, -1, -1, (.5, .5, .5), (0, 0, 0), 0, 0))
+    one.spheres, one.n_spheres, one.materials, one.n_materials, one.textures, one.n_textures = sph, 1, mat, 1, tex, 1
+    one.camera = capi.rt_camera((0, 0, 1), (0, 0, -1), (0, 1, 0), 40, 1.5, 0, 2, 0, 0)
+    one.bvh_mode = capi.RT_BVH_HOST_SAH
+    h1 = capi.SceneDesc(C.pointer(one), capi.load_library(), keepalive=(sph, mat, tex))
+    sc2 = rt.Scene(ctx, h1)
+    r = np.zeros(2, capi.RAY_DTYPE)
+    r["origin"] = (0, 0, 1)
+    r["direction"] = [(0, 0, -1), (0, 1, 0)]
+    hh = sc2.trace_primary(r, use_bvh=True)
+    assert hh["id"][0] == 7 and hh["t"][0] == np.float32(1.5) and hh["id"][1] == capi.RT_INVALID_ID
+    img, st = sc2.render(rt.default_params(width=37, height=23, spp=5))
+    assert np.isfinite(img).all() and st.paths == 37 * 23 * 5
+
+
+def test_errors_are_statuses_not_exits(ctx, scene_descs):
+    lib = capi.load_library()
+    sc = rt.Scene(ctx, scene_descs["earth_emitter"])
+    p = rt.default_params(width=0, height=8)
+    with pytest.raises(capi.RtError) as e:
+        sc.render_accum(p)
+    assert e.value.status == 1 and b"width" in lib.rt_last_error()
+    bad = capi.rt_scene_desc()
+    bad.n_spheres = 3  # spheres == NULL
+    with pytest.raises(capi.RtError):
+        rt.Scene(ctx, capi.SceneDesc(C.pointer(bad), lib, keepalive=True))
+    out = C.c_void_p()
+    assert lib.rt_context_create(99, C.byref(out)) == 1  # device out of range

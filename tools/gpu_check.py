@@ -17,8 +17,10 @@ import raytracing_renderer_cuda_b200 as rt  # noqa: E402
 from raytracing_renderer_cuda_b200 import capi  # noqa: E402
 from raytracing_renderer_cuda_b200.assets import load_earth  # noqa: E402
 
-OUT = ROOT / "gpurun_out"
-OUT.mkdir(exist_ok=True)
+import tempfile
+RES = ROOT / "gpurun_out"
+RES.mkdir(exist_ok=True)
+OUT = Path(tempfile.mkdtemp(prefix="rtcheck"))  # scratch: gpurun_out/ is size-capped
 REF = ROOT / "oracle" / "_ref"
 res = {}
 
@@ -150,5 +152,5 @@ r2 = ref_trace(c2_path, rays2, use_bvh=1)
 res["c2_trace_vs_ref_bvh"] = compare_hits(m_bvh, r2)
 print(res["c2_bvh_vs_list_mine"], res["c2_trace_vs_ref_bvh"], flush=True)
 
-json.dump(res, open(OUT / "gpu_check.json", "w"), indent=1)
+json.dump(res, open(RES / "gpu_check.json", "w"), indent=1)
 print(json.dumps(res))
