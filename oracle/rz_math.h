@@ -14,6 +14,17 @@
 
 namespace rz {
 
+#ifdef ORACLE_RZ_AS_RN
+// Timing build only (oracle/_ref/libref_cpu_rn.so, bench.py's host-core baseline): the rounding-mode
+// switches of the exact emulation cost more than the arithmetic, which would flatter the GPU.  Here the
+// _rz intrinsics round to nearest — SURVEY.md Appendix B's shim — so the CPU runs at its natural speed.
+static inline float add(float a, float b) { return a + b; }
+static inline float sub(float a, float b) { return a - b; }
+static inline float mul(float a, float b) { return a * b; }
+static inline float div(float a, float b) { return a / b; }
+static inline float sqrt(float a) { return ::sqrtf(a); }
+static inline float fma(float a, float b, float c) { return float(double(a) * double(b) + double(c)); }
+#else
 #define RZ_BINOP(name, insn)                                                                  \
     static inline float name(float a, float b) {                                               \
         uint32_t saved, mode;                                                                  \
@@ -52,6 +63,8 @@ static inline float fma(float a, float b, float c) {
                      : "x"(s), "m"(mode), "m"(saved));
     return r;
 }
+
+#endif // ORACLE_RZ_AS_RN
 
 // __saturatef: clamp to [0, 1], NaN -> 0
 static inline float saturate(float x) { return x > 0.f ? (x < 1.f ? x : 1.f) : 0.f; }

@@ -385,7 +385,8 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
         memcpy(&dt_bits, &dt, 4);
         hc[k] = make_uint4(dt_bits, sp.material, sp.id, order[k]);
         const bool moving = (sp.flags & RT_SPHERE_MOVING) != 0;
-        boxes[k] = rth::sphere_box(sp.center0, moving ? sp.center1 : sp.center0, sp.radius);
+        if (desc->bvh_mode != RT_BVH_GPU_LBVH && desc->bvh_mode != RT_BVH_NONE)
+            boxes[k] = rth::sphere_box(sp.center0, moving ? sp.center1 : sp.center0, sp.radius);
     }
 
     // ---- acceleration structure ----
@@ -422,15 +423,15 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     } else if (mode == RT_BVH_GPU_LBVH) {
         n_nodes = n - 1;
         if ((st = dev_alloc(s, &dnodes, n_nodes)) != RT_OK) return st;
-        rth::Box* dboxes = nullptr;
-        CUDA_TRY(cudaMalloc(&dboxes, n * sizeof(rth::Box)));
-        cudaError_t e = cudaMemcpyAsync(dboxes, boxes.data(), n * sizeof(rth::Box), cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = rtd::lbvh_build(reinterpret_cast<const float*>(dboxes), n, dnodes, stream, &lbvh_ms, &bstats.depth);
-        cudaFree(dboxes);
+        cudaError_t e = rtd::lbvh_build(da, db, n, n_static, dnodes, stream, &lbvh_ms, &bstats.depth);
         if (e != cudaSuccess) {
             set_error("GPU LBVH build failed: %s", cudaGetErrorString(e));
             return RT_ERR_CUDA;
         }
+    }
+    if (bstats.depth > RT_BVH_STACK_DEPTH) {
+        set_error("BVH depth %u exceeds the traversal stack (%d)", bstats.depth, RT_BVH_STACK_DEPTH);
+        return RT_ERR_UNSUPPORTED;
     }
 
     std::vector<rtd::DMaterial> hm(desc->n_materials);

@@ -78,6 +78,7 @@ struct BvhNode {
 };
 
 #define RT_MAX_IMAGES 8
+#define RT_BVH_STACK_DEPTH 64 // per-thread traversal stack entries (rt_intersect.cuh)
 
 struct DScene {
     // primitives, static spheres first: [0, n_static) static, [n_static, n) moving

@@ -126,7 +126,7 @@ RT_DEV bool slab(float4 lo, float4 hi, const V3& o, const V3& inv, float tmin, f
     return tn <= tf * 1.0000003f;
 }
 
-#define RT_BVH_STACK 64
+#define RT_BVH_STACK RT_BVH_STACK_DEPTH
 
 // Flattened-BVH closest hit: short per-thread stack, both child boxes fetched with four
 // float4 read-only loads per visited node, near child first, culled by the closest t so far.

@@ -1,8 +1,263 @@
-// rt_lbvh.cu — GPU LBVH build (placeholder until the Karras builder lands in this file).
+// rt_lbvh.cu — GPU LBVH build for large scenes (BASELINE.json north_star (1)): motion-union
+// AABBs -> 63-bit Morton codes of the box centres -> radix sort -> Karras' parallel binary
+// radix tree -> bottom-up refit, written straight into the flattened 64-byte two-child-box
+// node array the traversal kernel reads (rt_device.cuh BvhNode).  Replaces the reference's
+// single-thread recursive median split with an in-thread sort per level (bvh.h:75-113),
+// which is O(N log^2 N) on one GPU thread and cannot build 10^6 primitives in useful time.
 #include "rt_lbvh.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 
 namespace rtd {
 
-cudaError_t lbvh_build(const float*, uint32_t, BvhNode*, cudaStream_t, float*, uint32_t*) { return cudaErrorNotSupported; }
+namespace {
+
+__device__ __forceinline__ unsigned flip_f(float f) { // order-preserving float -> uint
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unflip_f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// Primitive bounds (sphere.h:142-146; moving: union of the boxes at both ends of the motion,
+// sphere.h:192-202), padded exactly like the host builder (rt_bvh_host.cpp sphere_box) so the
+// conservative slab test never rejects a ray the rounded sphere test accepts.
+__global__ void __launch_bounds__(256) k_prim_boxes(const float4* __restrict__ sph_a, const float4* __restrict__ sph_b,
+                                                    uint32_t n, uint32_t n_static, float4* __restrict__ lo,
+                                                    float4* __restrict__ hi, unsigned* __restrict__ cbounds) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float c[3] = {0.f, 0.f, 0.f};
+    bool valid = i < n;
+    if (valid) {
+        float4 a = __ldg(&sph_a[i]);
+        float c0[3] = {a.x, a.y, a.z}, c1[3] = {a.x, a.y, a.z};
+        if (i >= n_static) {
+            float4 b = __ldg(&sph_b[i]);
+            c1[0] = __fadd_rz(a.x, b.x); // where moving_center() puts the sphere at the end of its motion
+            c1[1] = __fadd_rz(a.y, b.y);
+            c1[2] = __fadd_rz(a.z, b.z);
+        }
+        float ar = fabsf(a.w), l[3], h[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float lk = fminf(c0[k], c1[k]) - ar, hk = fmaxf(c0[k], c1[k]) + ar;
+            float pad = ar * 6.1035156e-5f + (fabsf(lk) + fabsf(hk)) * 3.8146973e-6f;
+            l[k] = lk - pad;
+            h[k] = hk + pad;
+            c[k] = 0.5f * l[k] + 0.5f * h[k];
+        }
+        lo[i] = make_float4(l[0], l[1], l[2], 0.f);
+        hi[i] = make_float4(h[0], h[1], h[2], 0.f);
+    }
+    // centroid bounds: warp reduce, then one atomic per warp and axis
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        unsigned mn = valid ? flip_f(c[k]) : 0xffffffffu, mx = valid ? flip_f(c[k]) : 0u;
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&cbounds[k], mn);
+            atomicMax(&cbounds[3 + k], mx);
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x) { // 21 bits -> every third bit
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
+                                                const unsigned* __restrict__ cbounds, unsigned long long* __restrict__ keys,
+                                                uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 l = lo[i], h = hi[i];
+    float c[3] = {0.5f * l.x + 0.5f * h.x, 0.5f * l.y + 0.5f * h.y, 0.5f * l.z + 0.5f * h.z};
+    unsigned long long code = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float mn = unflip_f(cbounds[k]), mx = unflip_f(cbounds[3 + k]);
+        float ext = mx - mn;
+        float t = ext > 0.f ? (c[k] - mn) / ext : 0.f;
+        unsigned long long q = (unsigned long long)fminf(fmaxf(t * 2097152.f, 0.f), 2097151.f);
+        code |= spread21(q) << (2 - k);
+    }
+    keys[i] = code;
+    vals[i] = i;
+}
+
+// Karras 2012: length of the common prefix of keys i and j; ties are broken by the index so
+// duplicate codes still form a proper tree.
+__device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(unsigned(i) ^ unsigned(j));
+    return __clzll(a ^ b);
+}
+
+// One thread per internal node: range, split, children.  Node 0 is the root.
+__global__ void __launch_bounds__(256) k_topology(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                  int n, BvhNode* __restrict__ nodes, int* __restrict__ parent_inner,
+                                                  int* __restrict__ parent_leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + min(d, 0);
+    int lo_ = min(i, j), hi_ = max(i, j);
+    int left, right;
+    if (lo_ == gamma) {
+        left = ~int(vals[gamma]);
+        parent_leaf[gamma] = i;
+    } else {
+        left = gamma;
+        parent_inner[gamma] = i;
+    }
+    if (hi_ == gamma + 1) {
+        right = ~int(vals[gamma + 1]);
+        parent_leaf[gamma + 1] = i;
+    } else {
+        right = gamma + 1;
+        parent_inner[gamma + 1] = i;
+    }
+    // boxes are filled by the refit; only the child references are written here
+    reinterpret_cast<int*>(&nodes[i].lmin)[3] = left;
+    reinterpret_cast<int*>(&nodes[i].lmax)[3] = right;
+    if (i == 0) parent_inner[0] = -1;
+}
+
+// One thread per leaf climbs towards the root.  A thread writes its subtree's box into its
+// side of the parent node; the first thread to reach a node stops, the second (which then sees
+// both child boxes) carries the union upwards.
+__global__ void __launch_bounds__(256) k_refit(const uint32_t* __restrict__ vals, int n, const float4* __restrict__ lo,
+                                               const float4* __restrict__ hi, BvhNode* nodes, const int* __restrict__ parent_inner,
+                                               const int* __restrict__ parent_leaf, unsigned* __restrict__ visits) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t prim = vals[k];
+    float4 bl = lo[prim], bh = hi[prim];
+    int me = ~int(prim);
+    int parent = parent_leaf[k];
+    while (parent >= 0) {
+        BvhNode* nd = nodes + parent;
+        volatile float* f = reinterpret_cast<volatile float*>(nd);
+        int left = reinterpret_cast<const int*>(&nd->lmin)[3];
+        if (left == me) {
+            f[0] = bl.x; f[1] = bl.y; f[2] = bl.z;
+            f[4] = bh.x; f[5] = bh.y; f[6] = bh.z;
+        } else {
+            f[8] = bl.x; f[9] = bl.y; f[10] = bl.z; f[11] = 0.f;
+            f[12] = bh.x; f[13] = bh.y; f[14] = bh.z; f[15] = 0.f;
+        }
+        __threadfence();
+        if (atomicAdd(&visits[parent], 1u) == 0u) return; // sibling subtree not finished yet
+        __threadfence();
+        bl = make_float4(fminf(f[0], f[8]), fminf(f[1], f[9]), fminf(f[2], f[10]), 0.f);
+        bh = make_float4(fmaxf(f[4], f[12]), fmaxf(f[5], f[13]), fmaxf(f[6], f[14]), 0.f);
+        me = parent;
+        parent = parent_inner[parent];
+    }
+}
+
+// depth of the deepest leaf (for the traversal stack bound): every leaf walks its parent chain
+__global__ void __launch_bounds__(256) k_depth(int n, const int* __restrict__ parent_inner, const int* __restrict__ parent_leaf,
+                                               unsigned* __restrict__ max_depth) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned d = 0;
+    if (k < n) {
+        int p = parent_leaf[k];
+        while (p >= 0) {
+            ++d;
+            p = parent_inner[p];
+        }
+    }
+    d = __reduce_max_sync(0xffffffffu, d);
+    if ((threadIdx.x & 31) == 0) atomicMax(max_depth, d);
+}
+
+} // namespace
+
+cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n, uint32_t n_static, BvhNode* nodes,
+                       cudaStream_t st, float* ms, uint32_t* depth) {
+    if (n < 2) return cudaErrorInvalidValue;
+    cudaError_t e;
+    float4 *lo = nullptr, *hi = nullptr;
+    unsigned long long *keys = nullptr, *keys_out = nullptr;
+    uint32_t *vals = nullptr, *vals_out = nullptr;
+    int *parent_inner = nullptr, *parent_leaf = nullptr;
+    unsigned *visits = nullptr, *scal = nullptr; // scal: [0..5] centroid bounds, [6] depth
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(lo); cudaFree(hi); cudaFree(keys); cudaFree(keys_out); cudaFree(vals); cudaFree(vals_out);
+        cudaFree(parent_inner); cudaFree(parent_leaf); cudaFree(visits); cudaFree(scal); cudaFree(tmp);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+#define LB_TRY(x)              \
+    do {                       \
+        e = (x);               \
+        if (e != cudaSuccess) { \
+            cleanup();         \
+            return e;          \
+        }                      \
+    } while (0)
+    LB_TRY(cudaMalloc(&lo, n * sizeof(float4)));
+    LB_TRY(cudaMalloc(&hi, n * sizeof(float4)));
+    LB_TRY(cudaMalloc(&keys, n * sizeof(unsigned long long)));
+    LB_TRY(cudaMalloc(&keys_out, n * sizeof(unsigned long long)));
+    LB_TRY(cudaMalloc(&vals, n * sizeof(uint32_t)));
+    LB_TRY(cudaMalloc(&vals_out, n * sizeof(uint32_t)));
+    LB_TRY(cudaMalloc(&parent_inner, n * sizeof(int)));
+    LB_TRY(cudaMalloc(&parent_leaf, n * sizeof(int)));
+    LB_TRY(cudaMalloc(&visits, n * sizeof(unsigned)));
+    LB_TRY(cudaMalloc(&scal, 8 * sizeof(unsigned)));
+    LB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, vals_out, int(n), 0, 63, st));
+    LB_TRY(cudaMalloc(&tmp, tmp_bytes));
+    LB_TRY(cudaEventCreate(&e0));
+    LB_TRY(cudaEventCreate(&e1));
+
+    const unsigned init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+    LB_TRY(cudaMemcpyAsync(scal, init, sizeof init, cudaMemcpyHostToDevice, st));
+    LB_TRY(cudaEventRecord(e0, st));
+    LB_TRY(cudaMemsetAsync(visits, 0, n * sizeof(unsigned), st));
+    const unsigned blocks = (n + 255) / 256;
+    k_prim_boxes<<<blocks, 256, 0, st>>>(sph_a, sph_b, n, n_static, lo, hi, scal);
+    k_morton<<<blocks, 256, 0, st>>>(lo, hi, n, scal, keys, vals);
+    LB_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, vals_out, int(n), 0, 63, st));
+    k_topology<<<blocks, 256, 0, st>>>(keys_out, vals_out, int(n), nodes, parent_inner, parent_leaf);
+    k_refit<<<blocks, 256, 0, st>>>(vals_out, int(n), lo, hi, nodes, parent_inner, parent_leaf, visits);
+    k_depth<<<blocks, 256, 0, st>>>(int(n), parent_inner, parent_leaf, scal + 6);
+    LB_TRY(cudaEventRecord(e1, st));
+    LB_TRY(cudaGetLastError());
+    unsigned d = 0;
+    LB_TRY(cudaMemcpyAsync(&d, scal + 6, sizeof d, cudaMemcpyDeviceToHost, st));
+    LB_TRY(cudaStreamSynchronize(st));
+    if (ms) LB_TRY(cudaEventElapsedTime(ms, e0, e1));
+    if (depth) *depth = d;
+#undef LB_TRY
+    cleanup();
+    return cudaSuccess;
+}
 
 } // namespace rtd

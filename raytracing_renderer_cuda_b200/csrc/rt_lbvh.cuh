@@ -8,9 +8,9 @@
 
 namespace rtd {
 
-// boxes: n x 6 floats (lo.xyz, hi.xyz) on the device, prim index = array index.
-// nodes: n-1 BvhNode, root = 0.  n >= 2.
-cudaError_t lbvh_build(const float* boxes_dev, uint32_t n, BvhNode* nodes_dev, cudaStream_t st, float* ms,
-                       uint32_t* depth);
+// sph_a / sph_b: the device sphere arrays of DScene (static spheres first); prim index = array index.
+// nodes: n-1 BvhNode, root = 0.  n >= 2.  ms: device time of the build; depth: deepest leaf.
+cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n, uint32_t n_static, BvhNode* nodes_dev,
+                       cudaStream_t st, float* ms, uint32_t* depth);
 
 } // namespace rtd
