@@ -113,20 +113,30 @@ def cpu_baseline(cfg_key: str, desc, target_s: float = 12.0) -> dict:
     cores = os.cpu_count() or 1
     w, h = cfg["width"] // 4, cfg["height"] // 4
 
+    import raytracing_renderer_cuda_b200 as rt
+
     if oa.REFCPU_RN_SO.exists():
         kind = "reference"
         sc = oa.RefCpu(oa.REFCPU_RN_SO).scene(desc, use_bvh=True)
         run = lambda spp: sc.render(w, h, spp, nthreads=cores, want_fb=False)[2]  # noqa: E731
     else:
-        import raytracing_renderer_cuda_b200 as rt
-
         kind = "port"
         sc = oa.Oracle().scene(desc)
         run = lambda spp: sc.render(rt.default_params(width=w, height=h, spp=spp), sampler=0, arith=0, nthreads=cores)[1]  # noqa: E731
     t0 = time.perf_counter()
     run(1)
-    probe = max(time.perf_counter() - t0, 1e-3)
-    spp = int(max(1, min(cfg["spp"], target_s / probe)))
+    probe = max(time.perf_counter() - t0, 1e-4)  # one sample per pixel at 1/16 of the frame
+    rate = w * h / probe
+    if rate * target_s > 4 * w * h * 4:  # fast enough: use the full frame
+        w, h = cfg["width"], cfg["height"]
+        sc = None
+        if kind == "reference":
+            sc = oa.RefCpu(oa.REFCPU_RN_SO).scene(desc, use_bvh=True)
+            run = lambda spp: sc.render(w, h, spp, nthreads=cores, want_fb=False)[2]  # noqa: E731
+        else:
+            sc = oa.Oracle().scene(desc)
+            run = lambda spp: sc.render(rt.default_params(width=w, height=h, spp=spp), sampler=0, arith=0, nthreads=cores)[1]  # noqa: E731
+    spp = int(max(1, min(cfg["spp"], rate * target_s / (w * h))))
     t0 = time.perf_counter()
     rays = run(spp)
     dt = time.perf_counter() - t0
