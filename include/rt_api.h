@@ -198,6 +198,18 @@ typedef struct rt_hit {
     float u, v;   /* get_sphere_uv (sphere.h:61-83); computed for every sphere kind */
 } rt_hit;
 
+/* One integrator step at the closest hit of a caller-supplied ray (second parity hook): the terms of
+ * color()'s loop body, main.cu:45-55.  The step draws its random numbers with the Philox key
+ * (pixel = ray index, sample = 0, bounce = 1). */
+typedef struct rt_shade_sample {
+    uint32_t id;          /* closest object, RT_INVALID_ID on miss (everything below is then 0) */
+    uint32_t continues;   /* 1: material::scatter returned true and `scattered` is valid; 0: the path ends with `emitted` */
+    float t;
+    float emitted[3];     /* m.emit(h) + bloom (main.cu:49) */
+    float attenuation[3]; /* scatter()'s attenuation (main.cu:50-51) */
+    rt_ray scattered;     /* origin = hit point, direction NOT normalised, time (material.h:113,125,179-181) */
+} rt_shade_sample;
+
 typedef struct rt_context rt_context;
 typedef struct rt_scene rt_scene;
 
@@ -229,6 +241,10 @@ rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info);
  * for n caller-supplied rays. use_bvh=0 forces the brute-force list path. */
 rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n,
                            float tmin, int use_bvh, rt_hit* hits);
+
+/* Second parity hook: closest hit + one shading step per ray (see rt_shade_sample). */
+rt_status rt_shade_probe(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n,
+                         const rt_render_params* p, int use_bvh, rt_shade_sample* out);
 
 /* Replaces init_rand_state + render (main.cu:76-132, :438-449). out_rgb is a
  * HOST buffer of width*height*3 floats in the reference framebuffer layout:

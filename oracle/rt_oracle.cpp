@@ -563,6 +563,44 @@ void orc_render(const orc_scene* s, const rt_render_params* rp, int sampler, int
     if (rays_out) *rays_out = total.load();
 }
 
+// One integrator step per caller-supplied ray with the product's sampling (Philox key: pixel = ray index,
+// sample 0, bounce 1): the counterpart of rt_shade_probe.
+void orc_shade_probe(const orc_scene* s, const rt_ray* rays, size_t n, const rt_render_params* rp, int arith,
+                     rt_shade_sample* out) {
+    for (size_t i = 0; i < n; ++i) {
+        const rt_ray& in = rays[i];
+        Ray r{mk(in.origin[0], in.origin[1], in.origin[2]), mk(in.direction[0], in.direction[1], in.direction[2]), in.time};
+        rt_shade_sample o;
+        memset(&o, 0, sizeof o);
+        o.id = RT_INVALID_ID;
+        Hit h;
+        if (scene_hit(*s, r, rp->tmin, FLT_MAX, arith, h)) {
+            if (!h.uv_set) sphere_uv(h.n, h.u, h.v);
+            const rt_material& m = s->materials[s->spheres[h.prim].material];
+            Sampler sm;
+            sm.mode = 1;
+            sm.seed = rp->seed;
+            sm.pixel = uint32_t(i);
+            sm.sample = 0;
+            Ray next{mk(0, 0, 0), mk(0, 0, 0), 0.f};
+            V3 att = mk(0, 0, 0);
+            V3 e = emit(*s, m, h) + mk(rp->bloom, rp->bloom, rp->bloom);
+            bool cont = scatter(*s, m, r, h, sm, 1u, att, next);
+            o.id = s->spheres[h.prim].id;
+            o.continues = cont ? 1u : 0u;
+            o.t = h.t;
+            store3(o.emitted, e);
+            if (m.kind != RT_MAT_EMITTER) store3(o.attenuation, att);
+            if (cont) {
+                store3(o.scattered.origin, next.o);
+                store3(o.scattered.direction, next.d);
+                o.scattered.time = next.time;
+            }
+        }
+        out[i] = o;
+    }
+}
+
 // Pixel finalisation (main.cu:124-127): col /= spp (vec3.h:138-151: rz(1/f), truncated
 // multiplies), saturate, per-channel truncated sqrt.  accum as above; out: W*H*3.
 void orc_tonemap(const float* accum, int width, int height, float* out_rgb) {

@@ -14,6 +14,8 @@ void orc_trace(const orc_scene* s, const rt_ray* rays, size_t n, float tmin, int
 /* render (main.cu:97-132): accum = width*height*4 floats (sum r,g,b, count), j = 0 bottom row */
 void orc_render(const orc_scene* s, const rt_render_params* rp, int sampler, int arith, int nthreads, float* accum,
                 unsigned long long* rays_out);
+void orc_shade_probe(const orc_scene* s, const rt_ray* rays, size_t n, const rt_render_params* rp, int arith,
+                     rt_shade_sample* out);
 void orc_tonemap(const float* accum, int width, int height, float* out_rgb); /* main.cu:124-127 */
 float orc_perlin_noise(const float p[3]);
 float orc_turbulence(const float p[3]);

@@ -96,9 +96,17 @@ class rt_hit(C.Structure):
                 ("v", C.c_float)]
 
 
+class rt_shade_sample(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("continues", C.c_uint32), ("t", C.c_float), ("emitted", C.c_float * 3),
+                ("attenuation", C.c_float * 3), ("scattered", rt_ray)]
+
+
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("time", "<f4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("id", "<u4"), ("p", "<f4", 3), ("n", "<f4", 3), ("u", "<f4"), ("v", "<f4")])
+SHADE_DTYPE = np.dtype([("id", "<u4"), ("continues", "<u4"), ("t", "<f4"), ("emitted", "<f4", 3), ("attenuation", "<f4", 3),
+                        ("scattered", RAY_DTYPE)])
 assert RAY_DTYPE.itemsize == C.sizeof(rt_ray) and HIT_DTYPE.itemsize == C.sizeof(rt_hit)
+assert SHADE_DTYPE.itemsize == C.sizeof(rt_shade_sample)
 
 # every symbol include/rt_api.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
@@ -115,6 +123,7 @@ _SIGNATURES = {
     "rt_scene_destroy": (None, [_VP]),
     "rt_scene_get_info": (C.c_int, [_VP, C.POINTER(rt_scene_info)]),
     "rt_trace_primary": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_float, C.c_int, _VP]),
+    "rt_shade_probe": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.POINTER(rt_render_params), C.c_int, _VP]),
     "rt_render": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
     "rt_render_accum": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
     "rt_render_accum_device": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
@@ -156,7 +165,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 
 def check_layout(lib: C.CDLL) -> None:
     for cls in (rt_sphere, rt_material, rt_texture, rt_image, rt_camera, rt_scene_desc, rt_render_params, rt_stats,
-                rt_scene_info, rt_ray, rt_hit):
+                rt_scene_info, rt_ray, rt_hit, rt_shade_sample):
         want = lib.rt_abi_sizeof(cls.__name__.encode())
         if want != C.sizeof(cls):
             raise RuntimeError(f"ABI drift: sizeof({cls.__name__}) is {want} in the library, {C.sizeof(cls)} here")
@@ -285,6 +294,13 @@ class Scene:
         _check(self.lib, self.lib.rt_trace_primary(self.ctx._h, self._h, rays.ctypes.data, rays.shape[0], tmin,
                                                    int(use_bvh), hits.ctypes.data))
         return hits
+
+    def shade_probe(self, rays: np.ndarray, params: rt_render_params, use_bvh: bool = True) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        out = np.zeros(rays.shape[0], dtype=SHADE_DTYPE)
+        _check(self.lib, self.lib.rt_shade_probe(self.ctx._h, self._h, rays.ctypes.data, rays.shape[0], C.byref(params),
+                                                 int(use_bvh), out.ctypes.data))
+        return out
 
     def render(self, params: rt_render_params, out: np.ndarray | None = None):
         """rt_render: HOST float RGB [H, W, 3], reference framebuffer layout (row 0 = bottom)."""

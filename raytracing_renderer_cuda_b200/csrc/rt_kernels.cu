@@ -43,6 +43,58 @@ void launch_trace_primary(const DScene& sc, const rt_ray* rays_dev, size_t n, fl
     k_trace_primary<<<blocks, 256, 0, st>>>(sc, rays_dev, n, tmin, use_bvh ? 1 : 0, hits_dev);
 }
 
+// --------------------------------------------------------------- shade_probe ----
+__global__ void __launch_bounds__(256) k_shade_probe(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp,
+                                                     const rt_ray* __restrict__ rays, size_t n, int use_bvh,
+                                                     rt_shade_sample* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    perlin_stage(smem, threadIdx.x, blockDim.x);
+    __syncthreads();
+    PerlinTab pt{smem, threadIdx.x & 31u};
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rt_ray in = rays[i];
+    Ray r;
+    r.o = mk(in.origin[0], in.origin[1], in.origin[2]);
+    r.d = mk(in.direction[0], in.direction[1], in.direction[2]);
+    r.time = in.time;
+    RayQ q = make_rayq(r);
+    Hit h = closest_hit(sc, q, rp.tmin, use_bvh != 0);
+    rt_shade_sample o;
+    memset(&o, 0, sizeof o);
+    o.id = RT_INVALID_ID;
+    if (h.prim != RT_INVALID_ID) {
+        V3 E, att;
+        Ray next;
+        next.o = next.d = mk(0.f, 0.f, 0.f);
+        next.time = 0.f;
+        bool cont = shade_terms(sc, rp, pt, q, h, uint32_t(i), 0u, 1u, E, att, next);
+        o.id = __ldg(&sc.sph_c[h.prim]).z;
+        o.continues = cont ? 1u : 0u;
+        o.t = h.t;
+        o.emitted[0] = E.x; o.emitted[1] = E.y; o.emitted[2] = E.z;
+        o.attenuation[0] = att.x; o.attenuation[1] = att.y; o.attenuation[2] = att.z;
+        if (cont) {
+            o.scattered.origin[0] = next.o.x; o.scattered.origin[1] = next.o.y; o.scattered.origin[2] = next.o.z;
+            o.scattered.direction[0] = next.d.x; o.scattered.direction[1] = next.d.y; o.scattered.direction[2] = next.d.z;
+            o.scattered.time = next.time;
+        }
+    }
+    out[i] = o;
+}
+
+void launch_shade_probe(const DScene& sc, const DRenderParams& rp, const rt_ray* rays_dev, size_t n, bool use_bvh,
+                        rt_shade_sample* out_dev, cudaStream_t st) {
+    if (n == 0) return;
+    const size_t smem = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_shade_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        attr_set = true;
+    }
+    k_shade_probe<<<unsigned((n + 255) / 256), 256, smem, st>>>(sc, rp, rays_dev, n, use_bvh ? 1 : 0, out_dev);
+}
+
 // --------------------------------------------------------------- megakernel ----
 // One thread per path, grid-stride over (sample, pixel) with pixel fastest so a warp
 // covers 32 neighbouring pixels of one sample.  This is the reference's structure
@@ -51,7 +103,7 @@ void launch_trace_primary(const DScene& sc, const rt_ray* rays_dev, size_t n, fl
 __global__ void __launch_bounds__(256) k_render_mega(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp,
                                                      int use_bvh, float4* __restrict__ accum,
                                                      unsigned long long* __restrict__ ray_counter) {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     perlin_stage(smem, threadIdx.x, blockDim.x);
     __syncthreads();
     PerlinTab pt{smem, threadIdx.x & 31u};

@@ -11,6 +11,10 @@ namespace rtd {
 void launch_trace_primary(const DScene& sc, const rt_ray* rays_dev, size_t n, float tmin, bool use_bvh,
                           rt_hit* hits_dev, cudaStream_t st);
 
+// parity hook: closest hit + one shading step (terms of main.cu:45-55) per caller-supplied ray
+void launch_shade_probe(const DScene& sc, const DRenderParams& rp, const rt_ray* rays_dev, size_t n, bool use_bvh,
+                        rt_shade_sample* out_dev, cudaStream_t st);
+
 // one thread runs whole paths (reference structure, main.cu:35-74,97-132)
 void launch_render_mega(const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
                         unsigned long long* ray_counter, int sm_count, cudaStream_t st);

@@ -8,6 +8,16 @@
 namespace rtd {
 
 // ------------------------------------------------------------------ Perlin ----
+// perlin_noise() is one out-of-line function and the octave loop is not unrolled: the shade kernel drops from
+// 9 000 to 3 900 SASS instructions (144 KB -> 62 KB), which removes the instruction-cache stalls ncu showed
+// (profiles/r01_wavefront_ncu.md) and lets ptxas fit 4 CTAs of 256 threads per SM (64 registers).
+#ifndef RT_PERLIN_INLINE
+#define RT_PERLIN_FN static __device__ __noinline__
+#define RT_PERLIN_UNROLL _Pragma("unroll 1")
+#else
+#define RT_PERLIN_FN RT_DEV
+#define RT_PERLIN_UNROLL _Pragma("unroll")
+#endif
 // Ken Perlin's 2002 permutation (perlin_noise.h:24-37).  p[512] of the reference is
 // this table twice (perlin_noise.h:43), so p[i] == perm[i & 255] for every index used.
 __device__ const uint8_t k_perlin_perm[256] = {
@@ -34,9 +44,12 @@ struct PerlinTab {
     uint32_t lane;
 };
 RT_DEV void perlin_stage(uint32_t* smem, uint32_t tid, uint32_t nthreads) {
-    for (uint32_t w = tid; w < RT_PERLIN_SMEM_WORDS; w += nthreads) {
-        uint32_t i = w >> 5;
-        smem[w] = uint32_t(k_perlin_perm[i]) | (uint32_t(k_perlin_perm[(i + 1) & 255]) << 8);
+    // 4 consecutive replica words hold the same pair: one 16-byte store per 4 words
+    uint4* s4 = reinterpret_cast<uint4*>(smem);
+    for (uint32_t w = tid; w < RT_PERLIN_SMEM_WORDS / 4; w += nthreads) {
+        uint32_t i = w >> 3;
+        uint32_t v = uint32_t(k_perlin_perm[i]) | (uint32_t(k_perlin_perm[(i + 1) & 255]) << 8);
+        s4[w] = make_uint4(v, v, v, v);
     }
 }
 RT_DEV uint32_t perlin_pair(const PerlinTab& pt, uint32_t i) { return pt.s[((i & 255u) << 5) | pt.lane]; }
@@ -52,7 +65,7 @@ RT_DEV float perlin_ease(float t) { return t * t * t * (t * (t * 6.f - 15.f) + 1
 RT_DEV float perlin_lerp(float t, float a, float b) { return a + t * (b - a); }         // :167-171
 
 // perlin_noise::noise (perlin_noise.h:46-105)
-RT_DEV float perlin_noise(const PerlinTab& pt, V3 p) {
+RT_PERLIN_FN float perlin_noise(const PerlinTab& pt, V3 p) {
     float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
     uint32_t xi = uint32_t(int(fx)) & 255u, yi = uint32_t(int(fy)) & 255u, zi = uint32_t(int(fz)) & 255u;
     float xf = p.x - fx, yf = p.y - fy, zf = p.z - fz;
@@ -80,7 +93,7 @@ RT_DEV float perlin_noise(const PerlinTab& pt, V3 p) {
 // lacunacity 2, gain .5, 6 octaves (perlin_noise.h:13-17)
 RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
     float frequency = 1.f, sum = 0.f, amplitude = 1.f;
-#pragma unroll
+    RT_PERLIN_UNROLL
     for (int i = 0; i < 6; ++i) {
         float r = perlin_noise(pt, p * frequency);
         sum += fabsf(r * 2.f - 1.f) * amplitude;
@@ -274,37 +287,42 @@ RT_DEV void scatter_dielectric(const RayQ& q, V3 p, V3 n, float ri, U4 r, Ray& o
     out.time = 0.f;
 }
 
-// One integrator step at an accepted hit — the body of color()'s loop (main.cu:45-55):
-//   E = m.emit(h) + bloom;  if m.scatter(...)  A = E + att*A, continue with `out`
-//                           else               the path's value is E (A is dropped).
-// Returns true if the path continues.  `bounce` counts from 1 for the RNG key.
-RT_DEV bool shade_hit(const DScene& sc, const DRenderParams& rp, const PerlinTab& pt, const RayQ& q, Hit h,
-                      uint32_t pixel, uint32_t sample, uint32_t bounce, V3& A, Ray& out) {
+// The terms of one integrator step at an accepted hit — the body of color()'s loop (main.cu:45-55):
+//   E = m.emit(h) + bloom;  `att`/`out` = what m.scatter(...) produces.  Returns false when scatter() does
+// (emitter, absorbed metal ray): the path's value is then E.  `bounce` counts from 1 for the RNG key.
+RT_DEV bool shade_terms(const DScene& sc, const DRenderParams& rp, const PerlinTab& pt, const RayQ& q, Hit h,
+                        uint32_t pixel, uint32_t sample, uint32_t bounce, V3& E, V3& att, Ray& out) {
     V3 p, n;
     hit_surface(sc, q, h, p, n);
     DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
     V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
+    att = mk(0.f, 0.f, 0.f);
     if (m.kind == RT_MAT_EMITTER) { // emitter::emit / scatter (material.h:42-52)
-        A = texture_value(sc, pt, m.tex, n, p) * m.param + bloom;
+        E = texture_value(sc, pt, m.tex, n, p) * m.param + bloom;
         return false;
     }
-    V3 E = mk(0.f, 0.f, 0.f) + bloom; // material::emit (material.h:14-16)
+    E = mk(0.f, 0.f, 0.f) + bloom; // material::emit (material.h:14-16)
     U4 r = rng_block(rp.seed, pixel, sample, bounce, 0);
-    V3 att;
     if (m.kind == RT_MAT_LAMBERTIAN) {
         scatter_lambertian(q, p, n, r, out);
         att = texture_value(sc, pt, m.tex, n, p);
-    } else if (m.kind == RT_MAT_METAL) {
-        att = mk(m.ax, m.ay, m.az);
-        if (!scatter_metal(q, p, n, m.param, r, out)) { // absorbed: the path's value is E
-            A = E;
-            return false;
-        }
-    } else {
-        att = mk(m.ax, m.ay, m.az);
-        scatter_dielectric(q, p, n, m.param, r, out);
+        return true;
     }
-    A = E + att * A; // main.cu:51
+    att = mk(m.ax, m.ay, m.az);
+    if (m.kind == RT_MAT_METAL) return scatter_metal(q, p, n, m.param, r, out); // false: absorbed, the value is E
+    scatter_dielectric(q, p, n, m.param, r, out);
+    return true;
+}
+
+// A <- E + att*A (main.cu:51) or A <- E when the path ends.  Returns true if the path continues.
+RT_DEV bool shade_hit(const DScene& sc, const DRenderParams& rp, const PerlinTab& pt, const RayQ& q, Hit h,
+                      uint32_t pixel, uint32_t sample, uint32_t bounce, V3& A, Ray& out) {
+    V3 E, att;
+    if (!shade_terms(sc, rp, pt, q, h, pixel, sample, bounce, E, att, out)) {
+        A = E;
+        return false;
+    }
+    A = E + att * A;
     return true;
 }
 

@@ -35,6 +35,9 @@ namespace rtd {
 enum : int { Q_NEW = 0, Q_LAMB_CONST, Q_LAMB_NOISE1, Q_LAMB_NOISE6, Q_LAMB_IMAGE, Q_METAL, Q_DIEL, Q_EMIT, NQ };
 #define Q_NONE (-1)
 #define WF_THREADS 256
+#ifndef WF_MINBLOCKS
+#define WF_MINBLOCKS 4 // 64 registers/thread: 32 warps per SM (A/B on C1: 15.4 ms at 2, 13.5 at 3, 12.6 at 4)
+#endif
 
 struct WfRecord { // 64 B, one per slot
     float4 o;     // origin.xyz, ray time
@@ -96,10 +99,10 @@ RT_DEV int classify_hit(const DScene& sc, const DRenderParams& rp, const RayQ& q
 }
 
 template <bool USE_BVH>
-__global__ void __launch_bounds__(WF_THREADS, 2)
+__global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     k_wf_step(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t s_count[NQ];
     __shared__ uint32_t s_base[NQ];
     __shared__ unsigned long long s_path_base;

@@ -36,6 +36,7 @@ class Oracle:
         L.orc_render.argtypes = [_VP, C.POINTER(capi.rt_render_params), C.c_int, C.c_int, C.c_int, _VP,
                                  C.POINTER(C.c_ulonglong)]
         L.orc_tonemap.argtypes = [_VP, C.c_int, C.c_int, _VP]
+        L.orc_shade_probe.argtypes = [_VP, _VP, C.c_size_t, C.POINTER(capi.rt_render_params), C.c_int, _VP]
         L.orc_perlin_noise.restype = C.c_float
         L.orc_perlin_noise.argtypes = [_F3]
         L.orc_turbulence.restype = C.c_float
@@ -94,6 +95,12 @@ class OracleScene:
         hits = np.zeros(len(rays), capi.HIT_DTYPE)
         self.L.orc_trace(self._h, rays.ctypes.data, len(rays), tmin, arith, hits.ctypes.data)
         return hits
+
+    def shade_probe(self, rays: np.ndarray, params: capi.rt_render_params, arith: int = 1) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, capi.RAY_DTYPE)
+        out = np.zeros(len(rays), capi.SHADE_DTYPE)
+        self.L.orc_shade_probe(self._h, rays.ctypes.data, len(rays), C.byref(params), arith, out.ctypes.data)
+        return out
 
     def render(self, params: capi.rt_render_params, sampler: int, arith: int = 0, nthreads: int = 8):
         acc = np.zeros((params.height, params.width, 4), np.float32)
