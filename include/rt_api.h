@@ -234,6 +234,8 @@ rt_status rt_context_synchronize(rt_context* ctx);
  * upload (main.cu:383-388): copies the POD scene to the device, prepares the
  * SoA sphere arrays and builds the acceleration structure. */
 rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out);
+/* A scene belongs to its context (device memory comes from the context's stream-ordered pool and is
+ * released on the context stream): destroy scenes before their context. */
 void rt_scene_destroy(rt_scene* scene); /* replaces free_scene<<<1,1>>> (main.cu:360-366) */
 rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info);
 

@@ -71,6 +71,13 @@ struct rt_context {
     float* out_rgb = nullptr;
     size_t out_px = 0;
     rtd::WavefrontState* wf = nullptr;
+    // cudaArray allocations cost milliseconds; arrays of destroyed scenes are kept for the next scene of the
+    // same image size (a frame loop that re-uploads its scene every frame then allocates nothing)
+    struct CachedArray {
+        int32_t width, height;
+        cudaArray_t arr;
+    };
+    std::vector<CachedArray> array_cache;
 };
 
 struct rt_scene {
@@ -78,7 +85,7 @@ struct rt_scene {
     rtd::DScene d{};
     rt_scene_info info{};
     std::vector<void*> allocs;
-    std::vector<cudaArray_t> arrays;
+    std::vector<rt_context::CachedArray> arrays;
     std::vector<cudaTextureObject_t> texobjs;
 };
 
@@ -94,7 +101,7 @@ rt_status dev_alloc(rt_scene* s, T** out, size_t count) {
     *out = nullptr;
     if (count == 0) return RT_OK;
     void* p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+    CUDA_TRY(cudaMallocAsync(&p, count * sizeof(T), s->ctx->stream)); // stream-ordered pool: no map/unmap per scene
     s->allocs.push_back(p);
     s->info.device_bytes += count * sizeof(T);
     *out = static_cast<T*>(p);
@@ -310,6 +317,13 @@ rt_status rt_context_create(int device, rt_context** out) {
     ctx->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        // keep freed scene memory in the device's stream-ordered pool instead of returning it to the driver
+        cudaMemPool_t pool = nullptr;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CUDA_TRY(cudaMalloc(&ctx->d_ray_counter, sizeof(unsigned long long)));
     for (auto& ev : ctx->ev) CUDA_TRY(cudaEventCreate(&ev));
     *out = ctx;
@@ -323,6 +337,7 @@ void rt_context_destroy(rt_context* ctx) {
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->out_rgb) cudaFree(ctx->out_rgb);
     if (ctx->d_ray_counter) cudaFree(ctx->d_ray_counter);
+    for (auto& c : ctx->array_cache) cudaFreeArray(c.arr);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -457,28 +472,33 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
         const size_t texels = size_t(im.width) * size_t(im.height);
         float* d_rgb = nullptr;
         float4* d_rgba = nullptr;
-        CUDA_TRY(cudaMalloc(&d_rgb, texels * 3 * sizeof(float)));
-        cudaError_t e = cudaMalloc(&d_rgba, texels * sizeof(float4));
+        CUDA_TRY(cudaMallocAsync(&d_rgb, texels * 3 * sizeof(float), stream));
+        cudaError_t e = cudaMallocAsync(&d_rgba, texels * sizeof(float4), stream);
         if (e != cudaSuccess) {
-            cudaFree(d_rgb);
-            set_error("cudaMalloc(image staging) failed: %s", cudaGetErrorString(e));
+            cudaFreeAsync(d_rgb, stream);
+            set_error("cudaMallocAsync(image staging) failed: %s", cudaGetErrorString(e));
             return RT_ERR_OOM;
         }
         cudaArray_t arr = nullptr;
+        for (size_t k = 0; k < ctx->array_cache.size(); ++k)
+            if (ctx->array_cache[k].width == im.width && ctx->array_cache[k].height == im.height) {
+                arr = ctx->array_cache[k].arr;
+                ctx->array_cache.erase(ctx->array_cache.begin() + long(k));
+                break;
+            }
         cudaChannelFormatDesc cd = cudaCreateChannelDesc<float4>();
         e = cudaMemcpyAsync(d_rgb, im.rgb, texels * 3 * sizeof(float), cudaMemcpyHostToDevice, stream);
         if (e == cudaSuccess) {
             rtd::launch_rgb_to_rgba(d_rgb, d_rgba, texels, stream);
-            e = cudaMallocArray(&arr, &cd, size_t(im.width), size_t(im.height));
+            if (!arr) e = cudaMallocArray(&arr, &cd, size_t(im.width), size_t(im.height));
         }
         if (e == cudaSuccess) {
-            s->arrays.push_back(arr);
+            s->arrays.push_back(rt_context::CachedArray{im.width, im.height, arr});
             e = cudaMemcpy2DToArrayAsync(arr, 0, 0, d_rgba, size_t(im.width) * sizeof(float4), size_t(im.width) * sizeof(float4),
                                          size_t(im.height), cudaMemcpyDeviceToDevice, stream);
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        cudaFree(d_rgb);
-        cudaFree(d_rgba);
+        cudaFreeAsync(d_rgb, stream);
+        cudaFreeAsync(d_rgba, stream);
         if (e != cudaSuccess) {
             set_error("image texture upload failed: %s", cudaGetErrorString(e));
             return RT_ERR_CUDA;
@@ -529,9 +549,16 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
 void rt_scene_destroy(rt_scene* scene) {
     if (!scene) return;
     if (scene->ctx) cudaSetDevice(scene->ctx->device);
+    // the scene's kernels are ordered before these on the context stream
     for (auto t : scene->texobjs) cudaDestroyTextureObject(t);
-    for (auto a : scene->arrays) cudaFreeArray(a);
-    for (auto p : scene->allocs) cudaFree(p);
+    for (auto& a : scene->arrays) {
+        if (scene->ctx && scene->ctx->array_cache.size() < 8) scene->ctx->array_cache.push_back(a);
+        else cudaFreeArray(a.arr);
+    }
+    for (auto p : scene->allocs) {
+        if (scene->ctx) cudaFreeAsync(p, scene->ctx->stream);
+        else cudaFree(p);
+    }
     delete scene;
 }
 
@@ -550,8 +577,8 @@ rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray*
     if (st != RT_OK) return st;
     rt_ray* d_rays = nullptr;
     rt_hit* d_hits = nullptr;
-    CUDA_TRY(cudaMalloc(&d_rays, n * sizeof(rt_ray)));
-    cudaError_t e = cudaMalloc(&d_hits, n * sizeof(rt_hit));
+    CUDA_TRY(cudaMallocAsync(&d_rays, n * sizeof(rt_ray), ctx->stream));
+    cudaError_t e = cudaMallocAsync(&d_hits, n * sizeof(rt_hit), ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         rtd::launch_trace_primary(scene->d, d_rays, n, tmin, use_bvh != 0, d_hits, ctx->stream);
@@ -559,8 +586,8 @@ rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray*
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_hits, n * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_rays);
-    if (d_hits) cudaFree(d_hits);
+    cudaFreeAsync(d_rays, ctx->stream);
+    if (d_hits) cudaFreeAsync(d_hits, ctx->stream);
     if (e != cudaSuccess) {
         set_error("rt_trace_primary: %s", cudaGetErrorString(e));
         return RT_ERR_CUDA;
@@ -578,8 +605,8 @@ rt_status rt_shade_probe(rt_context* ctx, const rt_scene* scene, const rt_ray* r
     if (st != RT_OK) return st;
     rt_ray* d_rays = nullptr;
     rt_shade_sample* d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_rays, n * sizeof(rt_ray)));
-    cudaError_t e = cudaMalloc(&d_out, n * sizeof(rt_shade_sample));
+    CUDA_TRY(cudaMallocAsync(&d_rays, n * sizeof(rt_ray), ctx->stream));
+    cudaError_t e = cudaMallocAsync(&d_out, n * sizeof(rt_shade_sample), ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         rtd::launch_shade_probe(scene->d, to_device_params(*p), d_rays, n, use_bvh != 0, d_out, ctx->stream);
@@ -587,8 +614,8 @@ rt_status rt_shade_probe(rt_context* ctx, const rt_scene* scene, const rt_ray* r
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(rt_shade_sample), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_rays);
-    if (d_out) cudaFree(d_out);
+    cudaFreeAsync(d_rays, ctx->stream);
+    if (d_out) cudaFreeAsync(d_out, ctx->stream);
     if (e != cudaSuccess) {
         set_error("rt_shade_probe: %s", cudaGetErrorString(e));
         return RT_ERR_CUDA;

@@ -214,7 +214,9 @@ def test_one_shading_step_matches_oracle(ctx, oracle, scene_descs, name):
         scale = np.linalg.norm(want["scattered"]["direction"][both], axis=1)
         swapped = dd > 1e-3 * np.maximum(scale, 1.0)   # dielectric reflect/refract decided the other way
         assert swapped.mean() < 1e-3
-        assert (dd[~swapped] <= 2e-5 * np.maximum(scale[~swapped], 1.0)).all(), float(dd[~swapped].max())
+        # target = p + n + ball is formed at the magnitude of p (up to 1000 on the ground): allow 2 ulp of |p|
+        tol = 2e-5 * np.maximum(scale, 1.0) + 2.4e-7 * np.abs(want["scattered"]["origin"][both]).max(axis=1)
+        assert (dd[~swapped] <= tol[~swapped]).all(), float((dd[~swapped] - tol[~swapped]).max())
         ok = hit & ~flips
         assert np.abs(got["attenuation"][ok] - want["attenuation"][ok]).max() < 2e-3       # __sinf at |x| up to ~100
         assert np.median(np.abs(got["attenuation"][ok] - want["attenuation"][ok])) < 1e-6
