@@ -196,18 +196,53 @@ def run_ours(args) -> None:
     params = rt.default_params(width=W, height=H, spp=spp, sample_offset=rank * spp)
 
     with torch.cuda.stream(stream):
-        accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
-        rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
-        rgb8 = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        collective = "none"
+        hdl = None
+        if world > 1 and args.collective != "nccl":
+            # symmetric memory: every rank maps every rank's accumulator (NVLink peer pointers + NVLS multicast)
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                accum = symm.empty((H, W, 4), dtype=torch.float32, device=torch.device("cuda", local_rank))
+                rgb = symm.empty((H, W, 3), dtype=torch.float32, device=torch.device("cuda", local_rank))
+                rgb8 = symm.empty((H, W, 3), dtype=torch.uint8, device=torch.device("cuda", local_rank))
+                hdl = symm.rendezvous(accum, dist.group.WORLD)
+                h_rgb = symm.rendezvous(rgb, dist.group.WORLD)
+                h_rgb8 = symm.rendezvous(rgb8, dist.group.WORLD)
+                peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
+                mc_ptr = int(hdl.multicast_ptr) if (args.collective in ("auto", "multimem") and hdl.has_multicast_support) else 0
+                root_rgb, root_rgb8 = int(h_rgb.buffer_ptrs[0]), int(h_rgb8.buffer_ptrs[0])
+                row0, row1 = rank * H // world, (rank + 1) * H // world
+                collective = "fused peer-memory reduce+tonemap (" + ("NVLS multimem.ld_reduce" if mc_ptr else "NVLink peer loads") + ")"
+            except Exception as ex:  # noqa: BLE001
+                if args.collective != "auto":
+                    raise
+                print(f"[bench] symmetric memory unavailable ({ex!r}); using the NCCL reduce", file=sys.stderr)
+                hdl = None
+        if hdl is None:
+            accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+            rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+            rgb8 = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+            if world > 1:
+                collective = "NCCL reduce(SUM) to rank 0 + tonemap"
+
+        def finish():
+            """sum over ranks + pixel finalisation; the frame ends up on rank 0"""
+            if hdl is not None:
+                hdl.barrier(0)  # every rank has finished rendering into its accumulator
+                rt.reduce_tonemap_peers(ctx, peer_ptrs, mc_ptr, W, H, row0, row1, root_rgb, root_rgb8)
+                hdl.barrier(1)  # every band is in rank 0's image; accumulators may be reused
+            else:
+                if world > 1:
+                    dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    rt.tonemap_device(ctx, accum.data_ptr(), W, H, rgb.data_ptr(), rgb8.data_ptr())
 
         def step():
             accum.zero_()
             scene.render_accum_device(params, accum.data_ptr())
-            if world > 1:
-                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                rt.tonemap_device(ctx, accum.data_ptr(), W, H, rgb.data_ptr(), rgb8.data_ptr())
+            finish()
 
         # one instrumented step: rays and launches per step (deterministic: the RNG is keyed on pixel/sample/bounce)
         accum.zero_()
@@ -232,10 +267,7 @@ def run_ours(args) -> None:
             rv[k][0].record(stream)
             scene.render_accum_device(params, accum.data_ptr())
             rv[k][1].record(stream)
-            if world > 1:
-                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                rt.tonemap_device(ctx, accum.data_ptr(), W, H, rgb.data_ptr(), rgb8.data_ptr())
+            finish()
             ev[k][1].record(stream)
         stream.synchronize()
         if world > 1:
@@ -264,9 +296,8 @@ def run_ours(args) -> None:
             else:
                 accum.zero_()
                 sc.render_accum_device(params, accum.data_ptr())
-                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+                finish()
                 if rank == 0:
-                    rt.tonemap_device(ctx, accum.data_ptr(), W, H, rgb.data_ptr(), 0)
                     out_host.copy_(rgb, non_blocking=True)
                 stream.synchronize()
             sc.close()
@@ -311,7 +342,7 @@ def run_ours(args) -> None:
             "rays_per_path": rays_total / paths_total,
             "config": {"workload": cfg["name"], "scene": cfg["scene"], "width": W, "height": H, "spp_per_gpu": spp,
                        "spp_total": spp * world, "max_depth": 50, "n_spheres": int(info.n_spheres), "bvh_nodes": int(info.n_nodes),
-                       "bvh_mode": int(info.bvh_mode), "pipeline": "wavefront", "parallelism": f"samples x{world}",
+                       "bvh_mode": int(info.bvh_mode), "pipeline": "wavefront", "parallelism": f"samples x{world}", "collective": collective,
                        "l2": "flushed between timed steps (256 MiB fill, outside the timed spans)",
                        "timing": "sum of per-step CUDA-event spans on the launching stream, max over ranks"},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
@@ -324,7 +355,7 @@ def run_ours(args) -> None:
             "e2e": {"value": paths_total / e2e_ms / 1e3, "unit": "Mpaths/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": W * H * 3 * 4,
                     "what": "rt_scene_create (H2D scene + texture, BVH build) + rt_render to a pinned host buffer, wall clock"},
-            "gpu_launches": int(args.steps * launches_step),
+            "gpu_launches": int(args.steps * launches_step),  # k_wf_init + k_wf_step x iterations + tonemap / fused reduce-tonemap
             "wavefront_iterations": iters, "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -413,6 +444,8 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--ref-device", choices=["gpu", "cpu"], default="gpu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", choices=["auto", "multimem", "peer", "nccl"], default="auto",
+                    help="N > 1: fused peer-memory reduce+tonemap (NVLS multimem / peer loads) or the plain NCCL reduce")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

@@ -271,6 +271,17 @@ rt_status rt_render_accum_device(rt_context* ctx, const rt_scene* scene, const r
 rt_status rt_tonemap_device(rt_context* ctx, const void* accum_dev, int32_t width, int32_t height,
                             void* out_rgb_dev, void* out_rgb8_dev);
 
+/* Multi-GPU finalisation fused with the collective, over NVLink peer memory (one process per GPU, the
+ * accumulators allocated as symmetric memory so every rank holds device pointers to every rank's copy):
+ * for rows [row_begin, row_end) sums the n_peers accumulators — with NVLS `multimem.ld_reduce` on
+ * `multicast_accum` when it is not NULL, else with peer loads added in rank order — and applies the pixel
+ * finalisation of rt_tonemap_device to the sum.  Outputs may be peer pointers (e.g. the root's image);
+ * out_sum_dev (may be NULL) receives the summed float4 accumulator.  The caller orders this kernel after
+ * every rank's render (a symmetric-memory barrier) and before the root reads the image (a second one). */
+rt_status rt_reduce_tonemap_peers(rt_context* ctx, const void* const* peer_accum_dev, int32_t n_peers,
+                                  const void* multicast_accum, int32_t width, int32_t height, int32_t row_begin,
+                                  int32_t row_end, void* out_rgb_dev, void* out_rgb8_dev, void* out_sum_dev);
+
 /* Host restatement of the writer loop main.cu:475-488 (Y flip + int(255.999f*c)&255). */
 rt_status rt_quantize_rgb8(const float* rgb, int32_t width, int32_t height, uint8_t* out_rgb8);
 rt_status rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t* rgb8);

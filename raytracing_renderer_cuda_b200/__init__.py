@@ -6,4 +6,4 @@ only carries the ctypes binding used by tests/, bench.py and __graft_entry__.py.
 """
 from . import capi  # noqa: F401
 from .capi import (Context, Scene, SceneDesc, default_params, load_library, psnr, quantize_rgb8,  # noqa: F401
-                   tonemap_device)
+                   reduce_tonemap_peers, tonemap_device)

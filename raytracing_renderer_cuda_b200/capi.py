@@ -128,6 +128,8 @@ _SIGNATURES = {
     "rt_render_accum": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
     "rt_render_accum_device": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
     "rt_tonemap_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
+    "rt_reduce_tonemap_peers": (C.c_int, [_VP, C.POINTER(_VP), C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          _VP, _VP, _VP]),
     "rt_quantize_rgb8": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP]),
     "rt_write_ppm": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _VP]),
     "rt_read_ppm_f32": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
@@ -337,6 +339,15 @@ class Scene:
 def tonemap_device(ctx: Context, accum_ptr: int, width: int, height: int, out_rgb_ptr: int = 0, out_rgb8_ptr: int = 0):
     _check(ctx.lib, ctx.lib.rt_tonemap_device(ctx._h, _VP(accum_ptr), width, height, _VP(out_rgb_ptr or None),
                                               _VP(out_rgb8_ptr or None)))
+
+
+def reduce_tonemap_peers(ctx: Context, peer_ptrs, multicast_ptr: int, width: int, height: int, row_begin: int, row_end: int,
+                         out_rgb_ptr: int = 0, out_rgb8_ptr: int = 0, out_sum_ptr: int = 0) -> None:
+    """rt_reduce_tonemap_peers: fused NVLink reduce (+ NVLS multimem when multicast_ptr != 0) and tonemap."""
+    n = len(peer_ptrs)
+    arr = (_VP * n)(*[_VP(int(p)) for p in peer_ptrs])
+    _check(ctx.lib, ctx.lib.rt_reduce_tonemap_peers(ctx._h, arr, n, _VP(multicast_ptr or None), width, height, row_begin, row_end,
+                                                    _VP(out_rgb_ptr or None), _VP(out_rgb8_ptr or None), _VP(out_sum_ptr or None)))
 
 
 def quantize_rgb8(rgb: np.ndarray) -> np.ndarray:

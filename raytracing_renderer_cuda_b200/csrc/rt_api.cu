@@ -664,6 +664,26 @@ rt_status rt_tonemap_device(rt_context* ctx, const void* accum_dev, int32_t widt
     return RT_OK;
 }
 
+rt_status rt_reduce_tonemap_peers(rt_context* ctx, const void* const* peer_accum_dev, int32_t n_peers, const void* multicast_accum,
+                                  int32_t width, int32_t height, int32_t row_begin, int32_t row_end, void* out_rgb_dev,
+                                  void* out_rgb8_dev, void* out_sum_dev) {
+    ARG_CHECK(ctx != nullptr, "ctx is NULL");
+    ARG_CHECK(width > 0 && height > 0, "width/height must be positive");
+    ARG_CHECK(row_begin >= 0 && row_begin <= row_end && row_end <= height, "bad row range");
+    ARG_CHECK(n_peers >= 1 && n_peers <= 16, "n_peers must be in [1, 16]");
+    ARG_CHECK(multicast_accum || peer_accum_dev, "no accumulator pointers");
+    ARG_CHECK(out_rgb_dev || out_rgb8_dev || out_sum_dev, "no output buffer");
+    if (peer_accum_dev)
+        for (int k = 0; k < n_peers; ++k) ARG_CHECK(peer_accum_dev[k] != nullptr, "peer accumulator pointer is NULL");
+    rt_status st = make_current(ctx);
+    if (st != RT_OK) return st;
+    rtd::launch_reduce_tonemap(peer_accum_dev, n_peers, multicast_accum, width, height, row_begin, row_end,
+                               static_cast<float*>(out_rgb_dev), static_cast<uint8_t*>(out_rgb8_dev),
+                               static_cast<float4*>(out_sum_dev), ctx->stream);
+    CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
 rt_status rt_render(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, float* out_rgb, rt_stats* stats) {
     ARG_CHECK(ctx && scene && out_rgb, "ctx/scene/out_rgb is NULL");
     rt_status st = check_params(p);

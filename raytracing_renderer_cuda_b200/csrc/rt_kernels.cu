@@ -185,6 +185,73 @@ __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accu
     }
 }
 
+// --------------------------------------------------------------- fused reduce + tonemap ----
+// Multi-GPU pixel finalisation in ONE kernel over NVLink peer memory: sums the float4 accumulators of all
+// ranks for a band of rows and applies main.cu:124-127 (+ the writer conversion) to the sum.  Two ways to
+// form the sum:
+//   * multicast != nullptr: one `multimem.ld_reduce.global.add.v4.f32` per pixel on the NVLS multicast
+//     address of the symmetric accumulator — the NVSwitch adds the G copies in the fabric and returns the sum;
+//   * otherwise: G `ld.global` loads from the peers' mapped accumulators, added in rank order (bit-reproducible).
+// The outputs may themselves be peer pointers (each rank writes its band straight into the root's image).
+struct PeerPtrs {
+    const float4* p[16];
+};
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256) k_reduce_tonemap(const __grid_constant__ PeerPtrs peers, int n_peers,
+                                                        const float4* __restrict__ multicast, int width, int height,
+                                                        int row_begin, int row_end, float* __restrict__ out_rgb,
+                                                        uint8_t* __restrict__ out_rgb8, float4* __restrict__ out_sum) {
+    const size_t first = size_t(row_begin) * size_t(width), last = size_t(row_end) * size_t(width);
+    for (size_t idx = first + size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < last; idx += size_t(gridDim.x) * blockDim.x) {
+        float4 a;
+        if (multicast) {
+            a = multimem_ld_reduce_add(multicast + idx);
+        } else {
+            a = peers.p[0][idx];
+            for (int k = 1; k < n_peers; ++k) {
+                float4 b = peers.p[k][idx];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+        }
+        if (out_sum) out_sum[idx] = a;
+        float inv = __fdiv_rz(1.0f, a.w);
+        float r = __fsqrt_rz(__saturatef(__fmul_rz(a.x, inv)));
+        float g = __fsqrt_rz(__saturatef(__fmul_rz(a.y, inv)));
+        float b = __fsqrt_rz(__saturatef(__fmul_rz(a.z, inv)));
+        if (out_rgb) {
+            out_rgb[idx * 3 + 0] = r;
+            out_rgb[idx * 3 + 1] = g;
+            out_rgb[idx * 3 + 2] = b;
+        }
+        if (out_rgb8) {
+            size_t i = idx % size_t(width), j = idx / size_t(width);
+            size_t rev = (size_t(height) - 1 - j) * size_t(width) + i;
+            out_rgb8[rev * 3 + 0] = uint8_t(int(255.999f * r) & 255);
+            out_rgb8[rev * 3 + 1] = uint8_t(int(255.999f * g) & 255);
+            out_rgb8[rev * 3 + 2] = uint8_t(int(255.999f * b) & 255);
+        }
+    }
+}
+
+void launch_reduce_tonemap(const void* const* peer_accum, int n_peers, const void* multicast, int width, int height,
+                           int row_begin, int row_end, float* out_rgb, uint8_t* out_rgb8, float4* out_sum, cudaStream_t st) {
+    if (row_end <= row_begin || width <= 0) return;
+    PeerPtrs pp{};
+    for (int k = 0; k < n_peers && k < 16; ++k) pp.p[k] = static_cast<const float4*>(peer_accum[k]);
+    size_t npix = size_t(row_end - row_begin) * size_t(width);
+    size_t want = (npix + 255) / 256;
+    unsigned blocks = unsigned(want < 148 * 8 ? want : 148 * 8);
+    k_reduce_tonemap<<<blocks, 256, 0, st>>>(pp, n_peers, static_cast<const float4*>(multicast), width, height, row_begin, row_end,
+                                             out_rgb, out_rgb8, out_sum);
+}
+
 void launch_tonemap(const float4* accum, int width, int height, float* out_rgb, uint8_t* out_rgb8, cudaStream_t st) {
     size_t npix = size_t(width) * height;
     if (npix == 0) return;

@@ -22,6 +22,10 @@ void launch_render_mega(const DScene& sc, const DRenderParams& rp, bool use_bvh,
 // pixel finalisation (main.cu:124-127) + optional writer conversion (main.cu:476-487)
 void launch_tonemap(const float4* accum, int width, int height, float* out_rgb, uint8_t* out_rgb8, cudaStream_t st);
 
+// multi-GPU: sum of the peers' accumulators (peer loads or NVLS multimem.ld_reduce) fused with the tonemap
+void launch_reduce_tonemap(const void* const* peer_accum, int n_peers, const void* multicast, int width, int height,
+                           int row_begin, int row_end, float* out_rgb, uint8_t* out_rgb8, float4* out_sum, cudaStream_t st);
+
 // float RGB (w*h*3) -> float4 RGBA staging for the image-texture cudaArray
 void launch_rgb_to_rgba(const float* rgb, float4* rgba, size_t n_texels, cudaStream_t st);
 
