@@ -211,7 +211,7 @@ def run_ours(args) -> None:
                 h_rgb = symm.rendezvous(rgb, dist.group.WORLD)
                 h_rgb8 = symm.rendezvous(rgb8, dist.group.WORLD)
                 peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
-                mc_ptr = int(hdl.multicast_ptr) if (args.collective in ("auto", "multimem") and hdl.has_multicast_support) else 0
+                mc_ptr = int(hdl.multicast_ptr or 0) if args.collective in ("auto", "multimem") else 0  # 0: no NVLS multicast
                 root_rgb, root_rgb8 = int(h_rgb.buffer_ptrs[0]), int(h_rgb8.buffer_ptrs[0])
                 row0, row1 = rank * H // world, (rank + 1) * H // world
                 collective = "fused peer-memory reduce+tonemap (" + ("NVLS multimem.ld_reduce" if mc_ptr else "NVLink peer loads") + ")"
@@ -435,6 +435,10 @@ def run_reference(args) -> None:
 
 
 def main() -> None:
+    # stdout carries exactly ONE JSON line: anything libraries print on fd 1 (NCCL's version banner, ...) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -107,7 +107,6 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     __shared__ uint32_t s_base[NQ];
     __shared__ unsigned long long s_path_base;
 
-    perlin_stage(smem, threadIdx.x, blockDim.x);
     const PerlinTab pt{smem, threadIdx.x & 31u};
     const uint32_t lane = threadIdx.x & 31u;
 
@@ -130,6 +129,12 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
         total_chunks += (n_q[order[k]] + WF_THREADS - 1) / WF_THREADS;
         chunk_end[k] = total_chunks;
     }
+
+    // Tail iterations hold a few hundred live paths: CTAs without a chunk leave before staging anything, and
+    // the 32 KB Perlin table is staged only by CTAs that will run a noise shader (their first chunk is the
+    // lowest-numbered one they get, and the noise queues come first; textured emitters may need it too).
+    if (blockIdx.x >= total_chunks) return;
+    if (blockIdx.x < chunk_end[1] || n_q[Q_EMIT] != 0u) perlin_stage(smem, threadIdx.x, blockDim.x);
 
     const unsigned long long npix = (unsigned long long)rp.width * rp.height;
     const unsigned long long npaths = npix * (unsigned long long)rp.spp;

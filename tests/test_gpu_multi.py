@@ -42,7 +42,8 @@ with torch.cuda.stream(stream):
     scene.render_accum_device(rt.default_params(width=W, height=H, spp=count, sample_offset=first), accum.data_ptr())
     row0, row1 = rank * H // world, (rank + 1) * H // world
     out = {}
-    for name, mc in (("peer", 0), ("multimem", int(hdl.multicast_ptr) if hdl.has_multicast_support else 0)):
+    mc_ptr = int(hdl.multicast_ptr or 0)  # 0 when the fabric has no NVLS multicast
+    for name, mc in (("peer", 0), ("multimem", mc_ptr)):
         rgb.zero_(); total.zero_()
         hdl.barrier(0)
         rt.reduce_tonemap_peers(ctx, [int(p) for p in hdl.buffer_ptrs], mc, W, H, row0, row1,
@@ -62,7 +63,7 @@ with torch.cuda.stream(stream):
         scene.render_accum_device(rt.default_params(width=W, height=H, spp=SPP), one.data_ptr())
         stream.synchronize()
         out.update(nccl_sum=ref.cpu().numpy(), nccl_rgb=ref_rgb.cpu().numpy(), one_gpu_sum=one.cpu().numpy(),
-                   has_multicast=np.array([int(hdl.has_multicast_support)]))
+                   has_multicast=np.array([int(mc_ptr != 0)]))
         np.savez(os.environ["RT_OUT"], **out)
 dist.barrier()
 dist.destroy_process_group()
