@@ -50,7 +50,7 @@ struct WfBuffers {
     WfRecord* rec;               // [pool]
     uint32_t* queue;             // [2][NQ][pool]
     uint32_t* counts;            // [3][NQ] queue sizes, rotating: cur / next / being-zeroed
-    unsigned long long* next_path; // next path id to generate
+    unsigned long long* next_path; // [2], rotating: [it & 1] = paths started before iteration `it`
     uint32_t pool;
 };
 
@@ -103,9 +103,8 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     k_wf_step(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint32_t s_count[NQ];
-    __shared__ uint32_t s_base[NQ];
-    __shared__ unsigned long long s_path_base;
+    __shared__ uint32_t s_count[2][NQ]; // double-buffered by chunk parity: two barriers per chunk instead of four
+    __shared__ uint32_t s_base[2][NQ];
 
     const PerlinTab pt{smem, threadIdx.x & 31u};
     const uint32_t lane = threadIdx.x & 31u;
@@ -113,6 +112,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     const uint32_t* cnt_cur = wb.counts + (it % 3) * NQ;
     uint32_t* cnt_next = wb.counts + ((it + 1) % 3) * NQ;
     if (blockIdx.x == 0 && threadIdx.x < NQ) wb.counts[((it + 2) % 3) * NQ + threadIdx.x] = 0; // next iteration's target
+    const unsigned long long path_base = wb.next_path[it & 1]; // paths started by earlier iterations
     const int par_cur = it & 1, par_next = par_cur ^ 1;
 
     uint32_t n_q[NQ], chunk_end[NQ];
@@ -133,33 +133,52 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     // Tail iterations hold a few hundred live paths: CTAs without a chunk leave before staging anything, and
     // the 32 KB Perlin table is staged only by CTAs that will run a noise shader (their first chunk is the
     // lowest-numbered one they get, and the noise queues come first; textured emitters may need it too).
+    if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
     if (blockIdx.x >= total_chunks) return;
     if (blockIdx.x < chunk_end[1] || n_q[Q_EMIT] != 0u) perlin_stage(smem, threadIdx.x, blockDim.x);
+    if (threadIdx.x < 2 * NQ) (&s_count[0][0])[threadIdx.x] = 0u;
+    __syncthreads();
 
     const unsigned long long npix = (unsigned long long)rp.width * rp.height;
     const unsigned long long npaths = npix * (unsigned long long)rp.spp;
     const V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
     unsigned long long nrays = 0;
 
-    for (uint32_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    // chunk -> (queue kind, first entry)
+    auto locate = [&](uint32_t chunk, int& kind, uint32_t& first) {
         int kpos = 0;
 #pragma unroll
         for (int k = 0; k < NQ - 1; ++k) kpos += (chunk >= chunk_end[k]) ? 1 : 0;
-        const int kind = order[kpos];
-        const uint32_t first = (chunk - (kpos ? chunk_end[kpos - 1] : 0u)) * WF_THREADS;
+        kind = order[kpos];
+        first = (chunk - (kpos ? chunk_end[kpos - 1] : 0u)) * WF_THREADS;
+    };
+    uint32_t cpar = 0;
+    int kind;
+    uint32_t first;
+    locate(blockIdx.x, kind, first);
+    uint32_t slot = (first + threadIdx.x < n_q[kind]) ? __ldg(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
+
+    for (uint32_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
         const uint32_t idx = first + threadIdx.x;
         const bool valid = idx < n_q[kind];
+        const int kind_now = kind;
 
-        __syncthreads(); // previous chunk's pushes are done with s_count/s_base; perlin table staged
-        if (threadIdx.x < NQ) s_count[threadIdx.x] = 0;
-        if (kind == Q_NEW && threadIdx.x == 0) {
-            uint32_t want = min(uint32_t(WF_THREADS), n_q[Q_NEW] - first);
-            s_path_base = atomicAdd(wb.next_path, (unsigned long long)want);
+        // Software pipeline over chunks: the slot index of this CTA's NEXT chunk is requested now and its
+        // 64-byte record is prefetched into L2 at the bottom of this iteration, so the next iteration starts
+        // with its dependent load chain (queue -> record -> sphere) already in flight.
+        uint32_t slot_next = 0u;
+        bool valid_next = false;
+        if (chunk + gridDim.x < total_chunks) {
+            locate(chunk + gridDim.x, kind, first);
+            valid_next = first + threadIdx.x < n_q[kind];
+            if (valid_next) slot_next = __ldg(wf_queue(wb, par_cur, kind) + first + threadIdx.x);
         }
-        __syncthreads();
 
-        uint32_t slot = valid ? __ldg(wf_queue(wb, par_cur, kind) + idx) : 0u;
         WfRecord* rec = wb.rec + slot;
+
+        // ray-gen chunks: path id = (paths started before this iteration) + position in the ray-gen queue.
+        // The running total is carried from launch to launch by block 0 (no atomics, no hand-off barrier).
+        const unsigned long long path = path_base + idx;
 
         bool has_ray = false;   // a ray to extend
         bool finished = false;  // path ended: add `A` to the pixel
@@ -169,8 +188,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
         uint32_t pixel = 0, sample = 0, bounce = 0;
 
         if (valid) {
-            if (kind == Q_NEW) {
-                unsigned long long path = s_path_base + threadIdx.x;
+            if (kind_now == Q_NEW) {
                 if (path < npaths) {
                     pixel = uint32_t(path % npix);
                     sample = uint32_t(path / npix) + uint32_t(rp.sample_offset);
@@ -199,7 +217,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
                 A = mk(ra.x, ra.y, ra.z);
                 V3 p, n;
                 hit_surface(sc, q, h, p, n);
-                if (kind == Q_EMIT) { // emitter::emit (material.h:50-52): value = tex * intensity + bloom; A is dropped
+                if (kind_now == Q_EMIT) { // emitter::emit (material.h:50-52): value = tex * intensity + bloom; A is dropped
                     DTexture t = load_tex(sc, int32_t(ids.w));
                     float intensity = __ldg(reinterpret_cast<const float4*>(sc.mats + __ldg(&sc.sph_c[h.prim]).y) + 1).y;
                     A = texture_leaf_value(sc, pt, t, n, p) * intensity + bloom;
@@ -210,19 +228,19 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
                     const U4 rn = rng_block(rp.seed, pixel, sample, bounce, 0);
                     V3 att;
                     bool scattered = true;
-                    if (kind == Q_METAL) {
+                    if (kind_now == Q_METAL) {
                         DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
                         att = mk(m.ax, m.ay, m.az);
                         scattered = scatter_metal(q, p, n, m.param, rn, r);
-                    } else if (kind == Q_DIEL) {
+                    } else if (kind_now == Q_DIEL) {
                         DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
                         att = mk(m.ax, m.ay, m.az);
                         scatter_dielectric(q, p, n, m.param, rn, r);
                     } else {
                         DTexture t = load_tex(sc, int32_t(ids.w));
-                        if (kind == Q_LAMB_CONST) att = tex_constant(t);
-                        else if (kind == Q_LAMB_NOISE1) att = t.kind == RT_TEX_WOOD ? tex_wood(pt, t, p) : tex_perlin(pt, t, p);
-                        else if (kind == Q_LAMB_NOISE6) att = t.kind == RT_TEX_NOISE_MARBLE ? tex_marble(pt, t, p) : tex_turbulence(pt, t, p);
+                        if (kind_now == Q_LAMB_CONST) att = tex_constant(t);
+                        else if (kind_now == Q_LAMB_NOISE1) att = t.kind == RT_TEX_WOOD ? tex_wood(pt, t, p) : tex_perlin(pt, t, p);
+                        else if (kind_now == Q_LAMB_NOISE6) att = t.kind == RT_TEX_NOISE_MARBLE ? tex_marble(pt, t, p) : tex_turbulence(pt, t, p);
                         else att = tex_image(sc, t, n);
                         scatter_lambertian(q, p, n, rn, r);
                     }
@@ -280,18 +298,24 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
             if (out_q != Q_NONE) {
                 const int leader = __ffs(peers) - 1;
                 uint32_t base = 0;
-                if (int(lane) == leader) base = atomicAdd(&s_count[out_q], uint32_t(__popc(peers)));
+                if (int(lane) == leader) base = atomicAdd(&s_count[cpar][out_q], uint32_t(__popc(peers)));
                 base = __shfl_sync(peers, base, leader);
                 local = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
             }
         }
+#ifndef WF_NO_PREFETCH
+        if (valid_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(wb.rec + slot_next));
+#endif
         __syncthreads();
         if (threadIdx.x < NQ) {
-            uint32_t c = s_count[threadIdx.x];
-            s_base[threadIdx.x] = c ? atomicAdd(cnt_next + threadIdx.x, c) : 0u;
+            uint32_t c = s_count[cpar][threadIdx.x];
+            s_base[cpar][threadIdx.x] = c ? atomicAdd(cnt_next + threadIdx.x, c) : 0u;
+            s_count[cpar ^ 1u][threadIdx.x] = 0u; // the other buffer was last read before the barrier above
         }
         __syncthreads();
-        if (out_q != Q_NONE) wf_queue(wb, par_next, out_q)[s_base[out_q] + local] = slot;
+        if (out_q != Q_NONE) wf_queue(wb, par_next, out_q)[s_base[cpar][out_q] + local] = slot;
+        cpar ^= 1u;
+        slot = slot_next;
     }
 
     for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
@@ -303,7 +327,7 @@ __global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_slots) wf_queue(wb, 0, Q_NEW)[i] = i;
     if (i < 3 * NQ) wb.counts[i] = (i == Q_NEW) ? n_slots : 0u;
-    if (i == 0) *wb.next_path = 0ull;
+    if (i == 0) wb.next_path[0] = wb.next_path[1] = 0ull;
 }
 
 WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st) {
@@ -313,7 +337,7 @@ WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st) {
     bool ok = cudaMalloc(&ws->b.rec, pool_paths * sizeof(WfRecord)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.queue, size_t(2) * NQ * pool_paths * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.counts, 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && cudaMalloc(&ws->b.next_path, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ws->b.next_path, 2 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ws->h_status, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ws->h_counts, 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
     if (!ok) {
@@ -374,7 +398,7 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
             ++*launches;
         }
         cudaMemcpyAsync(ws->h_counts, wb.counts, 3 * NQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(ws->h_status, wb.next_path, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(ws->h_status, wb.next_path + (it & 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) break;
         const uint32_t* c = ws->h_counts + (it % 3) * NQ; // queues the NEXT iteration would read
         uint64_t live = 0;
