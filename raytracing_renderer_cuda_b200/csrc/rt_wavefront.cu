@@ -50,6 +50,7 @@ struct WfBuffers {
     WfRecord* rec;               // [pool]
     uint32_t* queue;             // [2][NQ][pool]
     uint32_t* counts;            // [3][NQ] queue sizes, rotating: cur / next / being-zeroed
+    uint32_t* tickets;           // [3] chunk ticket counters, same rotation
     unsigned long long* next_path; // [2], rotating: [it & 1] = paths started before iteration `it`
     uint32_t pool;
 };
@@ -98,9 +99,135 @@ RT_DEV int classify_hit(const DScene& sc, const DRenderParams& rp, const RayQ& q
     }
 }
 
+// One queue entry: shade the pending hit of `slot` (or generate a camera ray for path `path`), scatter, extend
+// the new ray, classify its hit and store the record.  Returns the queue the slot goes to next (Q_NONE: retired).
+template <bool USE_BVH>
+RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind,
+                            bool valid, uint32_t slot, unsigned long long path, unsigned long long npix,
+                            unsigned long long npaths, float4* __restrict__ accum, unsigned long long& nrays) {
+    const V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
+    WfRecord* rec = wb.rec + slot;
+
+    bool has_ray = false;   // a ray to extend
+    bool finished = false;  // path ended: add `A` to the pixel
+    bool slot_free = false; // hand the slot to Q_NEW
+    Ray r;
+    V3 A = mk(0.f, 0.f, 0.f);
+    uint32_t pixel = 0, sample = 0, bounce = 0;
+
+    if (valid) {
+        if (kind == Q_NEW) {
+            if (path < npaths) {
+                pixel = uint32_t(path % npix);
+                sample = uint32_t(path / npix) + uint32_t(rp.sample_offset);
+                A = mk(rp.world_r, rp.world_g, rp.world_b);
+                if (rp.max_depth > 0) {
+                    r = camera_ray(sc, rp, pixel, sample);
+                    has_ray = true;
+                } else { // exceeded recursion before the first hit test (main.cu:42,70)
+                    A = mk(0.f, 0.f, 0.f);
+                    finished = true;
+                    slot_free = true;
+                }
+            } // else: no paths left; the slot retires
+        } else {
+            const float4 ro = rec->o, rd = rec->d, ra = rec->a;
+            const uint4 ids = rec->ids;
+            pixel = ids.x;
+            sample = ids.y;
+            bounce = ids.z;
+            RayQ q;
+            q.o = mk(ro.x, ro.y, ro.z);
+            q.d = mk(rd.x, rd.y, rd.z);
+            q.time = ro.w;
+            q.a = 0.f; // not needed for shading
+            Hit h{rd.w, __float_as_uint(ra.w)};
+            A = mk(ra.x, ra.y, ra.z);
+            V3 p, n;
+            hit_surface(sc, q, h, p, n);
+            if (kind == Q_EMIT) { // emitter::emit (material.h:50-52): value = tex * intensity + bloom; A is dropped
+                DTexture t = load_tex(sc, int32_t(ids.w));
+                float intensity = __ldg(reinterpret_cast<const float4*>(sc.mats + __ldg(&sc.sph_c[h.prim]).y) + 1).y;
+                A = texture_leaf_value(sc, pt, t, n, p) * intensity + bloom;
+                finished = true;
+                slot_free = true;
+            } else {
+                const V3 E = mk(0.f, 0.f, 0.f) + bloom; // material::emit (material.h:14-16) + bloom
+                const U4 rn = rng_block(rp.seed, pixel, sample, bounce, 0);
+                V3 att;
+                bool scattered = true;
+                if (kind == Q_METAL) {
+                    DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
+                    att = mk(m.ax, m.ay, m.az);
+                    scattered = scatter_metal(q, p, n, m.param, rn, r);
+                } else if (kind == Q_DIEL) {
+                    DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
+                    att = mk(m.ax, m.ay, m.az);
+                    scatter_dielectric(q, p, n, m.param, rn, r);
+                } else {
+                    DTexture t = load_tex(sc, int32_t(ids.w));
+                    if (kind == Q_LAMB_CONST) att = tex_constant(t);
+                    else if (kind == Q_LAMB_NOISE1) att = t.kind == RT_TEX_WOOD ? tex_wood(pt, t, p) : tex_perlin(pt, t, p);
+                    else if (kind == Q_LAMB_NOISE6) att = t.kind == RT_TEX_NOISE_MARBLE ? tex_marble(pt, t, p) : tex_turbulence(pt, t, p);
+                    else att = tex_image(sc, t, n);
+                    scatter_lambertian(q, p, n, rn, r);
+                }
+                if (!scattered) { // absorbed (material.h:129-130): the path's value is E (main.cu:53-54)
+                    A = E;
+                    finished = true;
+                    slot_free = true;
+                } else {
+                    A = E + att * A; // main.cu:51
+                    if (int(bounce) >= rp.max_depth) { // exceeded recursion (main.cu:70)
+                        A = mk(0.f, 0.f, 0.f);
+                        finished = true;
+                        slot_free = true;
+                    } else {
+                        has_ray = true;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- extend: closest hit of the new ray, classification into the next queues ----
+    int out_q = Q_NONE;
+    if (has_ray) {
+        RayQ q = make_rayq(r);
+        Hit h = USE_BVH ? closest_hit_bvh(sc, q, rp.tmin) : closest_hit_list(sc, q, rp.tmin);
+        ++nrays;
+        ++bounce;
+        if (h.prim == RT_INVALID_ID) { // miss: the path's value is A (main.cu:66-67)
+            finished = true;
+            slot_free = true;
+        } else {
+            int32_t leaf;
+            V3 value;
+            out_q = classify_hit(sc, rp, q, h, leaf, value);
+            if (out_q == Q_NONE) { // constant emitter: terminate here
+                A = value;
+                finished = true;
+                slot_free = true;
+            } else {
+                rec->o = make_float4(r.o.x, r.o.y, r.o.z, r.time);
+                rec->d = make_float4(r.d.x, r.d.y, r.d.z, h.t);
+                rec->a = make_float4(A.x, A.y, A.z, __uint_as_float(h.prim));
+                rec->ids = make_uint4(pixel, sample, bounce, uint32_t(leaf));
+            }
+        }
+    }
+    if (finished) atomicAdd(&accum[pixel], make_float4(A.x, A.y, A.z, 1.f));
+    if (slot_free) out_q = Q_NEW;
+    return out_q;
+}
+
+// Work granularity, variant 1: a CTA takes 256 consecutive entries of ONE queue and aggregates its pushes in shared
+// memory: one global atomic per CTA chunk and target queue, two block-wide barriers per chunk.  Best when all
+// rays of a chunk cost the same (brute-force scenes): C1 runs 11 % faster this way than with warp chunks, whose
+// four-fold atomic traffic (~1 atomic per 3.5 ns and queue counter) saturates the L2 atomic units.
 template <bool USE_BVH>
 __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
-    k_wf_step(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
+    k_wf_step_cta(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t s_count[2][NQ]; // double-buffered by chunk parity: two barriers per chunk instead of four
@@ -141,7 +268,6 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 
     const unsigned long long npix = (unsigned long long)rp.width * rp.height;
     const unsigned long long npaths = npix * (unsigned long long)rp.spp;
-    const V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
     unsigned long long nrays = 0;
 
     // chunk -> (queue kind, first entry)
@@ -174,122 +300,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
             if (valid_next) slot_next = __ldg(wf_queue(wb, par_cur, kind) + first + threadIdx.x);
         }
 
-        WfRecord* rec = wb.rec + slot;
-
-        // ray-gen chunks: path id = (paths started before this iteration) + position in the ray-gen queue.
-        // The running total is carried from launch to launch by block 0 (no atomics, no hand-off barrier).
-        const unsigned long long path = path_base + idx;
-
-        bool has_ray = false;   // a ray to extend
-        bool finished = false;  // path ended: add `A` to the pixel
-        bool slot_free = false; // hand the slot to Q_NEW
-        Ray r;
-        V3 A = mk(0.f, 0.f, 0.f);
-        uint32_t pixel = 0, sample = 0, bounce = 0;
-
-        if (valid) {
-            if (kind_now == Q_NEW) {
-                if (path < npaths) {
-                    pixel = uint32_t(path % npix);
-                    sample = uint32_t(path / npix) + uint32_t(rp.sample_offset);
-                    A = mk(rp.world_r, rp.world_g, rp.world_b);
-                    if (rp.max_depth > 0) {
-                        r = camera_ray(sc, rp, pixel, sample);
-                        has_ray = true;
-                    } else { // exceeded recursion before the first hit test (main.cu:42,70)
-                        A = mk(0.f, 0.f, 0.f);
-                        finished = true;
-                        slot_free = true;
-                    }
-                } // else: no paths left; the slot retires
-            } else {
-                const float4 ro = rec->o, rd = rec->d, ra = rec->a;
-                const uint4 ids = rec->ids;
-                pixel = ids.x;
-                sample = ids.y;
-                bounce = ids.z;
-                RayQ q;
-                q.o = mk(ro.x, ro.y, ro.z);
-                q.d = mk(rd.x, rd.y, rd.z);
-                q.time = ro.w;
-                q.a = 0.f; // not needed for shading
-                Hit h{rd.w, __float_as_uint(ra.w)};
-                A = mk(ra.x, ra.y, ra.z);
-                V3 p, n;
-                hit_surface(sc, q, h, p, n);
-                if (kind_now == Q_EMIT) { // emitter::emit (material.h:50-52): value = tex * intensity + bloom; A is dropped
-                    DTexture t = load_tex(sc, int32_t(ids.w));
-                    float intensity = __ldg(reinterpret_cast<const float4*>(sc.mats + __ldg(&sc.sph_c[h.prim]).y) + 1).y;
-                    A = texture_leaf_value(sc, pt, t, n, p) * intensity + bloom;
-                    finished = true;
-                    slot_free = true;
-                } else {
-                    const V3 E = mk(0.f, 0.f, 0.f) + bloom; // material::emit (material.h:14-16) + bloom
-                    const U4 rn = rng_block(rp.seed, pixel, sample, bounce, 0);
-                    V3 att;
-                    bool scattered = true;
-                    if (kind_now == Q_METAL) {
-                        DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
-                        att = mk(m.ax, m.ay, m.az);
-                        scattered = scatter_metal(q, p, n, m.param, rn, r);
-                    } else if (kind_now == Q_DIEL) {
-                        DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
-                        att = mk(m.ax, m.ay, m.az);
-                        scatter_dielectric(q, p, n, m.param, rn, r);
-                    } else {
-                        DTexture t = load_tex(sc, int32_t(ids.w));
-                        if (kind_now == Q_LAMB_CONST) att = tex_constant(t);
-                        else if (kind_now == Q_LAMB_NOISE1) att = t.kind == RT_TEX_WOOD ? tex_wood(pt, t, p) : tex_perlin(pt, t, p);
-                        else if (kind_now == Q_LAMB_NOISE6) att = t.kind == RT_TEX_NOISE_MARBLE ? tex_marble(pt, t, p) : tex_turbulence(pt, t, p);
-                        else att = tex_image(sc, t, n);
-                        scatter_lambertian(q, p, n, rn, r);
-                    }
-                    if (!scattered) { // absorbed (material.h:129-130): the path's value is E (main.cu:53-54)
-                        A = E;
-                        finished = true;
-                        slot_free = true;
-                    } else {
-                        A = E + att * A; // main.cu:51
-                        if (int(bounce) >= rp.max_depth) { // exceeded recursion (main.cu:70)
-                            A = mk(0.f, 0.f, 0.f);
-                            finished = true;
-                            slot_free = true;
-                        } else {
-                            has_ray = true;
-                        }
-                    }
-                }
-            }
-        }
-
-        // ---- extend: closest hit of the new ray, classification into the next queues ----
-        int out_q = Q_NONE;
-        if (has_ray) {
-            RayQ q = make_rayq(r);
-            Hit h = USE_BVH ? closest_hit_bvh(sc, q, rp.tmin) : closest_hit_list(sc, q, rp.tmin);
-            ++nrays;
-            ++bounce;
-            if (h.prim == RT_INVALID_ID) { // miss: the path's value is A (main.cu:66-67)
-                finished = true;
-                slot_free = true;
-            } else {
-                int32_t leaf;
-                V3 value;
-                out_q = classify_hit(sc, rp, q, h, leaf, value);
-                if (out_q == Q_NONE) { // constant emitter: terminate here
-                    A = value;
-                    finished = true;
-                    slot_free = true;
-                } else {
-                    rec->o = make_float4(r.o.x, r.o.y, r.o.z, r.time);
-                    rec->d = make_float4(r.d.x, r.d.y, r.d.z, h.t);
-                    rec->a = make_float4(A.x, A.y, A.z, __uint_as_float(h.prim));
-                    rec->ids = make_uint4(pixel, sample, bounce, uint32_t(leaf));
-                }
-            }
-        }
-        if (finished) atomicAdd(&accum[pixel], make_float4(A.x, A.y, A.z, 1.f));
-        if (slot_free) out_q = Q_NEW;
+        const int out_q = wf_process_entry<USE_BVH>(sc, rp, wb, pt, kind_now, valid, slot, path_base + idx, npix, npaths, accum, nrays);
 
         // ---- queue push: warp ballot -> shared counters -> one global atomic per queue ----
         uint32_t local = 0;
@@ -322,11 +333,132 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
 }
 
+
+// Work granularity, variant 2: a WARP draws WF_WCHUNK consecutive entries of ONE queue (WF_ROUNDS rounds of 32) from a
+// ticket counter and pushes its results with one global atomic per target queue.  No block-wide barrier inside the
+// loop: a warp whose rays finish early moves on instead of waiting for the slowest BVH traversal of the CTA
+// (ncu, C2: 21 % of all stall samples sat on that barrier; C2 runs 14 % faster this way, C3 4 %).
+#ifndef WF_ROUNDS
+#define WF_ROUNDS 1
+#endif
+#define WF_WCHUNK (32 * WF_ROUNDS)
+
+template <bool USE_BVH>
+__global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
+    k_wf_step_warp(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
+              int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
+    extern __shared__ __align__(16) uint32_t smem[];
+
+    const PerlinTab pt{smem, threadIdx.x & 31u};
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    const uint32_t* cnt_cur = wb.counts + (it % 3) * NQ;
+    uint32_t* cnt_next = wb.counts + ((it + 1) % 3) * NQ;
+    if (blockIdx.x == 0 && threadIdx.x < NQ) wb.counts[((it + 2) % 3) * NQ + threadIdx.x] = 0; // next iteration's target
+    uint32_t* ticket = wb.tickets + (it % 3); // dynamic chunk distribution: warps draw chunk numbers from here
+    if (blockIdx.x == 0 && threadIdx.x == 0) wb.tickets[(it + 2) % 3] = 0u;
+    const unsigned long long path_base = wb.next_path[it & 1]; // paths started by earlier iterations
+    const int par_cur = it & 1, par_next = par_cur ^ 1;
+
+    uint32_t n_q[NQ], chunk_end[NQ];
+    uint32_t total_chunks = 0;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) n_q[k] = __ldg(cnt_cur + k);
+    // chunk order, most expensive classes first so the long chunks start early:
+    // NOISE6, NOISE1, IMAGE, EMIT, DIEL, METAL, LAMB_CONST, NEW
+    const int order[NQ] = {Q_LAMB_NOISE6, Q_LAMB_NOISE1, Q_LAMB_IMAGE, Q_EMIT, Q_DIEL, Q_METAL, Q_LAMB_CONST, Q_NEW};
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        total_chunks += (n_q[order[k]] + WF_WCHUNK - 1) / WF_WCHUNK;
+        chunk_end[k] = total_chunks;
+    }
+
+    // Tail iterations hold a few hundred live paths: CTAs without a chunk leave before staging anything, and
+    // the 32 KB Perlin table is staged only by CTAs that will run a noise shader (their first chunk is the
+    // lowest-numbered one they get, and the noise queues come first; textured emitters may need it too).
+    if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
+    const uint32_t warps_per_cta = WF_THREADS / 32;
+    if (blockIdx.x * warps_per_cta >= total_chunks) return;
+    if (chunk_end[1] != 0u || n_q[Q_EMIT] != 0u) perlin_stage(smem, threadIdx.x, blockDim.x);
+    __syncthreads(); // the only block-wide barrier of the kernel
+
+    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
+    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+    unsigned long long nrays = 0;
+
+    // Chunks are handed out dynamically (heavy classes first) so no warp idles at the end of the launch; the
+    // ticket for the NEXT chunk is drawn before the current one is processed, which hides the atomic's latency.
+    auto draw = [&]() -> uint32_t {
+        uint32_t c = 0u;
+        if (lane == 0u) c = atomicAdd(ticket, 1u);
+        return c;
+    };
+    uint32_t ticket_next = draw();
+    for (;;) {
+        const uint32_t chunk = __shfl_sync(0xffffffffu, ticket_next, 0);
+        if (chunk >= total_chunks) break;
+        ticket_next = draw();
+        int kpos = 0;
+#pragma unroll
+        for (int k = 0; k < NQ - 1; ++k) kpos += (chunk >= chunk_end[k]) ? 1 : 0;
+        const int kind = order[kpos];
+        const uint32_t first = (chunk - (kpos ? chunk_end[kpos - 1] : 0u)) * WF_WCHUNK;
+        const uint32_t n_kind = n_q[kind];
+        const uint32_t* q_in = wf_queue(wb, par_cur, kind);
+
+        uint32_t outq_pack = 0u; // 4 bits per round: target queue + 1 (0 = none)
+
+#pragma unroll 1
+        for (int e = 0; e < WF_ROUNDS; ++e) {
+            const uint32_t idx = first + uint32_t(e) * 32u + lane;
+            const bool valid = idx < n_kind;
+            const uint32_t slot = valid ? __ldg(q_in + idx) : 0u;
+            const int out_q = wf_process_entry<USE_BVH>(sc, rp, wb, pt, kind, valid, slot, path_base + idx, npix, npaths, accum, nrays);
+            outq_pack |= uint32_t(out_q + 1) << (4 * e);
+        }
+
+        // ---- queue push: ballots over all rounds -> ONE global atomic per target queue and warp chunk ----
+        // lane q (< NQ) owns queue q: it sums the warp's pushes to q, reserves the range, and hands the base out.
+        uint32_t my_total = 0u;
+        uint32_t rank_r[WF_ROUNDS];
+#pragma unroll
+        for (int e = 0; e < WF_ROUNDS; ++e) rank_r[e] = 0u;
+#pragma unroll
+        for (int qk = 0; qk < NQ; ++qk) {
+            uint32_t run = 0u;
+#pragma unroll
+            for (int e = 0; e < WF_ROUNDS; ++e) {
+                const bool mine = ((outq_pack >> (4 * e)) & 15u) == uint32_t(qk + 1);
+                const unsigned b = __ballot_sync(0xffffffffu, mine);
+                if (mine) rank_r[e] = run + uint32_t(__popc(b & lt_mask));
+                run += uint32_t(__popc(b));
+            }
+            if (int(lane) == qk) my_total = run;
+        }
+        uint32_t my_base = 0u;
+        if (lane < uint32_t(NQ) && my_total) my_base = atomicAdd(cnt_next + lane, my_total);
+#pragma unroll
+        for (int e = 0; e < WF_ROUNDS; ++e) {
+            const uint32_t oq1 = (outq_pack >> (4 * e)) & 15u; // queue + 1
+            const uint32_t base = __shfl_sync(0xffffffffu, my_base, int(oq1 + 31u) & 31);
+            if (oq1) { // the slot index is re-read from the input queue (an L1 hit) instead of living in a register
+                const uint32_t slot = __ldg(q_in + first + uint32_t(e) * 32u + lane);
+                wf_queue(wb, par_next, int(oq1) - 1)[base + rank_r[e]] = slot;
+            }
+        }
+    }
+
+    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
+    if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
+}
+
 // fills Q_NEW of iteration 0 with every slot and resets the path counter
 __global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_slots) wf_queue(wb, 0, Q_NEW)[i] = i;
     if (i < 3 * NQ) wb.counts[i] = (i == Q_NEW) ? n_slots : 0u;
+    if (i < 3) wb.tickets[i] = 0u;
     if (i == 0) wb.next_path[0] = wb.next_path[1] = 0ull;
 }
 
@@ -337,6 +469,7 @@ WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st) {
     bool ok = cudaMalloc(&ws->b.rec, pool_paths * sizeof(WfRecord)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.queue, size_t(2) * NQ * pool_paths * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.counts, 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ws->b.tickets, 3 * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.next_path, 2 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ws->h_status, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ws->h_counts, 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
@@ -352,6 +485,7 @@ void wavefront_destroy(WavefrontState* ws) {
     if (ws->b.rec) cudaFree(ws->b.rec);
     if (ws->b.queue) cudaFree(ws->b.queue);
     if (ws->b.counts) cudaFree(ws->b.counts);
+    if (ws->b.tickets) cudaFree(ws->b.tickets);
     if (ws->b.next_path) cudaFree(ws->b.next_path);
     if (ws->h_status) cudaFreeHost(ws->h_status);
     if (ws->h_counts) cudaFreeHost(ws->h_counts);
@@ -370,8 +504,10 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     static bool attr_set = false;
     const size_t smem = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
     if (!attr_set) {
-        cudaFuncSetAttribute(k_wf_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        cudaFuncSetAttribute(k_wf_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaFuncSetAttribute(k_wf_step_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaFuncSetAttribute(k_wf_step_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaFuncSetAttribute(k_wf_step_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaFuncSetAttribute(k_wf_step_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         attr_set = true;
     }
     // slots in use: never more than there are paths
@@ -380,9 +516,20 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     k_wf_init<<<(slots + 255) / 256 > 0 ? (slots + 255) / 256 : 1, 256, 0, st>>>(wb, slots);
     ++*launches;
 
-    const unsigned grid_cap = unsigned(sm_count) * 8u;
-    const unsigned grid_need = (slots + WF_THREADS - 1) / WF_THREADS + NQ;
-    const unsigned grid = grid_need < grid_cap ? grid_need : grid_cap;
+    // Granularity: warp chunks (barrier-free, ticketed) when rays cost unevenly — BVH traversal —, CTA chunks
+    // (4x fewer queue atomics) when they cost the same — the brute-force list.  RT_WF_GRAIN=cta|warp overrides.
+    bool warp_grain = use_bvh;
+    if (const char* e = getenv("RT_WF_GRAIN")) warp_grain = (e[0] == 'w');
+    unsigned grid;
+    if (warp_grain) { // resident CTAs only: work is drawn dynamically
+        const unsigned cap = unsigned(sm_count) * WF_MINBLOCKS;
+        const unsigned need = (slots + WF_WCHUNK * (WF_THREADS / 32) - 1) / (WF_WCHUNK * (WF_THREADS / 32)) + NQ;
+        grid = need < cap ? need : cap;
+    } else { // two waves of CTAs, chunks by stride
+        const unsigned cap = unsigned(sm_count) * 8u;
+        const unsigned need = (slots + WF_THREADS - 1) / WF_THREADS + NQ;
+        grid = need < cap ? need : cap;
+    }
 
     uint32_t it = 0;
     // Iterations are enqueued in batches; between batches the host reads back the queue
@@ -391,10 +538,13 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     const uint32_t max_iters = 4u * (uint32_t(rp.max_depth) + 2u) + 64u * uint32_t((npaths + slots - 1) / slots);
     while (true) {
         for (uint32_t k = 0; k < batch; ++k, ++it) {
-            if (use_bvh)
-                k_wf_step<true><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
-            else
-                k_wf_step<false><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
+            if (warp_grain) {
+                if (use_bvh) k_wf_step_warp<true><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
+                else k_wf_step_warp<false><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
+            } else {
+                if (use_bvh) k_wf_step_cta<true><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
+                else k_wf_step_cta<false><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
+            }
             ++*launches;
         }
         cudaMemcpyAsync(ws->h_counts, wb.counts, 3 * NQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
