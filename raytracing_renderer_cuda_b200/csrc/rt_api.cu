@@ -234,8 +234,9 @@ rt_status render_into(rt_context* ctx, const rt_scene* scene, const rt_render_pa
     } else {
         const size_t npaths = size_t(p->width) * size_t(p->height) * size_t(p->spp);
         // pool of path slots (RT_WF_POOL overrides).  Measured on C1 (ms/frame): 256 Ki 18.7, 512 Ki 14.7, 1 Mi 13.5,
-        // 2 Mi 12.6, 4 Mi 12.4 — fewer, fuller iterations beat keeping the 64-byte records L2-resident.
-        size_t pool_cap = size_t(4) << 20;
+        // 2 Mi 12.6, 4 Mi 12.4 (before the later kernel work), then 4 Mi 11.0, 8 Mi 11.0, 16 Mi 10.5 — fewer, fuller
+        // iterations beat keeping the 64-byte records L2-resident.  16 Mi slots = 1 GiB of records + 1 GiB of queues.
+        size_t pool_cap = size_t(16) << 20;
         if (const char* e = getenv("RT_WF_POOL")) {
             long long v = atoll(e);
             if (v >= 1024 && v <= (1ll << 28)) pool_cap = size_t(v);

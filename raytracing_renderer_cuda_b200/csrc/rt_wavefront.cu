@@ -22,8 +22,8 @@
 // to the float4 accumulator with a single vector reduction (RED.ADD.F32x4) and hand their
 // slot to Q_NEW, so the pool stays full until the frame's paths run out (path regeneration).
 //
-// The pool is sized to stay resident in B200's 126 MB L2 (default 1 Mi slots = 64 MiB of
-// records), so queue and record traffic is L2 traffic, not HBM traffic.
+// Pool size: measured, bigger is better up to 16 Mi slots (rt_api.cu) — the records stream through HBM at ~25 %
+// of its bandwidth (ncu: 119 B per slot and iteration, the algorithmic 120 B/ray), far from being the limit.
 #include <cstdio>
 #include <cstdlib>
 
