@@ -334,6 +334,7 @@ rt_status rt_context_create(int device, rt_context** out) {
 void rt_context_destroy(rt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream); // polling copies of the last render may still be in flight
     if (ctx->wf) rtd::wavefront_destroy(ctx->wf);
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->out_rgb) cudaFree(ctx->out_rgb);

@@ -142,35 +142,33 @@ RT_DEV Hit closest_hit_bvh(const DScene& sc, const RayQ& q, float tmin) {
     int stack[RT_BVH_STACK];
     int sp = 0;
     int node = 0;
+    const int kDone = 0x7fffffff;
+    // "while-while" traversal: leaves travel through `node` and the stack like inner nodes, so the lanes of a
+    // warp first all descend through inner nodes and then test their pending leaves together, instead of each
+    // lane stopping for a sphere test in the middle of the others' descent.
     while (true) {
-        const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
-        float4 lmin = __ldg(np + 0), lmax = __ldg(np + 1), rmin = __ldg(np + 2), rmax = __ldg(np + 3);
-        float tl, tr;
-        bool hl = slab(lmin, lmax, q.o, inv, tmin, best.t, tl);
-        bool hr = slab(rmin, rmax, q.o, inv, tmin, best.t, tr);
-        int cl = __float_as_int(lmin.w), cr = __float_as_int(lmax.w);
-        if (hl && cl < 0) {
-            test_prim(sc, q, uint32_t(~cl), tmin, best);
-            hl = false;
+        while (node >= 0 && node != kDone) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+            float4 lmin = __ldg(np + 0), lmax = __ldg(np + 1), rmin = __ldg(np + 2), rmax = __ldg(np + 3);
+            float tl, tr;
+            const bool hl = slab(lmin, lmax, q.o, inv, tmin, best.t, tl);
+            const bool hr = slab(rmin, rmax, q.o, inv, tmin, best.t, tr);
+            const int cl = __float_as_int(lmin.w), cr = __float_as_int(lmax.w);
+            if (hl && hr) {
+                const bool left_first = tl <= tr;
+                if (sp < RT_BVH_STACK) stack[sp++] = left_first ? cr : cl;
+                node = left_first ? cl : cr;
+            } else if (hl) {
+                node = cl;
+            } else if (hr) {
+                node = cr;
+            } else {
+                node = sp ? stack[--sp] : kDone;
+            }
         }
-        if (hr && cr < 0) {
-            test_prim(sc, q, uint32_t(~cr), tmin, best);
-            hr = false;
-        }
-        if (hl && hr) {
-            bool left_first = tl <= tr;
-            int nearc = left_first ? cl : cr;
-            int farc = left_first ? cr : cl;
-            if (sp < RT_BVH_STACK) stack[sp++] = farc;
-            node = nearc;
-        } else if (hl) {
-            node = cl;
-        } else if (hr) {
-            node = cr;
-        } else {
-            if (sp == 0) break;
-            node = stack[--sp];
-        }
+        if (node == kDone) break;
+        test_prim(sc, q, uint32_t(~node), tmin, best);
+        node = sp ? stack[--sp] : kDone;
     }
     return best;
 }

@@ -13,14 +13,14 @@
 //   Q_EMIT        emitter with a non-constant texture (constant emitters and misses
 //                 terminate inside the extend step: "shadow/emission")
 //
-// A CTA takes a 256-entry chunk of ONE queue, so every warp runs one shader with all lanes
-// doing the same thing (the reference's megakernel mixes all of them in every warp).  The
-// shade step produces the scattered ray, the same thread extends it (closest hit), classifies
-// the hit and pushes its slot into the matching queue of the next iteration.  Pushes are
-// compacted with __match_any_sync ballots, aggregated per warp into shared-memory counters
-// and then into ONE global atomic per (CTA chunk, queue).  Terminated paths add their value
-// to the float4 accumulator with a single vector reduction (RED.ADD.F32x4) and hand their
-// slot to Q_NEW, so the pool stays full until the frame's paths run out (path regeneration).
+// Work is handed out in chunks of consecutive entries of ONE queue, so every warp runs one shader with all
+// lanes doing the same thing (the reference's megakernel mixes all of them in every warp).  The shade step
+// produces the scattered ray, the same thread extends it (closest hit), classifies the hit and pushes its slot
+// into the matching queue of the next iteration.  Pushes are compacted with warp ballots and aggregated into
+// one global atomic per (chunk, queue); two chunk granularities exist (CTA chunks / ticketed warp chunks, see
+// the two kernels below).  Terminated paths add their value to the float4 accumulator with a single vector
+// reduction (RED.ADD.F32x4) and hand their slot to Q_NEW, so the pool stays full until the frame's paths run
+// out (path regeneration).
 //
 // Pool size: measured, bigger is better up to 16 Mi slots (rt_api.cu) — the records stream through HBM at ~25 %
 // of its bandwidth (ncu: 119 B per slot and iteration, the algorithmic 120 B/ray), far from being the limit.
@@ -57,8 +57,9 @@ struct WfBuffers {
 
 struct WavefrontState {
     WfBuffers b{};
-    unsigned long long* h_status = nullptr; // pinned: [0] next_path, [1..NQ] counts of the polled buffer
-    uint32_t* h_counts = nullptr;
+    unsigned long long* h_status = nullptr; // pinned [2]: paths started, one per polling parity
+    uint32_t* h_counts = nullptr;           // pinned [2][3 * NQ]: queue sizes, one copy per polling parity
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
 };
 
@@ -471,8 +472,10 @@ WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st) {
     ok = ok && cudaMalloc(&ws->b.counts, 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.tickets, 3 * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.next_path, 2 * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMallocHost(&ws->h_status, sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMallocHost(&ws->h_counts, 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ws->h_status, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ws->h_counts, 2 * 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ws->poll_ev[0], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ws->poll_ev[1], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         wavefront_destroy(ws);
         return nullptr;
@@ -487,6 +490,8 @@ void wavefront_destroy(WavefrontState* ws) {
     if (ws->b.counts) cudaFree(ws->b.counts);
     if (ws->b.tickets) cudaFree(ws->b.tickets);
     if (ws->b.next_path) cudaFree(ws->b.next_path);
+    for (auto& e : ws->poll_ev)
+        if (e) cudaEventDestroy(e);
     if (ws->h_status) cudaFreeHost(ws->h_status);
     if (ws->h_counts) cudaFreeHost(ws->h_counts);
     delete ws;
@@ -532,12 +537,8 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     }
 
     uint32_t it = 0;
-    // Iterations are enqueued in batches; between batches the host reads back the queue
-    // sizes and the path counter (two small async copies) to decide whether to go on.
-    uint32_t batch = uint32_t((npaths + slots - 1) / slots) + 2; // at least this many are needed
-    const uint32_t max_iters = 4u * (uint32_t(rp.max_depth) + 2u) + 64u * uint32_t((npaths + slots - 1) / slots);
-    while (true) {
-        for (uint32_t k = 0; k < batch; ++k, ++it) {
+    auto enqueue = [&](uint32_t count) {
+        for (uint32_t k = 0; k < count; ++k, ++it) {
             if (warp_grain) {
                 if (use_bvh) k_wf_step_warp<true><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
                 else k_wf_step_warp<false><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
@@ -547,24 +548,37 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
             }
             ++*launches;
         }
-        cudaMemcpyAsync(ws->h_counts, wb.counts, 3 * NQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(ws->h_status, wb.next_path + (it & 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-        if (cudaStreamSynchronize(st) != cudaSuccess) break;
-        const uint32_t* c = ws->h_counts + (it % 3) * NQ; // queues the NEXT iteration would read
+    };
+    // Iterations are enqueued in batches.  After each batch the queue sizes and the path counter are copied to
+    // pinned memory; the host looks at the copy of batch k only AFTER batch k+1 has been enqueued, so the GPU
+    // never waits for the host.  Once the frame is finished the launches still in flight find empty queues and
+    // return immediately (every CTA exits before touching anything).
+    struct Polled {
+        uint32_t it_after; // iterations enqueued when the snapshot was requested
+    } polled[2];
+    auto snapshot = [&](int par) {
+        cudaMemcpyAsync(ws->h_counts + par * 3 * NQ, wb.counts, 3 * NQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(ws->h_status + par, wb.next_path + (it & 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(ws->poll_ev[par], st);
+        polled[par].it_after = it;
+    };
+    const uint32_t generations = uint32_t((npaths + slots - 1) / slots);
+    const uint32_t max_iters = 4u * (uint32_t(rp.max_depth) + 2u) + 64u * generations;
+    enqueue(2u * generations + 4u); // a path lives ~2 iterations: enough to start most of the frame
+    snapshot(0);
+    int par = 0;
+    while (true) {
+        enqueue(8u);
+        snapshot(par ^ 1);
+        if (cudaEventSynchronize(ws->poll_ev[par]) != cudaSuccess) break;
+        const uint32_t* c = ws->h_counts + par * 3 * NQ + (polled[par].it_after % 3) * NQ; // queues of the next iteration
         uint64_t live = 0;
         for (int k = 0; k < NQ; ++k)
             if (k != Q_NEW) live += c[k];
-        const unsigned long long started = *ws->h_status;
+        const unsigned long long started = ws->h_status[par];
         if (live == 0 && (started >= npaths || c[Q_NEW] == 0)) break;
         if (it >= max_iters) break; // safety net; cannot trigger for max_depth-bounded paths
-        if (started < npaths) {
-            // paths started per iteration so far -> iterations still needed to start the rest
-            double per_it = double(started) / double(it ? it : 1);
-            double need = per_it > 0 ? double(npaths - started) / per_it : 8.0;
-            batch = uint32_t(need < 4.0 ? 4.0 : (need > 256.0 ? 256.0 : need)) + 1;
-        } else {
-            batch = 6; // tail: at most max_depth more
-        }
+        par ^= 1;
     }
     *iterations = it;
 }
