@@ -331,10 +331,10 @@ def run_ours(args) -> None:
         dur_launch_s = ms_kernel_span / 1e3 / n_step_launches
         achieved = flop_launch / dur_launch_s / 1e12
         hbm_achieved = rays_rank * STATE_BYTES_PER_RAY / (ms_kernel_span / 1e3) / 1e9
-        traffic = None
+        traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get(args.config)
+            traffic = (json.loads(tp.read_text()).get(args.config) or {}).get("bytes_per_launch")
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -346,7 +346,7 @@ def run_ours(args) -> None:
                        "l2": "flushed between timed steps (256 MiB fill, outside the timed spans)",
                        "timing": "sum of per-step CUDA-event spans on the launching stream, max over ranks"},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": traffic, "kernel": "k_wf_step", "launches_per_step": n_step_launches,
+                         "traffic": traffic, "kernel": "k_wf_step_warp" if int(info.n_nodes) else "k_wf_step_cta", "launches_per_step": n_step_launches,
                          "avg_launch_ms": dur_launch_s * 1e3, "flop_per_ray": FLOP_PER_RAY[args.config],
                          "peak_source": f"148 SM x 128 lanes x 2 flop x {peaks['sm_max_mhz']:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peaks['source']})",
                          "note": "no dense contraction and L2-resident state: the bounding roofline is FP32 issue (SURVEY.md 8d), not hbm/tensor",
@@ -404,12 +404,13 @@ def run_reference(args) -> None:
         sp = Path(td) / "scene.rtsc"
         desc.save(str(sp))
         if args.config == "c4":
-            cap = 100_000  # the reference's single-thread device BVH build cannot do 1M in useful time
+            cap = 10_000  # the reference builds its BVH on ONE device thread, O(N log^2 N) with virtual calls (bvh.h:75-113):
+            #               10^5 spheres did not finish in 20 minutes on a B200, 10^6 is out of reach
             import raytracing_renderer_cuda_b200 as rt
 
             rt.SceneDesc.builtin("random_spheres", n=cap).save(str(sp))
         o = subprocess.run([str(ref / "ref_harness"), "render", str(sp), str(W), str(H), str(spp), str(Path(td) / "o.f32"), "1", "1",
-                            str(max(1, min(args.steps, 3)))], capture_output=True, text=True, timeout=3000)
+                            str(max(1, min(args.steps, 3)))], capture_output=True, text=True, timeout=900)
         if o.returncode == 0:
             info = json.loads(o.stdout.strip().splitlines()[-1])
             kernel_ms, rays = info["ms_render"] + info["ms_init_rand"], info["rays"]

@@ -132,45 +132,60 @@ RT_DEV bool slab(float4 lo, float4 hi, const V3& o, const V3& inv, float tmin, f
 // float4 read-only loads per visited node, near child first, culled by the closest t so far.
 // (Reference: bvh_node::dfs, bvh.h:121-155 — pointer-chasing, unordered, never culls by
 // `closest`, recomputes 1/d for every box: aabb.h:54-68.)
-RT_DEV Hit closest_hit_bvh(const DScene& sc, const RayQ& q, float tmin) {
-    Hit best{FLT_MAX, RT_INVALID_ID};
-    if (sc.n_spheres == 1) {
-        test_prim(sc, q, 0, tmin, best);
-        return best;
+// Resumable traversal state: the persistent wavefront kernel interleaves the traversals of a warp's lanes with
+// refilling finished lanes, so the loop body is exposed as two steps.
+#define RT_TRAV_DONE 0x7fffffff
+struct Trav {
+    int node; // >= 0 inner node, < 0 leaf ~prim, RT_TRAV_DONE finished
+    int sp;
+    Hit best;
+    V3 inv;
+};
+RT_DEV void trav_begin(const RayQ& q, Trav& t) {
+    t.node = 0;
+    t.sp = 0;
+    t.best = Hit{FLT_MAX, RT_INVALID_ID};
+    t.inv = V3{1.0f / q.d.x, 1.0f / q.d.y, 1.0f / q.d.z};
+}
+// one inner-node visit (precondition: t.node >= 0 && t.node != RT_TRAV_DONE)
+RT_DEV void trav_inner(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {
+    const float4* np = reinterpret_cast<const float4*>(sc.nodes + t.node);
+    float4 lmin = __ldg(np + 0), lmax = __ldg(np + 1), rmin = __ldg(np + 2), rmax = __ldg(np + 3);
+    float tl, tr;
+    const bool hl = slab(lmin, lmax, q.o, t.inv, tmin, t.best.t, tl);
+    const bool hr = slab(rmin, rmax, q.o, t.inv, tmin, t.best.t, tr);
+    const int cl = __float_as_int(lmin.w), cr = __float_as_int(lmax.w);
+    if (hl && hr) {
+        const bool left_first = tl <= tr;
+        if (t.sp < RT_BVH_STACK) stack[t.sp++] = left_first ? cr : cl;
+        t.node = left_first ? cl : cr;
+    } else if (hl) {
+        t.node = cl;
+    } else if (hr) {
+        t.node = cr;
+    } else {
+        t.node = t.sp ? stack[--t.sp] : RT_TRAV_DONE;
     }
-    V3 inv{1.0f / q.d.x, 1.0f / q.d.y, 1.0f / q.d.z};
+}
+// one leaf test (precondition: t.node < 0)
+RT_DEV void trav_leaf(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {
+    test_prim(sc, q, uint32_t(~t.node), tmin, t.best);
+    t.node = t.sp ? stack[--t.sp] : RT_TRAV_DONE;
+}
+
+RT_DEV Hit closest_hit_bvh(const DScene& sc, const RayQ& q, float tmin) {
     int stack[RT_BVH_STACK];
-    int sp = 0;
-    int node = 0;
-    const int kDone = 0x7fffffff;
+    Trav t;
+    trav_begin(q, t);
     // "while-while" traversal: leaves travel through `node` and the stack like inner nodes, so the lanes of a
     // warp first all descend through inner nodes and then test their pending leaves together, instead of each
     // lane stopping for a sphere test in the middle of the others' descent.
     while (true) {
-        while (node >= 0 && node != kDone) {
-            const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
-            float4 lmin = __ldg(np + 0), lmax = __ldg(np + 1), rmin = __ldg(np + 2), rmax = __ldg(np + 3);
-            float tl, tr;
-            const bool hl = slab(lmin, lmax, q.o, inv, tmin, best.t, tl);
-            const bool hr = slab(rmin, rmax, q.o, inv, tmin, best.t, tr);
-            const int cl = __float_as_int(lmin.w), cr = __float_as_int(lmax.w);
-            if (hl && hr) {
-                const bool left_first = tl <= tr;
-                if (sp < RT_BVH_STACK) stack[sp++] = left_first ? cr : cl;
-                node = left_first ? cl : cr;
-            } else if (hl) {
-                node = cl;
-            } else if (hr) {
-                node = cr;
-            } else {
-                node = sp ? stack[--sp] : kDone;
-            }
-        }
-        if (node == kDone) break;
-        test_prim(sc, q, uint32_t(~node), tmin, best);
-        node = sp ? stack[--sp] : kDone;
+        while (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner(sc, q, tmin, t, stack);
+        if (t.node == RT_TRAV_DONE) break;
+        trav_leaf(sc, q, tmin, t, stack);
     }
-    return best;
+    return t.best;
 }
 
 RT_DEV Hit closest_hit(const DScene& sc, const RayQ& q, float tmin, bool use_bvh) {

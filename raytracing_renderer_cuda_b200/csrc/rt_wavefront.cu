@@ -100,21 +100,29 @@ RT_DEV int classify_hit(const DScene& sc, const DRenderParams& rp, const RayQ& q
     }
 }
 
-// One queue entry: shade the pending hit of `slot` (or generate a camera ray for path `path`), scatter, extend
-// the new ray, classify its hit and store the record.  Returns the queue the slot goes to next (Q_NONE: retired).
-template <bool USE_BVH>
-RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind,
-                            bool valid, uint32_t slot, unsigned long long path, unsigned long long npix,
-                            unsigned long long npaths, float4* __restrict__ accum, unsigned long long& nrays) {
-    const V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
-    WfRecord* rec = wb.rec + slot;
+// Per-lane state of one queue entry between its shading step and the end of its ray's traversal.
+struct WfLane {
+    uint32_t slot, pixel, sample, bounce;
+    V3 A;
+    Ray r;
+};
 
+// First half of one queue entry: shade the pending hit of `slot` (or generate the camera ray of path `path`) and
+// scatter.  Returns true when a new ray (ln.r) has to be extended.  Otherwise the entry is finished here —
+// emitter, absorbed ray, depth limit, or no path left — and `out_q` says where the slot goes (Q_NEW / Q_NONE).
+RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind, bool valid,
+                     uint32_t slot, unsigned long long path, unsigned long long npix, unsigned long long npaths,
+                     float4* __restrict__ accum, WfLane& ln, int& out_q) {
+    const V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
+    const WfRecord* rec = wb.rec + slot;
     bool has_ray = false;   // a ray to extend
     bool finished = false;  // path ended: add `A` to the pixel
     bool slot_free = false; // hand the slot to Q_NEW
-    Ray r;
     V3 A = mk(0.f, 0.f, 0.f);
     uint32_t pixel = 0, sample = 0, bounce = 0;
+    Ray r;
+    r.o = r.d = mk(0.f, 0.f, 0.f);
+    r.time = 0.f;
 
     if (valid) {
         if (kind == Q_NEW) {
@@ -190,35 +198,62 @@ RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfB
             }
         }
     }
+    if (finished) atomicAdd(&accum[pixel], make_float4(A.x, A.y, A.z, 1.f));
+    out_q = slot_free ? int(Q_NEW) : Q_NONE;
+    ln.slot = slot;
+    ln.pixel = pixel;
+    ln.sample = sample;
+    ln.bounce = bounce;
+    ln.A = A;
+    ln.r = r;
+    return has_ray;
+}
 
-    // ---- extend: closest hit of the new ray, classification into the next queues ----
-    int out_q = Q_NONE;
-    if (has_ray) {
-        RayQ q = make_rayq(r);
-        Hit h = USE_BVH ? closest_hit_bvh(sc, q, rp.tmin) : closest_hit_list(sc, q, rp.tmin);
-        ++nrays;
-        ++bounce;
-        if (h.prim == RT_INVALID_ID) { // miss: the path's value is A (main.cu:66-67)
+// Second half: the closest hit `h` of ln.r is known.  Miss / constant emitter: the path ends (accumulate, slot to
+// Q_NEW); otherwise the record is stored and the slot goes to the shading queue of the hit.  Returns that queue.
+RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, float4* __restrict__ accum, WfLane& ln,
+                     const RayQ& q, Hit h) {
+    WfRecord* rec = wb.rec + ln.slot;
+    const uint32_t bounce = ln.bounce + 1u;
+    V3 A = ln.A;
+    int out_q;
+    bool finished = false;
+    if (h.prim == RT_INVALID_ID) { // miss: the path's value is A (main.cu:66-67)
+        finished = true;
+    } else {
+        int32_t leaf;
+        V3 value;
+        out_q = classify_hit(sc, rp, q, h, leaf, value);
+        if (out_q == Q_NONE) { // constant emitter: terminate here
+            A = value;
             finished = true;
-            slot_free = true;
         } else {
-            int32_t leaf;
-            V3 value;
-            out_q = classify_hit(sc, rp, q, h, leaf, value);
-            if (out_q == Q_NONE) { // constant emitter: terminate here
-                A = value;
-                finished = true;
-                slot_free = true;
-            } else {
-                rec->o = make_float4(r.o.x, r.o.y, r.o.z, r.time);
-                rec->d = make_float4(r.d.x, r.d.y, r.d.z, h.t);
-                rec->a = make_float4(A.x, A.y, A.z, __uint_as_float(h.prim));
-                rec->ids = make_uint4(pixel, sample, bounce, uint32_t(leaf));
-            }
+            rec->o = make_float4(ln.r.o.x, ln.r.o.y, ln.r.o.z, ln.r.time);
+            rec->d = make_float4(ln.r.d.x, ln.r.d.y, ln.r.d.z, h.t);
+            rec->a = make_float4(A.x, A.y, A.z, __uint_as_float(h.prim));
+            rec->ids = make_uint4(ln.pixel, ln.sample, bounce, uint32_t(leaf));
         }
     }
-    if (finished) atomicAdd(&accum[pixel], make_float4(A.x, A.y, A.z, 1.f));
-    if (slot_free) out_q = Q_NEW;
+    if (finished) {
+        atomicAdd(&accum[ln.pixel], make_float4(A.x, A.y, A.z, 1.f));
+        out_q = Q_NEW;
+    }
+    return out_q;
+}
+
+// One whole queue entry (the CTA-chunk and warp-chunk kernels): begin, closest hit, finish.
+template <bool USE_BVH>
+RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind,
+                            bool valid, uint32_t slot, unsigned long long path, unsigned long long npix,
+                            unsigned long long npaths, float4* __restrict__ accum, unsigned long long& nrays) {
+    WfLane ln;
+    int out_q;
+    if (wf_begin(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q)) {
+        RayQ q = make_rayq(ln.r);
+        Hit h = USE_BVH ? closest_hit_bvh(sc, q, rp.tmin) : closest_hit_list(sc, q, rp.tmin);
+        ++nrays;
+        out_q = wf_finish(sc, rp, wb, accum, ln, q, h);
+    }
     return out_q;
 }
 
