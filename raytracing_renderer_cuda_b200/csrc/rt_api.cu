@@ -1,6 +1,7 @@
 // rt_api.cu — C-ABI of librt_b200.so (include/rt_api.h): context, scene upload +
 // acceleration-structure build, render / accumulate / tonemap entry points.
 // Host logic only; the kernels live in rt_kernels.cu / rt_wavefront.cu / rt_lbvh.cu.
+#include <algorithm>
 #include <cfenv>
 #include <chrono>
 #include <cmath>
@@ -433,6 +434,7 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
         CUDA_TRY(cudaMemcpyAsync(dc, hc.data(), n * sizeof(uint4), cudaMemcpyHostToDevice, stream));
     }
     float lbvh_ms = 0.f;
+    uint32_t bvh_root = 0;
     uint32_t n_nodes = 0;
     if (mode == RT_BVH_HOST_SAH) {
         n_nodes = uint32_t(nodes.size());
@@ -441,10 +443,61 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     } else if (mode == RT_BVH_GPU_LBVH) {
         n_nodes = n - 1;
         if ((st = dev_alloc(s, &dnodes, n_nodes)) != RT_OK) return st;
-        cudaError_t e = rtd::lbvh_build(da, db, n, n_static, dnodes, stream, &lbvh_ms, &bstats.depth);
+        // Outsized primitives (the r = 1000 ground every scene of this renderer has) would sit deep in a Morton-ordered
+        // tree and inflate the boxes of all their ancestors, so every ray would walk that whole chain.  They are kept
+        // out of the LBVH and hung above its root instead: root -> (big_k, (... (big_0, LBVH root))).
+        std::vector<uint32_t> big, normal;
+        {
+            std::vector<float> radii(n);
+            for (uint32_t k = 0; k < n; ++k) radii[k] = std::fabs(ha[k].w);
+            std::vector<float> tmp(radii);
+            std::nth_element(tmp.begin(), tmp.begin() + n / 2, tmp.end());
+            const float limit = 32.f * tmp[n / 2];
+            for (uint32_t k = 0; k < n; ++k) (radii[k] > limit && big.size() < 32 ? big : normal).push_back(k);
+            if (normal.size() < 2) { // nothing sensible to separate
+                big.clear();
+                normal.clear();
+            }
+        }
+        const uint32_t m = big.empty() ? n : uint32_t(normal.size());
+        uint32_t* d_ids = nullptr;
+        if (!big.empty()) {
+            CUDA_TRY(cudaMallocAsync(&d_ids, m * sizeof(uint32_t), stream));
+            CUDA_TRY(cudaMemcpyAsync(d_ids, normal.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        }
+        float rb[6];
+        cudaError_t e = rtd::lbvh_build(da, db, n_static, d_ids, m, dnodes, stream, &lbvh_ms, &bstats.depth, rb);
+        if (d_ids) cudaFreeAsync(d_ids, stream);
         if (e != cudaSuccess) {
             set_error("GPU LBVH build failed: %s", cudaGetErrorString(e));
             return RT_ERR_CUDA;
+        }
+        if (!big.empty()) {
+            std::vector<rth::NodeHost> chain(big.size());
+            rth::Box below{{rb[0], rb[1], rb[2]}, {rb[3], rb[4], rb[5]}};
+            int32_t below_ref = 0; // the LBVH root
+            for (size_t k = 0; k < big.size(); ++k) {
+                const rt_sphere& sp = desc->spheres[order[big[k]]];
+                const bool moving = (sp.flags & RT_SPHERE_MOVING) != 0;
+                rth::Box bb = rth::sphere_box(sp.center0, moving ? sp.center1 : sp.center0, sp.radius);
+                rth::NodeHost& nd = chain[k];
+                for (int a = 0; a < 3; ++a) {
+                    nd.lmin[a] = bb.lo[a];
+                    nd.lmax[a] = bb.hi[a];
+                    nd.rmin[a] = below.lo[a];
+                    nd.rmax[a] = below.hi[a];
+                    below.lo[a] = std::min(below.lo[a], bb.lo[a]);
+                    below.hi[a] = std::max(below.hi[a], bb.hi[a]);
+                }
+                nd.left = ~int32_t(big[k]);
+                nd.right = below_ref;
+                nd.pad0 = nd.pad1 = 0.f;
+                below_ref = int32_t(m - 1 + k);
+            }
+            CUDA_TRY(cudaMemcpyAsync(dnodes + (m - 1), chain.data(), chain.size() * sizeof(rtd::BvhNode), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream)); // `chain` is a pageable host buffer
+            bvh_root = uint32_t(below_ref);
+            bstats.depth += uint32_t(big.size());
         }
     }
     if (bstats.depth > RT_BVH_STACK_DEPTH) {
@@ -529,6 +582,7 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     s->d.n_static = n_static;
     s->d.nodes = dnodes;
     s->d.n_nodes = n_nodes;
+    s->d.root = bvh_root;
     s->d.mats = dmats;
     s->d.texs = dtexs;
     make_camera(desc->camera, s->d.cam);

@@ -89,6 +89,7 @@ struct DScene {
     uint32_t n_static;
     const BvhNode* nodes; // nullptr => brute force
     uint32_t n_nodes;
+    uint32_t root;        // index of the BVH root node
     const DMaterial* mats;
     const DTexture* texs;
     DImage images[RT_MAX_IMAGES];

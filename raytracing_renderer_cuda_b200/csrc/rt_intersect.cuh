@@ -141,8 +141,8 @@ struct Trav {
     Hit best;
     V3 inv;
 };
-RT_DEV void trav_begin(const RayQ& q, Trav& t) {
-    t.node = 0;
+RT_DEV void trav_begin(const DScene& sc, const RayQ& q, Trav& t) {
+    t.node = int(sc.root);
     t.sp = 0;
     t.best = Hit{FLT_MAX, RT_INVALID_ID};
     t.inv = V3{1.0f / q.d.x, 1.0f / q.d.y, 1.0f / q.d.z};
@@ -176,7 +176,7 @@ RT_DEV void trav_leaf(const DScene& sc, const RayQ& q, float tmin, Trav& t, int*
 RT_DEV Hit closest_hit_bvh(const DScene& sc, const RayQ& q, float tmin) {
     int stack[RT_BVH_STACK];
     Trav t;
-    trav_begin(q, t);
+    trav_begin(sc, q, t);
     // "while-while" traversal: leaves travel through `node` and the stack like inner nodes, so the lanes of a
     // warp first all descend through inner nodes and then test their pending leaves together, instead of each
     // lane stopping for a sphere test in the middle of the others' descent.

@@ -24,16 +24,18 @@ __device__ __forceinline__ float unflip_f(unsigned u) {
 // sphere.h:192-202), padded exactly like the host builder (rt_bvh_host.cpp sphere_box) so the
 // conservative slab test never rejects a ray the rounded sphere test accepts.
 __global__ void __launch_bounds__(256) k_prim_boxes(const float4* __restrict__ sph_a, const float4* __restrict__ sph_b,
-                                                    uint32_t n, uint32_t n_static, float4* __restrict__ lo,
-                                                    float4* __restrict__ hi, unsigned* __restrict__ cbounds) {
+                                                    const uint32_t* __restrict__ ids, uint32_t n, uint32_t n_static,
+                                                    float4* __restrict__ lo, float4* __restrict__ hi,
+                                                    unsigned* __restrict__ cbounds) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float c[3] = {0.f, 0.f, 0.f};
     bool valid = i < n;
     if (valid) {
-        float4 a = __ldg(&sph_a[i]);
+        const uint32_t prim = ids ? ids[i] : i;
+        float4 a = __ldg(&sph_a[prim]);
         float c0[3] = {a.x, a.y, a.z}, c1[3] = {a.x, a.y, a.z};
-        if (i >= n_static) {
-            float4 b = __ldg(&sph_b[i]);
+        if (prim >= n_static) {
+            float4 b = __ldg(&sph_b[prim]);
             c1[0] = __fadd_rz(a.x, b.x); // where moving_center() puts the sphere at the end of its motion
             c1[1] = __fadd_rz(a.y, b.y);
             c1[2] = __fadd_rz(a.z, b.z);
@@ -80,11 +82,15 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ lo, c
     if (i >= n) return;
     float4 l = lo[i], h = hi[i];
     float c[3] = {0.5f * l.x + 0.5f * h.x, 0.5f * l.y + 0.5f * h.y, 0.5f * l.z + 0.5f * h.z};
+    // one scale for all axes (the largest extent): Morton cells are cubes, so a flat scene is split along its long
+    // axes first instead of being cut into thin layers
+    float ext = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ext = fmaxf(ext, unflip_f(cbounds[3 + k]) - unflip_f(cbounds[k]));
     unsigned long long code = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float mn = unflip_f(cbounds[k]), mx = unflip_f(cbounds[3 + k]);
-        float ext = mx - mn;
+        float mn = unflip_f(cbounds[k]);
         float t = ext > 0.f ? (c[k] - mn) / ext : 0.f;
         unsigned long long q = (unsigned long long)fminf(fmaxf(t * 2097152.f, 0.f), 2097151.f);
         code |= spread21(q) << (2 - k);
@@ -104,8 +110,8 @@ __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys
 
 // One thread per internal node: range, split, children.  Node 0 is the root.
 __global__ void __launch_bounds__(256) k_topology(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                  int n, BvhNode* __restrict__ nodes, int* __restrict__ parent_inner,
-                                                  int* __restrict__ parent_leaf) {
+                                                  const uint32_t* __restrict__ ids, int n, BvhNode* __restrict__ nodes,
+                                                  int* __restrict__ parent_inner, int* __restrict__ parent_leaf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -126,14 +132,14 @@ __global__ void __launch_bounds__(256) k_topology(const unsigned long long* __re
     int lo_ = min(i, j), hi_ = max(i, j);
     int left, right;
     if (lo_ == gamma) {
-        left = ~int(vals[gamma]);
+        left = ~int(ids ? ids[vals[gamma]] : vals[gamma]);
         parent_leaf[gamma] = i;
     } else {
         left = gamma;
         parent_inner[gamma] = i;
     }
     if (hi_ == gamma + 1) {
-        right = ~int(vals[gamma + 1]);
+        right = ~int(ids ? ids[vals[gamma + 1]] : vals[gamma + 1]);
         parent_leaf[gamma + 1] = i;
     } else {
         right = gamma + 1;
@@ -148,14 +154,15 @@ __global__ void __launch_bounds__(256) k_topology(const unsigned long long* __re
 // One thread per leaf climbs towards the root.  A thread writes its subtree's box into its
 // side of the parent node; the first thread to reach a node stops, the second (which then sees
 // both child boxes) carries the union upwards.
-__global__ void __launch_bounds__(256) k_refit(const uint32_t* __restrict__ vals, int n, const float4* __restrict__ lo,
-                                               const float4* __restrict__ hi, BvhNode* nodes, const int* __restrict__ parent_inner,
-                                               const int* __restrict__ parent_leaf, unsigned* __restrict__ visits) {
+__global__ void __launch_bounds__(256) k_refit(const uint32_t* __restrict__ vals, const uint32_t* __restrict__ ids, int n,
+                                               const float4* __restrict__ lo, const float4* __restrict__ hi, BvhNode* nodes,
+                                               const int* __restrict__ parent_inner, const int* __restrict__ parent_leaf,
+                                               unsigned* __restrict__ visits, float* __restrict__ root_box) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    uint32_t prim = vals[k];
-    float4 bl = lo[prim], bh = hi[prim];
-    int me = ~int(prim);
+    uint32_t ci = vals[k]; // compact index of the primitive: lo/hi are indexed by it
+    float4 bl = lo[ci], bh = hi[ci];
+    int me = ~int(ids ? ids[ci] : ci);
     int parent = parent_leaf[k];
     while (parent >= 0) {
         BvhNode* nd = nodes + parent;
@@ -176,6 +183,9 @@ __global__ void __launch_bounds__(256) k_refit(const uint32_t* __restrict__ vals
         me = parent;
         parent = parent_inner[parent];
     }
+    // only the thread that closed the root gets here: (bl, bh) bound the whole tree
+    root_box[0] = bl.x; root_box[1] = bl.y; root_box[2] = bl.z;
+    root_box[3] = bh.x; root_box[4] = bh.y; root_box[5] = bh.z;
 }
 
 // depth of the deepest leaf (for the traversal stack bound): every leaf walks its parent chain
@@ -196,15 +206,15 @@ __global__ void __launch_bounds__(256) k_depth(int n, const int* __restrict__ pa
 
 } // namespace
 
-cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n, uint32_t n_static, BvhNode* nodes,
-                       cudaStream_t st, float* ms, uint32_t* depth) {
+cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n_static, const uint32_t* ids, uint32_t n,
+                       BvhNode* nodes, cudaStream_t st, float* ms, uint32_t* depth, float root_box[6]) {
     if (n < 2) return cudaErrorInvalidValue;
     cudaError_t e;
     float4 *lo = nullptr, *hi = nullptr;
     unsigned long long *keys = nullptr, *keys_out = nullptr;
     uint32_t *vals = nullptr, *vals_out = nullptr;
     int *parent_inner = nullptr, *parent_leaf = nullptr;
-    unsigned *visits = nullptr, *scal = nullptr; // scal: [0..5] centroid bounds, [6] depth
+    unsigned *visits = nullptr, *scal = nullptr; // scal: [0..5] centroid bounds, [6] depth, [8..13] root box
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -231,7 +241,7 @@ cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n, uin
     LB_TRY(cudaMalloc(&parent_inner, n * sizeof(int)));
     LB_TRY(cudaMalloc(&parent_leaf, n * sizeof(int)));
     LB_TRY(cudaMalloc(&visits, n * sizeof(unsigned)));
-    LB_TRY(cudaMalloc(&scal, 8 * sizeof(unsigned)));
+    LB_TRY(cudaMalloc(&scal, 16 * sizeof(unsigned)));
     LB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, vals_out, int(n), 0, 63, st));
     LB_TRY(cudaMalloc(&tmp, tmp_bytes));
     LB_TRY(cudaEventCreate(&e0));
@@ -242,17 +252,22 @@ cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n, uin
     LB_TRY(cudaEventRecord(e0, st));
     LB_TRY(cudaMemsetAsync(visits, 0, n * sizeof(unsigned), st));
     const unsigned blocks = (n + 255) / 256;
-    k_prim_boxes<<<blocks, 256, 0, st>>>(sph_a, sph_b, n, n_static, lo, hi, scal);
+    k_prim_boxes<<<blocks, 256, 0, st>>>(sph_a, sph_b, ids, n, n_static, lo, hi, scal);
     k_morton<<<blocks, 256, 0, st>>>(lo, hi, n, scal, keys, vals);
     LB_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, vals_out, int(n), 0, 63, st));
-    k_topology<<<blocks, 256, 0, st>>>(keys_out, vals_out, int(n), nodes, parent_inner, parent_leaf);
-    k_refit<<<blocks, 256, 0, st>>>(vals_out, int(n), lo, hi, nodes, parent_inner, parent_leaf, visits);
+    k_topology<<<blocks, 256, 0, st>>>(keys_out, vals_out, ids, int(n), nodes, parent_inner, parent_leaf);
+    k_refit<<<blocks, 256, 0, st>>>(vals_out, ids, int(n), lo, hi, nodes, parent_inner, parent_leaf, visits,
+                                    reinterpret_cast<float*>(scal + 8));
     k_depth<<<blocks, 256, 0, st>>>(int(n), parent_inner, parent_leaf, scal + 6);
     LB_TRY(cudaEventRecord(e1, st));
     LB_TRY(cudaGetLastError());
     unsigned d = 0;
+    float rb[6] = {0, 0, 0, 0, 0, 0};
     LB_TRY(cudaMemcpyAsync(&d, scal + 6, sizeof d, cudaMemcpyDeviceToHost, st));
+    LB_TRY(cudaMemcpyAsync(rb, scal + 8, sizeof rb, cudaMemcpyDeviceToHost, st));
     LB_TRY(cudaStreamSynchronize(st));
+    if (root_box)
+        for (int k = 0; k < 6; ++k) root_box[k] = rb[k];
     if (ms) LB_TRY(cudaEventElapsedTime(ms, e0, e1));
     if (depth) *depth = d;
 #undef LB_TRY

@@ -9,8 +9,9 @@
 namespace rtd {
 
 // sph_a / sph_b: the device sphere arrays of DScene (static spheres first); prim index = array index.
-// nodes: n-1 BvhNode, root = 0.  n >= 2.  ms: device time of the build; depth: deepest leaf.
-cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n, uint32_t n_static, BvhNode* nodes_dev,
-                       cudaStream_t st, float* ms, uint32_t* depth);
+// ids_dev: the m primitives to build over (nullptr: all of [0, m)); m >= 2.  Writes m-1 BvhNode, root = 0.
+// ms: device time of the build; depth: deepest leaf; root_box: lo.xyz, hi.xyz of the whole tree (host array).
+cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n_static, const uint32_t* ids_dev, uint32_t m,
+                       BvhNode* nodes_dev, cudaStream_t st, float* ms, uint32_t* depth, float root_box[6]);
 
 } // namespace rtd
