@@ -585,6 +585,9 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     s->d.root = bvh_root;
     s->d.mats = dmats;
     s->d.texs = dtexs;
+    s->d.has_noise = 0;
+    for (const auto& t : ht)
+        if (t.kind == RT_TEX_NOISE_PERLIN || t.kind == RT_TEX_NOISE_TURBULANCE || t.kind == RT_TEX_NOISE_MARBLE || t.kind == RT_TEX_WOOD) s->d.has_noise = 1;
     make_camera(desc->camera, s->d.cam);
 
     const auto t_end = std::chrono::steady_clock::now();

@@ -92,6 +92,7 @@ struct DScene {
     uint32_t root;        // index of the BVH root node
     const DMaterial* mats;
     const DTexture* texs;
+    uint32_t has_noise;   // any Perlin-based texture (noise / wood): the kernels stage the permutation table
     DImage images[RT_MAX_IMAGES];
     DCamera cam;
 };

@@ -114,16 +114,32 @@ RT_DEV Hit closest_hit_list(const DScene& sc, const RayQ& q, float tmin) {
     return best;
 }
 
-// Conservative slab test (the far bound is widened by 2 ulp so rounding can only
-// add node visits, never remove a leaf the sphere test would accept).
-RT_DEV bool slab(float4 lo, float4 hi, const V3& o, const V3& inv, float tmin, float tmax, float& tnear) {
-    float tx0 = (lo.x - o.x) * inv.x, tx1 = (hi.x - o.x) * inv.x;
-    float ty0 = (lo.y - o.y) * inv.y, ty1 = (hi.y - o.y) * inv.y;
-    float tz0 = (lo.z - o.z) * inv.z, tz1 = (hi.z - o.z) * inv.z;
+// Conservative slab test.  t = lo * (1/d) - o * (1/d) as one FFMA per bound against the per-ray products
+// noi = -(o * 1/d) (12 FFMA for the two boxes of a node instead of 12 FADD + 12 FMUL).  The product o * 1/d is rounded
+// once per ray, so every bound carries an extra absolute error of at most 2^-24 * max_k |o_k / d_k| over the
+// subtract-then-multiply form; the acceptance test is widened by `e` = 2^-22 * that maximum (and, as before, the far
+// bound by 2 ulp), so rounding can only add node visits, never remove a leaf the sphere test would accept (the
+// primitive boxes are padded on top of this: rt_bvh_host.cpp sphere_box / k_prim_boxes).
+// RT_SLAB_FAR_WIDEN: the far bound (box exit, or the closest t so far) is widened by 2^-8 relative.  The closest-t
+// culling must tolerate the NOISE of the reference's sphere arithmetic: at distance D from the ray origin the float
+// quadratic (sphere.h:94-107) resolves t only to about 2^-11 * D (dot(oc,oc) - r*r cancels), so a sphere can report a
+// t slightly outside the span of its own box.  With the margin the closest hit does not depend on the order in which
+// leaves are visited (per-lane loop, speculative rounds, refilled lanes: same image), at 0.4 % more box overlap.
+#define RT_SLAB_FAR_WIDEN 1.00390625f
+RT_DEV bool slab(float4 lo, float4 hi, const V3& inv, const V3& noi, float e, float tmin, float tmax, float& tnear) {
+#ifdef RT_SLAB_SUBMUL // A/B: subtract-then-multiply (noi holds -o here)
+    float tx0 = (lo.x + noi.x) * inv.x, tx1 = (hi.x + noi.x) * inv.x;
+    float ty0 = (lo.y + noi.y) * inv.y, ty1 = (hi.y + noi.y) * inv.y;
+    float tz0 = (lo.z + noi.z) * inv.z, tz1 = (hi.z + noi.z) * inv.z;
+#else
+    float tx0 = __fmaf_rn(lo.x, inv.x, noi.x), tx1 = __fmaf_rn(hi.x, inv.x, noi.x);
+    float ty0 = __fmaf_rn(lo.y, inv.y, noi.y), ty1 = __fmaf_rn(hi.y, inv.y, noi.y);
+    float tz0 = __fmaf_rn(lo.z, inv.z, noi.z), tz1 = __fmaf_rn(hi.z, inv.z, noi.z);
+#endif
     float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
     float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
     tnear = tn;
-    return tn <= tf * 1.0000003f;
+    return tn <= __fmaf_rn(tf, RT_SLAB_FAR_WIDEN, e);
 }
 
 #define RT_BVH_STACK RT_BVH_STACK_DEPTH
@@ -137,23 +153,50 @@ RT_DEV bool slab(float4 lo, float4 hi, const V3& o, const V3& inv, float tmin, f
 #define RT_TRAV_DONE 0x7fffffff
 struct Trav {
     int node; // >= 0 inner node, < 0 leaf ~prim, RT_TRAV_DONE finished
+    int leaf; // speculative traversal: postponed leaf (< 0), or >= 0 for none
     int sp;
     Hit best;
-    V3 inv;
+    V3 inv; // 1/d; an axis the ray does not move along (1/d not finite) gets +-2^100: its bounds stay exact (see trav_begin)
+    V3 noi; // -(o * inv)
+    float e; // widening of the slab acceptance test, 2^-22 * max |o * inv|
 };
 RT_DEV void trav_begin(const DScene& sc, const RayQ& q, Trav& t) {
     t.node = int(sc.root);
+    t.leaf = 0;
     t.sp = 0;
     t.best = Hit{FLT_MAX, RT_INVALID_ID};
+    // Per axis: inv = 1/d, noi = -(o * inv).  d == 0 (or so small that 1/d overflows): inv = +-2^100, a power of two, so
+    // o * inv is exact and fma(lo, inv, noi) is the correctly rounded (lo - o) * 2^100 — sign-exact like the infinities
+    // of the textbook slab test, and without a contribution to `e`.
+    const float dk[3] = {q.d.x, q.d.y, q.d.z}, ok[3] = {q.o.x, q.o.y, q.o.z};
+    float iv[3], no[3], m = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        iv[k] = 1.0f / dk[k];
+        if (fabsf(iv[k]) <= 3.0e38f) {
+            no[k] = -(ok[k] * iv[k]);
+            m = fmaxf(m, fabsf(no[k]));
+        } else {
+            iv[k] = copysignf(1.2676506e30f, dk[k]); // 2^100
+            no[k] = -(ok[k] * iv[k]);
+        }
+    }
+    t.inv = V3{iv[0], iv[1], iv[2]};
+    t.noi = V3{no[0], no[1], no[2]};
+    t.e = m * 2.3841858e-7f; // 2^-22
+#ifdef RT_SLAB_SUBMUL
     t.inv = V3{1.0f / q.d.x, 1.0f / q.d.y, 1.0f / q.d.z};
+    t.noi = V3{-q.o.x, -q.o.y, -q.o.z};
+    t.e = 0.f;
+#endif
 }
 // one inner-node visit (precondition: t.node >= 0 && t.node != RT_TRAV_DONE)
 RT_DEV void trav_inner(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {
     const float4* np = reinterpret_cast<const float4*>(sc.nodes + t.node);
     float4 lmin = __ldg(np + 0), lmax = __ldg(np + 1), rmin = __ldg(np + 2), rmax = __ldg(np + 3);
     float tl, tr;
-    const bool hl = slab(lmin, lmax, q.o, t.inv, tmin, t.best.t, tl);
-    const bool hr = slab(rmin, rmax, q.o, t.inv, tmin, t.best.t, tr);
+    const bool hl = slab(lmin, lmax, t.inv, t.noi, t.e, tmin, t.best.t, tl);
+    const bool hr = slab(rmin, rmax, t.inv, t.noi, t.e, tmin, t.best.t, tr);
     const int cl = __float_as_int(lmin.w), cr = __float_as_int(lmax.w);
     if (hl && hr) {
         const bool left_first = tl <= tr;
@@ -185,6 +228,46 @@ RT_DEV Hit closest_hit_bvh(const DScene& sc, const RayQ& q, float tmin) {
         if (t.node == RT_TRAV_DONE) break;
         trav_leaf(sc, q, tmin, t, stack);
     }
+    return t.best;
+}
+
+// Warp-cooperative variant for kernels that reach the traversal with all 32 lanes converged (the wavefront step
+// kernels): speculative while-while traversal (Aila & Laine 2009).  A lane that reaches a leaf does not stop and
+// wait for the other lanes' descents — it postpones the leaf and keeps walking inner nodes until every lane of the
+// warp holds a leaf (or has nothing left); then all pending leaves are tested together.  The postponed leaf cannot
+// shorten the ray while it waits, so a few extra nodes are visited, but the result is the same (closest t, ties to
+// the lower list ordinal: order-independent).  ncu on C4 (1 M spheres, one sphere per leaf): the plain per-lane
+// loop above ran with 5 of 32 lanes active because every lane waited at every leaf for the longest inner run.
+// MUST be called by all 32 lanes of the warp; lanes without a ray pass has_ray = false.
+RT_DEV void trav_inner_spec(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {
+    trav_inner(sc, q, tmin, t, stack);
+    if (t.node < 0 && t.leaf >= 0) { // first leaf: postpone it, go on with the next node
+        t.leaf = t.node;
+        t.node = t.sp ? stack[--t.sp] : RT_TRAV_DONE;
+    }
+}
+// one warp round: inner nodes until no lane is still looking for a leaf, then the pending leaves
+RT_DEV void trav_round_warp(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {
+    for (;;) {
+        const bool inner = t.node >= 0 && t.node != RT_TRAV_DONE;
+        if (!__any_sync(0xffffffffu, inner && t.leaf >= 0)) break;
+        if (inner) trav_inner_spec(sc, q, tmin, t, stack);
+    }
+    while (t.leaf < 0) {
+        test_prim(sc, q, uint32_t(~t.leaf), tmin, t.best);
+        t.leaf = 0;
+        if (t.node < 0) { // the node after the postponed leaf is a leaf too
+            t.leaf = t.node;
+            t.node = t.sp ? stack[--t.sp] : RT_TRAV_DONE;
+        }
+    }
+}
+RT_DEV Hit closest_hit_bvh_warp(const DScene& sc, const RayQ& q, float tmin, bool has_ray) {
+    int stack[RT_BVH_STACK];
+    Trav t;
+    trav_begin(sc, q, t);
+    if (!has_ray) t.node = RT_TRAV_DONE;
+    while (__any_sync(0xffffffffu, t.node != RT_TRAV_DONE)) trav_round_warp(sc, q, tmin, t, stack);
     return t.best;
 }
 

@@ -241,16 +241,30 @@ RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers&
     return out_q;
 }
 
-// One whole queue entry (the CTA-chunk and warp-chunk kernels): begin, closest hit, finish.
+// One whole queue entry (the CTA-chunk and warp-chunk kernels): begin, closest hit, finish.  Called by all 32 lanes of
+// the warp (the BVH traversal is warp-cooperative); `valid` = false for lanes past the end of the queue.
 template <bool USE_BVH>
 RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind,
                             bool valid, uint32_t slot, unsigned long long path, unsigned long long npix,
                             unsigned long long npaths, float4* __restrict__ accum, unsigned long long& nrays) {
     WfLane ln;
     int out_q;
-    if (wf_begin(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q)) {
-        RayQ q = make_rayq(ln.r);
-        Hit h = USE_BVH ? closest_hit_bvh(sc, q, rp.tmin) : closest_hit_list(sc, q, rp.tmin);
+    const bool has_ray = wf_begin(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q);
+    if (USE_BVH) {
+        const RayQ q = make_rayq(ln.r);
+#ifdef WF_NO_SPEC // A/B: the per-lane loop
+        Hit h{FLT_MAX, RT_INVALID_ID};
+        if (has_ray) h = closest_hit_bvh(sc, q, rp.tmin);
+#else
+        const Hit h = closest_hit_bvh_warp(sc, q, rp.tmin, has_ray);
+#endif
+        if (has_ray) {
+            ++nrays;
+            out_q = wf_finish(sc, rp, wb, accum, ln, q, h);
+        }
+    } else if (has_ray) {
+        const RayQ q = make_rayq(ln.r);
+        const Hit h = closest_hit_list(sc, q, rp.tmin);
         ++nrays;
         out_q = wf_finish(sc, rp, wb, accum, ln, q, h);
     }
@@ -298,7 +312,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     // lowest-numbered one they get, and the noise queues come first; textured emitters may need it too).
     if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
     if (blockIdx.x >= total_chunks) return;
-    if (blockIdx.x < chunk_end[1] || n_q[Q_EMIT] != 0u) perlin_stage(smem, threadIdx.x, blockDim.x);
+    if (sc.has_noise && (blockIdx.x < chunk_end[1] || n_q[Q_EMIT] != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     if (threadIdx.x < 2 * NQ) (&s_count[0][0])[threadIdx.x] = 0u;
     __syncthreads();
 
@@ -378,6 +392,18 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 #define WF_ROUNDS 1
 #endif
 #define WF_WCHUNK (32 * WF_ROUNDS)
+#ifndef RT_PT_MIN_SPHERES
+#define RT_PT_MIN_SPHERES 4096u // persistent-lane kernel from this many primitives on (measured: see profiles/)
+#endif
+#ifndef WF_PT_MINBLOCKS
+#define WF_PT_MINBLOCKS WF_MINBLOCKS
+#endif
+#ifndef RT_PT_LEAF_LANES_DEFAULT
+#define RT_PT_LEAF_LANES_DEFAULT 1
+#endif
+#ifndef RT_PT_REFILL_DEFAULT
+#define RT_PT_REFILL_DEFAULT 16
+#endif
 
 template <bool USE_BVH>
 __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
@@ -416,7 +442,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
     const uint32_t warps_per_cta = WF_THREADS / 32;
     if (blockIdx.x * warps_per_cta >= total_chunks) return;
-    if (chunk_end[1] != 0u || n_q[Q_EMIT] != 0u) perlin_stage(smem, threadIdx.x, blockDim.x);
+    if (sc.has_noise && (chunk_end[1] != 0u || n_q[Q_EMIT] != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     __syncthreads(); // the only block-wide barrier of the kernel
 
     const unsigned long long npix = (unsigned long long)rp.width * rp.height;
@@ -489,6 +515,164 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
 }
 
+// Work granularity, variant 3: persistent lanes.  A warp keeps a cursor into its current 32-entry chunk; a lane
+// whose ray has finished runs the second half of its entry (classify, store, push) and takes the NEXT entry of
+// the cursor — shade, scatter, start the new traversal — while the other lanes keep their half-walked rays.
+// The traversal loop is left whenever `refill` lanes are idle, and inside it every lane takes one step per
+// iteration — an inner node, or the leaf it stands at — instead of waiting for the warp at every leaf.
+// Measured on C4 (1 M spheres, 1920x1080x4, Mrays/s): per-lane while-while in warp chunks 722 (ncu: 5 of 32
+// lanes active per instruction, profiles/r01_wavefront_c4_lbvh_ncu.md), speculative rounds in warp chunks
+// 775-820 (11 of 32), this kernel 880-940.  On C2/C3 (a few hundred spheres, shading a third of the work) the
+// partial-width shading of refilled lanes costs more than the traversal gains (C2: 10.3 -> 7.1 Grays/s), so the
+// kernel is used from RT_PT_MIN_SPHERES primitives on.
+__global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
+    k_wf_step_pt(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
+                 int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter, int refill, int leaf_lanes) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t s_nq[NQ], s_cend[NQ];
+
+    const PerlinTab pt{smem, threadIdx.x & 31u};
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    const uint32_t* cnt_cur = wb.counts + (it % 3) * NQ;
+    uint32_t* cnt_next = wb.counts + ((it + 1) % 3) * NQ;
+    if (blockIdx.x == 0 && threadIdx.x < NQ) wb.counts[((it + 2) % 3) * NQ + threadIdx.x] = 0; // next iteration's target
+    uint32_t* ticket = wb.tickets + (it % 3);
+    if (blockIdx.x == 0 && threadIdx.x == 0) wb.tickets[(it + 2) % 3] = 0u;
+    const unsigned long long path_base = wb.next_path[it & 1];
+    const int par_cur = it & 1, par_next = par_cur ^ 1;
+
+    // chunk order, most expensive classes first: NOISE6, NOISE1, IMAGE, EMIT, DIEL, METAL, LAMB_CONST, NEW
+    const int order[NQ] = {Q_LAMB_NOISE6, Q_LAMB_NOISE1, Q_LAMB_IMAGE, Q_EMIT, Q_DIEL, Q_METAL, Q_LAMB_CONST, Q_NEW};
+    uint32_t total_chunks = 0, noise_chunks = 0, n_emit = 0, n_new = 0;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        const uint32_t n = __ldg(cnt_cur + order[k]);
+        total_chunks += (n + 31u) / 32u;
+        if (threadIdx.x == 0) {
+            s_nq[k] = n;
+            s_cend[k] = total_chunks;
+        }
+        if (k == 1) noise_chunks = total_chunks;
+        if (order[k] == Q_EMIT) n_emit = n;
+        if (order[k] == Q_NEW) n_new = n;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_new;
+    if (blockIdx.x * (WF_THREADS / 32) >= total_chunks) return;
+    if (sc.has_noise && (noise_chunks != 0u || n_emit != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
+    __syncthreads(); // the only block-wide barrier of the kernel
+
+    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
+    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+    unsigned long long nrays = 0;
+
+    auto draw = [&]() -> uint32_t {
+        uint32_t c = 0u;
+        if (lane == 0u) c = atomicAdd(ticket, 1u);
+        return c;
+    };
+    // warp-aggregated push: one global atomic per target queue
+    auto push = [&](int out_q, uint32_t slot) {
+        const unsigned peers = __match_any_sync(0xffffffffu, out_q);
+        if (out_q != Q_NONE) {
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0u;
+            if (int(lane) == leader) base = atomicAdd(cnt_next + out_q, uint32_t(__popc(peers)));
+            base = __shfl_sync(peers, base, leader);
+            wf_queue(wb, par_next, out_q)[base + uint32_t(__popc(peers & lt_mask))] = slot;
+        }
+    };
+
+    int stack[RT_BVH_STACK];
+    Trav t;
+    t.node = RT_TRAV_DONE;
+    t.leaf = 0;
+    t.sp = 0;
+    t.best = Hit{FLT_MAX, RT_INVALID_ID};
+    t.inv = t.noi = mk(0.f, 0.f, 0.f);
+    t.e = 0.f;
+    RayQ q;
+    q.o = q.d = mk(0.f, 0.f, 0.f);
+    q.time = q.a = 0.f;
+    WfLane ln;
+    ln.slot = 0u;
+    bool tracing = false; // the lane holds a ray (being traversed, or finished and not yet written back)
+
+    // cursor into the warp's current chunk (warp-uniform)
+    int kind = Q_NEW;
+    uint32_t pos = 0u, end = 0u;
+    const uint32_t* q_in = wb.queue;
+    bool more = true;
+    uint32_t ticket_next = draw();
+
+    for (;;) {
+        // ---- 1. second half of the entries whose ray is done ----
+        {
+            int out_q = Q_NONE;
+            if (tracing && t.node == RT_TRAV_DONE) {
+                ++nrays;
+                out_q = wf_finish(sc, rp, wb, accum, ln, q, t.best);
+                tracing = false;
+            }
+            push(out_q, ln.slot);
+        }
+        // ---- 2. idle lanes take the next entries of the cursor ----
+        unsigned idle = __ballot_sync(0xffffffffu, !tracing);
+        while (idle != 0u && more) {
+            if (pos == end) {
+                const uint32_t chunk = __shfl_sync(0xffffffffu, ticket_next, 0);
+                if (chunk >= total_chunks) {
+                    more = false;
+                    break;
+                }
+                ticket_next = draw();
+                int kpos = 0;
+#pragma unroll
+                for (int k = 0; k < NQ - 1; ++k) kpos += (chunk >= s_cend[k]) ? 1 : 0;
+                kind = order[kpos];
+                pos = (chunk - (kpos ? s_cend[kpos - 1] : 0u)) * 32u;
+                end = min(pos + 32u, s_nq[kpos]);
+                q_in = wf_queue(wb, par_cur, kind);
+            }
+            const uint32_t navail = end - pos;
+            const uint32_t rank = uint32_t(__popc(idle & lt_mask));
+            int out_q = Q_NONE;
+            if (!tracing && rank < navail) {
+                const uint32_t idx = pos + rank;
+                const uint32_t slot = __ldg(q_in + idx);
+                if (wf_begin(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
+                    q = make_rayq(ln.r);
+                    trav_begin(sc, q, t);
+                    tracing = true;
+                }
+            }
+            push(out_q, ln.slot);
+            pos += min(uint32_t(__popc(idle)), navail);
+            idle = __ballot_sync(0xffffffffu, !tracing);
+        }
+        const unsigned live = __ballot_sync(0xffffffffu, tracing);
+        if (live == 0u) break;
+        // ---- 3. traverse until `refill` lanes are idle (or, with no work left to hand out, until all are done) ----
+        const int keep = more ? max(__popc(live) - refill, 0) : 0;
+        int nlive;
+        do {
+            // One inner-node step for every lane that stands at an inner node; lanes that stand at a leaf (or just
+            // arrived at one) test it once `leaf_lanes` of them wait, or when no lane can take an inner step.
+            if (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner(sc, q, rp.tmin, t, stack);
+            const unsigned at_leaf = __ballot_sync(0xffffffffu, t.node < 0);
+            const unsigned can_go = __ballot_sync(0xffffffffu, t.node >= 0 && t.node != RT_TRAV_DONE);
+            if (__popc(at_leaf) >= leaf_lanes || can_go == 0u) {
+                if (t.node < 0) trav_leaf(sc, q, rp.tmin, t, stack);
+            }
+            nlive = __popc(__ballot_sync(0xffffffffu, t.node != RT_TRAV_DONE));
+        } while (nlive > keep);
+    }
+
+    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
+    if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
+}
+
 // fills Q_NEW of iteration 0 with every slot and resets the path counter
 __global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -542,12 +726,15 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     *iterations = 0;
     if (npaths == 0) return;
     static bool attr_set = false;
-    const size_t smem = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
+    const size_t smem_full = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
+    // scenes without Perlin textures leave the 32 KB table out: 128 KB more L1 per SM for BVH nodes
+    const size_t smem = sc.has_noise ? smem_full : 0;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_wf_step_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        cudaFuncSetAttribute(k_wf_step_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        cudaFuncSetAttribute(k_wf_step_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        cudaFuncSetAttribute(k_wf_step_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaFuncSetAttribute(k_wf_step_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
+        cudaFuncSetAttribute(k_wf_step_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
+        cudaFuncSetAttribute(k_wf_step_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
+        cudaFuncSetAttribute(k_wf_step_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
+        cudaFuncSetAttribute(k_wf_step_pt, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
         attr_set = true;
     }
     // slots in use: never more than there are paths
@@ -556,13 +743,26 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     k_wf_init<<<(slots + 255) / 256 > 0 ? (slots + 255) / 256 : 1, 256, 0, st>>>(wb, slots);
     ++*launches;
 
-    // Granularity: warp chunks (barrier-free, ticketed) when rays cost unevenly — BVH traversal —, CTA chunks
-    // (4x fewer queue atomics) when they cost the same — the brute-force list.  RT_WF_GRAIN=cta|warp overrides.
-    bool warp_grain = use_bvh;
-    if (const char* e = getenv("RT_WF_GRAIN")) warp_grain = (e[0] == 'w');
+    // Granularity: CTA chunks (4x fewer queue atomics) when all rays cost the same — the brute-force list —, warp
+    // chunks (barrier-free, ticketed) for BVH scenes, persistent lanes with refill when the BVH is large and the
+    // rays' traversal lengths spread widely.  RT_WF_GRAIN=cta|warp|pt overrides; RT_PT_REFILL = idle lanes per refill.
+    enum { G_CTA, G_WARP, G_PT };
+    int grain = !use_bvh ? G_CTA : (sc.n_spheres >= RT_PT_MIN_SPHERES ? G_PT : G_WARP);
+    if (const char* e = getenv("RT_WF_GRAIN")) grain = e[0] == 'w' ? G_WARP : (e[0] == 'p' && use_bvh ? G_PT : (e[0] == 'c' ? G_CTA : grain));
+    int refill = RT_PT_REFILL_DEFAULT;
+    if (const char* e = getenv("RT_PT_REFILL")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) refill = v;
+    }
+    int leaf_lanes = RT_PT_LEAF_LANES_DEFAULT;
+    if (const char* e = getenv("RT_PT_LEAF_LANES")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) leaf_lanes = v;
+    }
+    const bool warp_grain = grain != G_CTA;
     unsigned grid;
     if (warp_grain) { // resident CTAs only: work is drawn dynamically
-        const unsigned cap = unsigned(sm_count) * WF_MINBLOCKS;
+        const unsigned cap = unsigned(sm_count) * (grain == G_PT ? WF_PT_MINBLOCKS : WF_MINBLOCKS);
         const unsigned need = (slots + WF_WCHUNK * (WF_THREADS / 32) - 1) / (WF_WCHUNK * (WF_THREADS / 32)) + NQ;
         grid = need < cap ? need : cap;
     } else { // two waves of CTAs, chunks by stride
@@ -571,10 +771,38 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         grid = need < cap ? need : cap;
     }
 
+    // L2 residency of the BVH: the path records stream through L2 once per iteration (64 B per slot) and would evict
+    // the node array, which every ray re-reads along its walk; an access-policy window marks the nodes persisting.
+    bool l2_window = false;
+    if (use_bvh && sc.nodes && sc.n_nodes >= RT_PT_MIN_SPHERES && !getenv("RT_NO_L2_PERSIST")) {
+        static int persist_max = -1, window_max = 0;
+        if (persist_max < 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            if (persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(persist_max));
+        }
+        if (persist_max > 0 && window_max > 0) {
+            cudaStreamAttrValue av{};
+            size_t bytes = size_t(sc.n_nodes) * sizeof(BvhNode);
+            if (bytes > size_t(window_max)) bytes = size_t(window_max);
+            av.accessPolicyWindow.base_ptr = const_cast<BvhNode*>(sc.nodes);
+            av.accessPolicyWindow.num_bytes = bytes;
+            const float ratio = float(double(persist_max) * 0.9 / double(bytes));
+            av.accessPolicyWindow.hitRatio = ratio < 1.f ? ratio : 1.f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            l2_window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+        }
+    }
+
     uint32_t it = 0;
     auto enqueue = [&](uint32_t count) {
         for (uint32_t k = 0; k < count; ++k, ++it) {
-            if (warp_grain) {
+            if (grain == G_PT) {
+                k_wf_step_pt<<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
+            } else if (warp_grain) {
                 if (use_bvh) k_wf_step_warp<true><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
                 else k_wf_step_warp<false><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
             } else {
@@ -616,6 +844,11 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         par ^= 1;
     }
     *iterations = it;
+    if (l2_window) {
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
 }
 
 } // namespace rtd
