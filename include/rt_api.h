@@ -288,6 +288,27 @@ rt_status rt_write_ppm(const char* path, int32_t width, int32_t height, const ui
 rt_status rt_read_ppm_f32(const char* path, float** out_rgb, int32_t* width, int32_t* height); /* byte/255.f */
 void rt_free(void* p);
 
+/* ---- output stage ------------------------------------------------------------------
+ * Replaces stbi_write_jpg("render.jpg", W, H, 3, data, 100) (main.cu:491; vendored stb_image_write v1.15,
+ * stb_image_write.h:1368-1573) with CUDA kernels whose output is byte-identical to stb's for the same
+ * pixels and quality (1..100; <= 90 selects 4:2:0 chroma subsampling exactly like stb).
+ * `rgb8` is what the reference hands to stb: height rows of width RGB bytes, first row = top of the picture
+ * (rt_tonemap_device's out_rgb8_dev / rt_quantize_rgb8). */
+size_t rt_jpeg_max_bytes(int32_t width, int32_t height); /* capacity that always suffices */
+/* device image -> finished file in HOST memory; out_jpg == NULL only reports *n_bytes.  ms_device (may be NULL)
+ * receives the device time of the encoder passes. */
+rt_status rt_jpeg_encode_device(rt_context* ctx, const void* rgb8_dev, int32_t width, int32_t height, int32_t quality,
+                                uint8_t* out_jpg, size_t cap, size_t* n_bytes, float* ms_device);
+/* host image -> H2D -> encode -> D2H */
+rt_status rt_jpeg_encode(rt_context* ctx, const uint8_t* rgb8, int32_t width, int32_t height, int32_t quality,
+                         uint8_t* out_jpg, size_t cap, size_t* n_bytes);
+/* stbi_write_jpg(filename, w, h, 3, data, quality) */
+rt_status rt_write_jpg(rt_context* ctx, const char* path, int32_t width, int32_t height, const uint8_t* rgb8, int32_t quality);
+/* render + pixel finalisation + Y flip + quantisation + JPEG, all on the device: only the file crosses PCIe
+ * (main.cu:442-491 in one call).  stats->ms_d2h reports the device time of the JPEG passes. */
+rt_status rt_render_jpeg(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, int32_t quality,
+                         uint8_t* out_jpg, size_t cap, size_t* n_bytes, rt_stats* stats);
+
 /* Built-in scene generators written against the façade (BASELINE configs C1..C4):
  * "earth_emitter" (main.cu:188-356), "book1_final", "perlin_motion", "random_spheres".
  * `image_rgb` (may be NULL unless the scene needs it) is the earth texture; `n` is

@@ -21,6 +21,7 @@ LIB_PATH = _PKG / "librt_b200.so"
 
 RT_INVALID_ID = 0xFFFFFFFF
 RT_OK = 0
+RT_ERR_INVALID_ARG = 1
 STATUS_NAMES = {0: "RT_OK", 1: "RT_ERR_INVALID_ARG", 2: "RT_ERR_CUDA", 3: "RT_ERR_OOM", 4: "RT_ERR_UNSUPPORTED",
                 5: "RT_ERR_NO_DEVICE", 6: "RT_ERR_IO"}
 
@@ -135,6 +136,13 @@ _SIGNATURES = {
     "rt_read_ppm_f32": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32)]),
     "rt_free": (None, [_VP]),
+    "rt_jpeg_max_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "rt_jpeg_encode_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, C.c_size_t, C.POINTER(C.c_size_t),
+                                        C.POINTER(C.c_float)]),
+    "rt_jpeg_encode": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "rt_write_jpg": (C.c_int, [_VP, C.c_char_p, C.c_int32, C.c_int32, _VP, C.c_int32]),
+    "rt_render_jpeg": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), C.c_int32, _VP, C.c_size_t, C.POINTER(C.c_size_t),
+                                 C.POINTER(rt_stats)]),
     "rt_builtin_scene": (C.c_int, [C.c_char_p, _VP, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32,
                                    C.POINTER(C.POINTER(rt_scene_desc))]),
     "rt_scene_desc_free": (None, [C.POINTER(rt_scene_desc)]),
@@ -324,6 +332,17 @@ class Scene:
                                                          C.byref(st) if st is not None else None))
         return st
 
+    def render_jpeg(self, params: rt_render_params, quality: int = 100, out: np.ndarray | None = None):
+        """rt_render_jpeg: render -> finalise -> flip/quantise -> JPEG on the device; returns (file bytes, stats)."""
+        cap = self.lib.rt_jpeg_max_bytes(params.width, params.height)
+        if out is None:
+            out = np.empty(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        st = rt_stats()
+        _check(self.lib, self.lib.rt_render_jpeg(self.ctx._h, self._h, C.byref(params), quality, out.ctypes.data, out.size,
+                                                 C.byref(n), C.byref(st)))
+        return out[:n.value], st
+
     def close(self) -> None:
         if self._h:
             self.lib.rt_scene_destroy(self._h)
@@ -348,6 +367,26 @@ def reduce_tonemap_peers(ctx: Context, peer_ptrs, multicast_ptr: int, width: int
     arr = (_VP * n)(*[_VP(int(p)) for p in peer_ptrs])
     _check(ctx.lib, ctx.lib.rt_reduce_tonemap_peers(ctx._h, arr, n, _VP(multicast_ptr or None), width, height, row_begin, row_end,
                                                     _VP(out_rgb_ptr or None), _VP(out_rgb8_ptr or None), _VP(out_sum_ptr or None)))
+
+
+def jpeg_encode(ctx: Context, rgb8: np.ndarray, quality: int = 100) -> bytes:
+    """rt_jpeg_encode: stbi_write_jpg(.., w, h, 3, rgb8, quality) (main.cu:491) on the device; returns the file."""
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w = rgb8.shape[:2]
+    cap = ctx.lib.rt_jpeg_max_bytes(w, h)
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t(0)
+    _check(ctx.lib, ctx.lib.rt_jpeg_encode(ctx._h, rgb8.ctypes.data, w, h, quality, out.ctypes.data, cap, C.byref(n)))
+    return out[:n.value].tobytes()
+
+
+def jpeg_encode_device(ctx: Context, rgb8_ptr: int, width: int, height: int, quality: int, out: np.ndarray):
+    """rt_jpeg_encode_device: device rgb8 -> file in `out` (host uint8 array); returns (n_bytes, device ms)."""
+    n = C.c_size_t(0)
+    ms = C.c_float(0)
+    _check(ctx.lib, ctx.lib.rt_jpeg_encode_device(ctx._h, _VP(rgb8_ptr), width, height, quality, out.ctypes.data, out.size,
+                                                  C.byref(n), C.byref(ms)))
+    return n.value, ms.value
 
 
 def quantize_rgb8(rgb: np.ndarray) -> np.ndarray:

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "rt_bvh_host.hpp"
+#include "rt_jpeg.cuh"
 #include "rt_kernels.cuh"
 #include "rt_lbvh.cuh"
 
@@ -72,6 +73,9 @@ struct rt_context {
     float* out_rgb = nullptr;
     size_t out_px = 0;
     rtd::WavefrontState* wf = nullptr;
+    rtd::JpegState* jpg = nullptr; // device JPEG writer (rt_jpeg.cu), created on first use
+    uint8_t* rgb8 = nullptr;       // flipped, quantised frame: input of the JPEG writer
+    size_t rgb8_px = 0;
     // cudaArray allocations cost milliseconds; arrays of destroyed scenes are kept for the next scene of the
     // same image size (a frame loop that re-uploads its scene every frame then allocates nothing)
     struct CachedArray {
@@ -217,6 +221,47 @@ rt_status ensure_out(rt_context* ctx, size_t npix) {
     return RT_OK;
 }
 
+rt_status ensure_rgb8(rt_context* ctx, size_t npix) {
+    if (ctx->rgb8_px < npix) {
+        if (ctx->rgb8) cudaFree(ctx->rgb8);
+        ctx->rgb8 = nullptr;
+        ctx->rgb8_px = 0;
+        CUDA_TRY(cudaMalloc(&ctx->rgb8, npix * 3));
+        ctx->rgb8_px = npix;
+    }
+    return RT_OK;
+}
+
+rt_status ensure_jpeg(rt_context* ctx) {
+    if (!ctx->jpg) {
+        ctx->jpg = rtd::jpeg_create();
+        if (!ctx->jpg) {
+            set_error("jpeg_create failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return RT_ERR_OOM;
+        }
+    }
+    return RT_OK;
+}
+
+rt_status jpeg_from_device(rt_context* ctx, const uint8_t* rgb8_dev, int32_t w, int32_t h, int32_t quality, uint8_t* out, size_t cap,
+                           size_t* n_bytes, float* ms_device) {
+    rt_status st = ensure_jpeg(ctx);
+    if (st != RT_OK) return st;
+    size_t n = 0;
+    cudaError_t e = rtd::jpeg_encode(ctx->jpg, rgb8_dev, w, h, quality, out, cap, &n, ctx->stream, ms_device);
+    if (n_bytes) *n_bytes = n;
+    if (e == cudaErrorInvalidValue && out && n > cap) {
+        set_error("JPEG needs %zu bytes, the output buffer holds %zu", n, cap);
+        return RT_ERR_INVALID_ARG;
+    }
+    if (e != cudaSuccess) {
+        set_error("jpeg_encode: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA;
+    }
+    return RT_OK;
+}
+
 // Core: adds p->spp samples per pixel into accum (device).  Fills stats if requested
 // (which synchronises the stream).
 rt_status render_into(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, float4* accum, rt_stats* stats) {
@@ -337,6 +382,8 @@ void rt_context_destroy(rt_context* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream); // polling copies of the last render may still be in flight
     if (ctx->wf) rtd::wavefront_destroy(ctx->wf);
+    if (ctx->jpg) rtd::jpeg_destroy(ctx->jpg);
+    if (ctx->rgb8) cudaFree(ctx->rgb8);
     if (ctx->accum) cudaFree(ctx->accum);
     if (ctx->out_rgb) cudaFree(ctx->out_rgb);
     if (ctx->d_ray_counter) cudaFree(ctx->d_ray_counter);
@@ -764,6 +811,79 @@ rt_status rt_render(rt_context* ctx, const rt_scene* scene, const rt_render_para
     CUDA_TRY(cudaEventElapsedTime(&local.ms_tonemap, ctx->ev[1], ctx->ev[2]));
     CUDA_TRY(cudaEventElapsedTime(&local.ms_d2h, ctx->ev[2], ctx->ev[3]));
     local.launches += 1;
+    if (stats) *stats = local;
+    return RT_OK;
+}
+
+size_t rt_jpeg_max_bytes(int32_t width, int32_t height) {
+    if (width <= 0 || height <= 0) return 0;
+    return rtd::jpeg_max_bytes(width, height);
+}
+
+rt_status rt_jpeg_encode_device(rt_context* ctx, const void* rgb8_dev, int32_t width, int32_t height, int32_t quality,
+                                uint8_t* out_jpg, size_t cap, size_t* n_bytes, float* ms_device) {
+    ARG_CHECK(ctx && rgb8_dev && n_bytes, "ctx/rgb8_dev/n_bytes is NULL");
+    ARG_CHECK(width > 0 && height > 0 && width < 65536 && height < 65536, "JPEG dimensions must be in [1, 65535]");
+    rt_status st = make_current(ctx);
+    if (st != RT_OK) return st;
+    return jpeg_from_device(ctx, static_cast<const uint8_t*>(rgb8_dev), width, height, quality, out_jpg, cap, n_bytes, ms_device);
+}
+
+rt_status rt_jpeg_encode(rt_context* ctx, const uint8_t* rgb8, int32_t width, int32_t height, int32_t quality, uint8_t* out_jpg,
+                         size_t cap, size_t* n_bytes) {
+    ARG_CHECK(ctx && rgb8 && n_bytes, "ctx/rgb8/n_bytes is NULL");
+    ARG_CHECK(width > 0 && height > 0 && width < 65536 && height < 65536, "JPEG dimensions must be in [1, 65535]");
+    rt_status st = make_current(ctx);
+    if (st != RT_OK) return st;
+    const size_t npix = size_t(width) * size_t(height);
+    if ((st = ensure_rgb8(ctx, npix)) != RT_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(ctx->rgb8, rgb8, npix * 3, cudaMemcpyHostToDevice, ctx->stream));
+    return jpeg_from_device(ctx, ctx->rgb8, width, height, quality, out_jpg, cap, n_bytes, nullptr);
+}
+
+rt_status rt_write_jpg(rt_context* ctx, const char* path, int32_t width, int32_t height, const uint8_t* rgb8, int32_t quality) {
+    ARG_CHECK(path != nullptr, "path is NULL");
+    const size_t cap = rt_jpeg_max_bytes(width, height);
+    std::vector<uint8_t> buf(cap);
+    size_t n = 0;
+    rt_status st = rt_jpeg_encode(ctx, rgb8, width, height, quality, buf.data(), cap, &n);
+    if (st != RT_OK) return st;
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        set_error("cannot open %s for writing", path);
+        return RT_ERR_IO;
+    }
+    const bool ok = fwrite(buf.data(), 1, n, f) == n;
+    fclose(f);
+    if (!ok) {
+        set_error("short write to %s", path);
+        return RT_ERR_IO;
+    }
+    return RT_OK;
+}
+
+rt_status rt_render_jpeg(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, int32_t quality, uint8_t* out_jpg,
+                         size_t cap, size_t* n_bytes, rt_stats* stats) {
+    ARG_CHECK(ctx && scene && out_jpg && n_bytes, "ctx/scene/out_jpg/n_bytes is NULL");
+    rt_status st = check_params(p);
+    if (st != RT_OK) return st;
+    ARG_CHECK(p->width < 65536 && p->height < 65536, "JPEG dimensions must be in [1, 65535]");
+    if ((st = make_current(ctx)) != RT_OK) return st;
+    const size_t npix = size_t(p->width) * size_t(p->height);
+    if ((st = ensure_accum(ctx, npix)) != RT_OK) return st;
+    if ((st = ensure_rgb8(ctx, npix)) != RT_OK) return st;
+    CUDA_TRY(cudaMemsetAsync(ctx->accum, 0, npix * sizeof(float4), ctx->stream));
+    rt_stats local;
+    if ((st = render_into(ctx, scene, p, ctx->accum, &local)) != RT_OK) return st;
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    rtd::launch_tonemap(ctx->accum, p->width, p->height, nullptr, ctx->rgb8, ctx->stream);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+    float ms_jpg = 0.f;
+    if ((st = jpeg_from_device(ctx, ctx->rgb8, p->width, p->height, quality, out_jpg, cap, n_bytes, &ms_jpg)) != RT_OK) return st;
+    CUDA_TRY(cudaEventElapsedTime(&local.ms_tonemap, ctx->ev[1], ctx->ev[2]));
+    local.ms_d2h = ms_jpg; // device time of the JPEG passes; the D2H copy moves the finished file only
+    local.launches += 8;
     if (stats) *stats = local;
     return RT_OK;
 }

@@ -14,6 +14,7 @@ ROOT = Path(__file__).resolve().parent.parent
 ORACLE_SO = ROOT / "oracle" / "liboracle.so"
 REFCPU_SO = ROOT / "oracle" / "_ref" / "libref_cpu.so"
 REFCPU_RN_SO = ROOT / "oracle" / "_ref" / "libref_cpu_rn.so"
+REFSTB_SO = ROOT / "oracle" / "_ref" / "libref_stb.so"
 _VP = C.c_void_p
 _F3 = C.c_float * 3
 
@@ -238,3 +239,50 @@ def secondary_rays(desc: capi.SceneDesc, hits: np.ndarray, seed: int = 2) -> np.
     c = desc.desc.camera
     rays["time"] = (c.time0 + rng.random(len(h), dtype=np.float32) * (c.time1 - c.time0)).astype(np.float32)
     return rays
+
+
+def _jpeg_call(fn, rgb8: np.ndarray, quality: int) -> bytes:
+    rgb8 = np.ascontiguousarray(rgb8, dtype=np.uint8)
+    h, w = rgb8.shape[:2]
+    cap = 2048 + ((w + 15) // 8) * ((h + 15) // 8) * 3 * 440
+    out = np.empty(cap, dtype=np.uint8)
+    n = fn(rgb8.ctypes.data, w, h, quality, out.ctypes.data, cap)
+    assert n > 0, "encoder returned 0 bytes"
+    return out[:n].tobytes()
+
+
+def oracle_jpeg(rgb8: np.ndarray, quality: int = 100) -> bytes:
+    """oracle/jpeg_oracle.cpp: CPU restatement of stbi_write_jpg (main.cu:491)."""
+    L = C.CDLL(str(ORACLE_SO))
+    L.orc_jpeg_encode.restype = C.c_size_t
+    L.orc_jpeg_encode.argtypes = [_VP, C.c_int, C.c_int, C.c_int, _VP, C.c_size_t]
+    return _jpeg_call(L.orc_jpeg_encode, rgb8, quality)
+
+
+def ref_stb_jpeg(rgb8: np.ndarray, quality: int = 100) -> bytes:
+    """oracle/_ref/libref_stb.so: the reference's vendored stb_image_write.h itself."""
+    L = C.CDLL(str(REFSTB_SO))
+    L.ref_stb_write_jpg.restype = C.c_size_t
+    L.ref_stb_write_jpg.argtypes = [_VP, C.c_int, C.c_int, C.c_int, _VP, C.c_size_t]
+    return _jpeg_call(L.ref_stb_write_jpg, rgb8, quality)
+
+
+def jpeg_test_image(kind: str, w: int, h: int, seed: int = 0) -> np.ndarray:
+    """Deterministic rgb8 inputs for the JPEG parity tests (numpy Generator streams are stable across versions)."""
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    elif kind == "smooth":
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.stack([x * 255 / max(w - 1, 1), y * 255 / max(h - 1, 1), (x + y) * 127 / max(w + h - 2, 1)], -1).astype(np.uint8)
+    elif kind == "flat":
+        img = np.full((h, w, 3), 200, np.uint8)
+    elif kind == "sat":  # saturated checker noise: many 0xFF bytes in the stream, long zero runs at low quality
+        img = (rng.integers(0, 2, (h, w, 3)) * 255).astype(np.uint8)
+    elif kind == "photo":  # smooth + mild noise, like a rendered frame
+        y, x = np.mgrid[0:h, 0:w]
+        base = 128 + 90 * np.sin(x / 17.0)[..., None] * np.cos(y / 11.0)[..., None] * np.array([1.0, 0.7, 0.4])
+        img = np.clip(base + rng.normal(0, 6, (h, w, 3)), 0, 255).astype(np.uint8)
+    else:
+        raise ValueError(kind)
+    return np.ascontiguousarray(img)
