@@ -3,11 +3,16 @@
 // constructor calls), hands the flattened description to the C-ABI, renders, converts with the
 // reference's writer loop and stores the frame.
 //
-//   render_scene [scene] [width height spp] [out.ppm] [earth.ppm]
-//     scene: earth_emitter (default) | book1_final | perlin_motion | random_spheres:N
+//   render_scene [scene] [width height spp] [out] [earth.ppm]            (positional, as before)
+//   render_scene --scene <name | file.json> [--width W --height H --spp N --depth D --seed S]
+//                [--out render.jpg|.ppm] [--quality 100] [--earth assets/earth_stb.ppm]
+//     scene: earth_emitter (default) | book1_final | perlin_motion | random_spheres:N | a JSON document
+//            (include/rt/scene_json.hpp; the reference's compile-time scene and WIDTH/HEIGHT/SAMPLES_PER_PIXEL/SEED
+//            macros, main.cu:15,188-356, common.h:13-20, become runtime input)
+//     out:   *.jpg -> the device output stage (rt_render_jpeg: the same bytes stbi_write_jpg(…, 100) writes,
+//            main.cu:491); anything else -> binary PPM of the same pixels
 //
-// The earth texture is read from a binary PPM of the stb-decoded JPEG (see tools/make_assets.py);
-// JPEG decode/encode themselves are vendored stb in the reference and stay outside this library.
+// The earth texture is read from a binary PPM of the stb-decoded JPEG (see tools/make_assets.py).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,24 +30,63 @@
         }                                                                          \
     } while (0)
 
+static bool ends_with(const std::string& s, const char* suf) {
+    const size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
 int main(int argc, char** argv) {
-    std::string scene_name = argc > 1 ? argv[1] : "earth_emitter";
+    std::string scene_name = "earth_emitter", out_path = "render.jpg", earth_path = "assets/earth_stb.ppm";
+    int quality = 100; // main.cu:491
     rt_render_params p;
     rt_default_render_params(&p); // 1200x600x100, depth 50, seed 1000, tmin 1e-5 (common.h:13-20, main.cu:15,45)
-    if (argc > 4) {
-        p.width = atoi(argv[2]);
-        p.height = atoi(argv[3]);
-        p.spp = atoi(argv[4]);
+    bool size_given = false;
+    std::vector<std::string> pos;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&](const char* what) -> const char* {
+            if (i + 1 >= argc) {
+                fprintf(stderr, "%s needs a value\n", what);
+                exit(2);
+            }
+            return argv[++i];
+        };
+        if (a == "--scene") scene_name = next("--scene");
+        else if (a == "--width") p.width = atoi(next("--width")), size_given = true;
+        else if (a == "--height") p.height = atoi(next("--height")), size_given = true;
+        else if (a == "--spp") p.spp = atoi(next("--spp")), size_given = true;
+        else if (a == "--depth") p.max_depth = atoi(next("--depth"));
+        else if (a == "--seed") p.seed = uint32_t(atoll(next("--seed")));
+        else if (a == "--out") out_path = next("--out");
+        else if (a == "--quality") quality = atoi(next("--quality"));
+        else if (a == "--earth") earth_path = next("--earth");
+        else if (a == "--help" || a == "-h") {
+            printf("render_scene --scene <name|file.json> [--width W --height H --spp N --depth D --seed S] [--out f.jpg|f.ppm] "
+                   "[--quality Q] [--earth earth.ppm]\n");
+            return 0;
+        } else pos.push_back(a);
     }
-    const char* out_path = argc > 5 ? argv[5] : "render.ppm";
-    const char* earth_path = argc > 6 ? argv[6] : "assets/earth_stb.ppm";
+    if (pos.size() > 0) scene_name = pos[0];
+    if (pos.size() > 3) {
+        p.width = atoi(pos[1].c_str());
+        p.height = atoi(pos[2].c_str());
+        p.spp = atoi(pos[3].c_str());
+        size_given = true;
+    }
+    if (pos.size() > 4) out_path = pos[4];
+    if (pos.size() > 5) earth_path = pos[5];
 
     rt::arena A;
     rt::scenes::built b;
     float* earth = nullptr;
-    if (scene_name == "earth_emitter") {
+    rt_scene_desc* json_desc = nullptr;
+    if (ends_with(scene_name, ".json")) {
+        rt_render_params from_doc = p;
+        CHECK(rt_scene_desc_from_json_file(scene_name.c_str(), &from_doc, &json_desc));
+        if (!size_given) p = from_doc; // command-line sizes win over the document's "render" block
+    } else if (scene_name == "earth_emitter") {
         int32_t ew = 0, eh = 0;
-        CHECK(rt_read_ppm_f32(earth_path, &earth, &ew, &eh)); // stbi_loadf equivalent: byte/255.f (main.cu:376-380)
+        CHECK(rt_read_ppm_f32(earth_path.c_str(), &earth, &ew, &eh)); // stbi_loadf equivalent: byte/255.f (main.cu:376-380)
         b = rt::scenes::earth_emitter(A, earth, ew, eh);
     } else if (scene_name == "book1_final") {
         b = rt::scenes::book1_final(A);
@@ -55,8 +99,14 @@ int main(int argc, char** argv) {
         fprintf(stderr, "unknown scene %s\n", scene_name.c_str());
         return 2;
     }
-    rt::flat_scene fs = rt::flatten(*b.list, *b.cam);
-    rt_scene_desc desc = fs.desc();
+    rt::flat_scene fs;
+    rt_scene_desc desc;
+    if (json_desc) {
+        desc = *json_desc;
+    } else {
+        fs = rt::flatten(*b.list, *b.cam);
+        desc = fs.desc();
+    }
 
     rt_context* ctx = nullptr;
     rt_scene* scene = nullptr;
@@ -67,17 +117,32 @@ int main(int argc, char** argv) {
     printf("Rendering a %dx%d image (%d samples per pixel): %u spheres, %u BVH nodes (mode %u, build %.3f ms)\n", p.width,
            p.height, p.spp, info.n_spheres, info.n_nodes, info.bvh_mode, info.ms_build);
 
-    std::vector<float> fb(size_t(p.width) * p.height * 3);
     rt_stats st;
-    CHECK(rt_render(ctx, scene, &p, fb.data(), &st));
-    printf("took %.0fus.  (%.1f Mpaths/s, %.1f Mrays/s, %u launches)\n", st.ms_total * 1e3, st.paths / st.ms_total / 1e3,
-           st.rays / st.ms_total / 1e3, st.launches);
-
-    std::vector<uint8_t> img(fb.size());
-    CHECK(rt_quantize_rgb8(fb.data(), p.width, p.height, img.data())); // main.cu:475-488
-    CHECK(rt_write_ppm(out_path, p.width, p.height, img.data()));
+    if (ends_with(out_path, ".jpg") || ends_with(out_path, ".jpeg")) {
+        // device output stage: finalise, flip, quantise and JPEG-encode on the GPU; only the file comes back
+        std::vector<uint8_t> file(rt_jpeg_max_bytes(p.width, p.height));
+        size_t n = 0;
+        CHECK(rt_render_jpeg(ctx, scene, &p, quality, file.data(), file.size(), &n, &st));
+        FILE* f = fopen(out_path.c_str(), "wb");
+        if (!f || fwrite(file.data(), 1, n, f) != n) {
+            fprintf(stderr, "cannot write %s\n", out_path.c_str());
+            return 1;
+        }
+        fclose(f);
+        printf("took %.0fus.  (%.1f Mpaths/s, %.1f Mrays/s, %u launches; JPEG %zu bytes in %.3f ms on the device)\n", st.ms_total * 1e3,
+               st.paths / st.ms_total / 1e3, st.rays / st.ms_total / 1e3, st.launches, n, st.ms_d2h);
+    } else {
+        std::vector<float> fb(size_t(p.width) * p.height * 3);
+        CHECK(rt_render(ctx, scene, &p, fb.data(), &st));
+        printf("took %.0fus.  (%.1f Mpaths/s, %.1f Mrays/s, %u launches)\n", st.ms_total * 1e3, st.paths / st.ms_total / 1e3,
+               st.rays / st.ms_total / 1e3, st.launches);
+        std::vector<uint8_t> img(fb.size());
+        CHECK(rt_quantize_rgb8(fb.data(), p.width, p.height, img.data())); // main.cu:475-488
+        CHECK(rt_write_ppm(out_path.c_str(), p.width, p.height, img.data()));
+    }
     rt_scene_destroy(scene);
     rt_context_destroy(ctx);
     rt_free(earth);
+    rt_scene_desc_free(json_desc);
     return 0;
 }

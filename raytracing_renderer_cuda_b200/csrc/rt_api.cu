@@ -31,6 +31,13 @@ void set_error(const char* fmt, ...) {
     g_last_error = buf;
 }
 
+} // namespace
+namespace rtd {
+// message hook for the host-only translation unit (rt_host.cpp), which has no CUDA error paths of its own
+void set_error_message(const char* msg) { g_last_error = msg ? msg : ""; }
+} // namespace rtd
+namespace {
+
 #define CUDA_TRY(expr)                                                                          \
     do {                                                                                        \
         cudaError_t e__ = (expr);                                                               \

@@ -7,8 +7,13 @@
 #include <string>
 #include <vector>
 
+#include "../../include/rt/scene_json.hpp"
 #include "../../include/rt/scenes.hpp"
 #include "../../include/rt_api.h"
+
+namespace rtd {
+void set_error_message(const char* msg); // rt_api.cu
+}
 
 namespace {
 
@@ -139,6 +144,61 @@ rt_status rt_builtin_scene(const char* name, const float* image_rgb, int32_t ima
     } catch (const std::exception&) {
         return RT_ERR_INVALID_ARG;
     }
+}
+
+// Runtime scene front-end: JSON text -> façade objects -> flattened description.
+rt_status rt_scene_desc_from_json(const char* json_text, const char* base_dir, rt_render_params* render, rt_scene_desc** out) {
+    if (!json_text || !out) return RT_ERR_INVALID_ARG;
+    *out = nullptr;
+    OwnedDesc* od = nullptr;
+    try {
+        rt::arena A;
+        rt::scenes::json_scene js;
+        auto load = [](const std::string& path, std::vector<float>& rgb, int& w, int& h) {
+            float* p = nullptr;
+            int32_t ww = 0, hh = 0;
+            if (rt_read_ppm_f32(path.c_str(), &p, &ww, &hh) != RT_OK) return false;
+            rgb.assign(p, p + size_t(ww) * size_t(hh) * 3);
+            free(p);
+            w = ww;
+            h = hh;
+            return true;
+        };
+        rt::scenes::scene_from_json(json_text, base_dir ? base_dir : "", load, A, js, render);
+        od = new OwnedDesc();
+        od->fs = rt::flatten(*js.b.list, *js.b.cam);
+        for (const rt_image& im : od->fs.images)
+            od->image_data.emplace_back(im.rgb, im.rgb + size_t(im.width) * size_t(im.height) * 3);
+        od->bind();
+        *out = &od->desc;
+        return RT_OK;
+    } catch (const std::bad_alloc&) {
+        delete od;
+        return RT_ERR_OOM;
+    } catch (const std::exception& e) {
+        delete od;
+        rtd::set_error_message(e.what());
+        return RT_ERR_INVALID_ARG;
+    }
+}
+
+rt_status rt_scene_desc_from_json_file(const char* path, rt_render_params* render, rt_scene_desc** out) {
+    if (!path || !out) return RT_ERR_INVALID_ARG;
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        rtd::set_error_message((std::string("cannot open ") + path).c_str());
+        return RT_ERR_IO;
+    }
+    std::string text;
+    char buf[65536];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, n);
+    fclose(f);
+    std::string dir(path);
+    const size_t slash = dir.find_last_of('/');
+    dir = slash == std::string::npos ? std::string() : dir.substr(0, slash);
+    return rt_scene_desc_from_json(text.c_str(), dir.c_str(), render, out);
 }
 
 void rt_scene_desc_free(rt_scene_desc* desc) {

@@ -94,3 +94,23 @@ def test_8k_frame_properties(ctx):
     assert dec.shape == img.shape and capi.psnr(dec, img, peak=255.0) > 45.0
     band = np.ascontiguousarray(img[:16])
     assert capi.jpeg_encode(ctx, band, 100) == oa.oracle_jpeg(band, 100)
+
+
+def test_cpp_app_renders_a_json_scene_to_jpeg(ctx, scene_descs, tmp_path):
+    """The C++ host program (apps/render_scene.cpp, the replacement of the reference's main()) with a JSON scene and the
+    device output stage, against the same frame rendered through the Python binding."""
+    import subprocess
+    from PIL import Image
+
+    app = ROOT / "apps" / "render_scene"
+    out = tmp_path / "app.jpg"
+    r = subprocess.run([str(app), "--scene", str(ROOT / "assets" / "scenes" / "earth_emitter.json"), "--width", "300", "--height", "150",
+                        "--spp", "16", "--out", str(out)], capture_output=True, text=True, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "JPEG" in r.stdout
+    got = np.asarray(Image.open(out).convert("RGB"))
+    sc = rt.Scene(ctx, scene_descs["earth_emitter"])
+    f, _ = sc.render_jpeg(rt.default_params(width=300, height=150, spp=16), 100)
+    want = np.asarray(Image.open(io.BytesIO(f.tobytes())).convert("RGB"))
+    assert got.shape == want.shape == (150, 300, 3)
+    assert capi.psnr(got, want, peak=255.0) > 50.0  # same paths; float add order may flip a last bit before quantisation

@@ -1,0 +1,103 @@
+"""Runtime scene front-end, no GPU needed: a JSON document must flatten to exactly the description
+the hard-coded restatement of populate_scene_balls (main.cu:188-356) produces, and malformed input must come back as
+an error status with a message — never a crash."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+
+import raytracing_renderer_cuda_b200 as rt
+from raytracing_renderer_cuda_b200 import capi
+from tests.conftest import ROOT
+
+C1_JSON = ROOT / "assets" / "scenes" / "earth_emitter.json"
+
+
+def _raw(ptr, n, T):
+    return bytes(C.cast(ptr, C.POINTER(C.c_uint8 * (n * C.sizeof(T)))).contents) if n else b""
+
+
+def _same_desc(a, b):
+    assert (a.n_spheres, a.n_materials, a.n_textures, a.n_images, a.bvh_mode) == (
+        b.n_spheres, b.n_materials, b.n_textures, b.n_images, b.bvh_mode)
+    assert _raw(a.spheres, a.n_spheres, capi.rt_sphere) == _raw(b.spheres, b.n_spheres, capi.rt_sphere)
+    assert _raw(a.materials, a.n_materials, capi.rt_material) == _raw(b.materials, b.n_materials, capi.rt_material)
+    assert _raw(a.textures, a.n_textures, capi.rt_texture) == _raw(b.textures, b.n_textures, capi.rt_texture)
+    assert bytes(a.camera) == bytes(b.camera)
+    for i in range(a.n_images):
+        ia, ib = a.images[i], b.images[i]
+        assert (ia.width, ia.height) == (ib.width, ib.height)
+        n = ia.width * ia.height * 3
+        assert np.array_equal(np.ctypeslib.as_array(ia.rgb, (n,)), np.ctypeslib.as_array(ib.rgb, (n,)))
+
+
+@pytest.fixture(scope="module")
+def earth_ppm(earth):
+    """assets/earth_stb.ppm is a build artefact (written by __graft_entry__.build()); make it if it is missing."""
+    ppm = ROOT / "assets" / "earth_stb.ppm"
+    if not ppm.exists():
+        b = np.clip(np.rint(earth * 255.0), 0, 255).astype(np.uint8)
+        ppm.write_bytes(b"P6\n%d %d\n255\n" % (b.shape[1], b.shape[0]) + b.tobytes())
+    return ppm
+
+
+def test_c1_document_equals_the_hard_coded_scene(earth, earth_ppm):
+    p = rt.default_params(width=1, height=1, spp=1, seed=5)
+    d = rt.SceneDesc.from_json_file(C1_JSON, p)
+    b = rt.SceneDesc.builtin("earth_emitter", earth)  # keep the owner alive while its arrays are read
+    _same_desc(d.desc, b.desc)
+    # the "render" block replaces the reference's compile-time macros (common.h:13-20, main.cu:15)
+    assert (p.width, p.height, p.spp, p.max_depth, p.seed) == (1200, 600, 100, 50, 1000)
+
+
+def test_every_texture_and_material_kind_parses():
+    doc = {
+        "camera": {"lookfrom": [0, 1, 4], "lookat": [0, 0, 0], "vfov": 30, "aspect": 1.5, "aperture": 0.1, "focus_dist": 3.5},
+        "textures": {"a": {"type": "constant", "color": [0.1, 0.2, 0.3]}, "b": {"type": "noise", "noise": "TURBULANCE", "density": 2},
+                     "c": {"type": "checker", "even": "a", "odd": "b"}, "d": {"type": "wood", "color1": [0.8, 0.6, 0.4], "color2": [0.4, 0.3, 0.3], "density": 10},
+                     "e": {"type": "noise"}},
+        "materials": {"l": {"type": "lambertian", "texture": "c"}, "w": {"type": "lambertian", "texture": "d"},
+                      "m": {"type": "metal", "albedo": [0.7, 0.6, 0.5], "roughness": 3.0}, "g": {"type": "dielectric", "ri": 1.33},
+                      "e": {"type": "diffuse_light", "texture": "e", "intensity": 4}},
+        "objects": [{"type": "sphere", "center": [0, 0, 0], "radius": 1, "material": "l", "id": 7},
+                    {"type": "sphere", "center": [2, 0, 0], "radius": 1, "material": "w"},
+                    {"type": "sphere", "center": [-2, 0, 0], "radius": 1, "material": "m"},
+                    {"type": "moving_sphere", "center0": [0, 2, 0], "center1": [0, 3, 0], "time0": 0, "time1": 1, "radius": 0.5, "material": "g"},
+                    {"type": "sphere", "center": [0, 9, 0], "radius": 3, "material": "e"}],
+        "bvh": "none",
+    }
+    owner = rt.SceneDesc.from_json(json.dumps(doc))
+    d = owner.desc
+    assert d.n_spheres == 5 and d.bvh_mode == capi.RT_BVH_NONE
+    sp = owner.spheres()
+    assert sp["id"][0] == 7 and list(sp["id"][1:]) == [1, 2, 3, 4]
+    mats = np.ctypeslib.as_array(C.cast(d.materials, C.POINTER(C.c_uint8)), (d.n_materials * C.sizeof(capi.rt_material),))
+    assert mats.size
+    assert abs(d.camera.focus_dist - 3.5) < 1e-7 and abs(d.camera.aspect - 1.5) < 1e-7
+    # metal roughness is clamped to 1 by the material constructor (material.h:74-81)
+    m = [d.materials[i] for i in range(d.n_materials)]
+    assert any(abs(x.param - 1.0) < 1e-7 for x in m)
+
+
+@pytest.mark.parametrize("bad", [
+    "", "[]", '{"objects": [}', '{"camera": {}, "objects": []}',
+    '{"camera": {"lookfrom": [0,0,1], "lookat": [0,0,0]}, "objects": [{"type": "sphere", "center": [0,0,0], "radius": 1, "material": "nope"}]}',
+    '{"camera": {"lookfrom": [0,0,1], "lookat": [0,0,0]}, "textures": {"t": {"type": "plaid"}}, "objects": []}',
+    '{"camera": {"lookfrom": [0,0,1], "lookat": [0,0,0]}, "textures": {"t": {"type": "image", "file": "/nonexistent.ppm"}}, "objects": []}',
+    '{"camera": {"lookfrom": [0,0,1], "lookat": [0,0]}, "objects": []}',
+])
+def test_malformed_documents_are_errors(bad):
+    with pytest.raises(capi.RtError) as e:
+        rt.SceneDesc.from_json(bad)
+    assert e.value.status == capi.RT_ERR_INVALID_ARG and str(e.value)
+
+
+def test_cli_help_runs():
+    import subprocess
+
+    app = ROOT / "apps" / "render_scene"
+    if not app.exists():
+        subprocess.check_call(["make", "-C", str(ROOT / "apps")])
+    out = subprocess.run([str(app), "--help"], capture_output=True, text=True)
+    assert out.returncode == 0 and "--scene" in out.stdout and "--quality" in out.stdout
