@@ -313,6 +313,25 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.steps
 
+        # ---- output stage on the device: render + finalise + flip/quantise + JPEG, only the file is read back ----
+        jpeg = None
+        if world == 1:
+            sc = rt.Scene(ctx, desc)
+            file_host = torch.empty(int(ctx.lib.rt_jpeg_max_bytes(W, H)), dtype=torch.uint8).pin_memory()
+            for _ in range(min(args.warmup, 2)):
+                sc.render_jpeg(params, 100, file_host.numpy())
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                f_bytes, st_j = sc.render_jpeg(params, 100, file_host.numpy())
+            t_j = (time.perf_counter() - t0) / args.steps
+            sc.close()
+            jpeg = {"value": float(W) * H * spp / t_j / 1e6, "unit": "Mpaths/s", "ms_per_step": t_j * 1e3,
+                    "ms_device_jpeg": float(st_j.ms_d2h), "d2h_bytes_per_step": int(f_bytes.size), "quality": 100,
+                    "gb_per_s_pixels": W * H * 3 / (float(st_j.ms_d2h) / 1e3) / 1e9 if st_j.ms_d2h > 0 else None,
+                    "what": "rt_render_jpeg: render + finalise + Y-flip/quantise + baseline JPEG (byte-identical to the reference's "
+                            "stbi_write_jpg, main.cu:475-491) on the device; the D2H copy moves the finished file only"}
+
     vals = torch.tensor([ms_step, ms_kernel_span, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     rays_t = torch.tensor([rays_rank], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -346,7 +365,7 @@ def run_ours(args) -> None:
                        "l2": "flushed between timed steps (256 MiB fill, outside the timed spans)",
                        "timing": "sum of per-step CUDA-event spans on the launching stream, max over ranks"},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": traffic, "kernel": "k_wf_step_warp" if int(info.n_nodes) else "k_wf_step_cta", "launches_per_step": n_step_launches,
+                         "traffic": traffic, "kernel": ("k_wf_step_pt" if int(info.n_spheres) >= 4096 else "k_wf_step_warp") if int(info.n_nodes) else "k_wf_step_cta", "launches_per_step": n_step_launches,
                          "avg_launch_ms": dur_launch_s * 1e3, "flop_per_ray": FLOP_PER_RAY[args.config],
                          "peak_source": f"148 SM x 128 lanes x 2 flop x {peaks['sm_max_mhz']:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peaks['source']})",
                          "note": "no dense contraction and L2-resident state: the bounding roofline is FP32 issue (SURVEY.md 8d), not hbm/tensor",
@@ -358,6 +377,8 @@ def run_ours(args) -> None:
             "gpu_launches": int(args.steps * launches_step),  # k_wf_init + k_wf_step x iterations + tonemap / fused reduce-tonemap
             "wavefront_iterations": iters, "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        if jpeg is not None:
+            line["output_stage"] = jpeg
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.config, desc)
         print(json.dumps(line), flush=True)

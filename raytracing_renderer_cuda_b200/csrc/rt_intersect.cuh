@@ -101,6 +101,9 @@ RT_DEV void test_prim(const DScene& sc, const RayQ& q, uint32_t prim, float tmin
 RT_DEV Hit closest_hit_list(const DScene& sc, const RayQ& q, float tmin) {
     Hit best{FLT_MAX, RT_INVALID_ID};
     float t;
+#ifdef RT_LIST_UNROLL
+#pragma unroll RT_LIST_UNROLL
+#endif
     for (uint32_t i = 0; i < sc.n_static; ++i) {
         float4 a = __ldg(&sc.sph_a[i]);
         if (sphere_root_static(q, a, tmin, t)) consider(sc, i, t, best);

@@ -38,7 +38,14 @@ __device__ const uint8_t k_perlin_perm[256] = {
 // so the two neighbouring lookups every hash level needs (perlin_noise.h:67-72) cost one
 // load, and the table is replicated once per bank (word i*32 + lane) so the 32 lanes of a
 // warp never conflict however divergent their lattice cells are.  256 x 32 x 4 B = 32 KB.
-#define RT_PERLIN_SMEM_WORDS (256 * 32)
+// Optionally (RT_PERLIN_GTAB) a second table holds the 16 gradient directions of perlin_noise::grad as float4 coefficient vectors (one
+// LDS.128 per corner, replicated per lane: 16 x 32 x 16 B = 8 KB), see perlin_grad.
+#define RT_PERLIN_PERM_WORDS (256 * 32)
+#ifdef RT_PERLIN_GTAB // opt-in: measured 1 % SLOWER on C1 than the compare/select form (gpurun_out/ab_perlin.log)
+#define RT_PERLIN_SMEM_WORDS (RT_PERLIN_PERM_WORDS + 16 * 32 * 4)
+#else
+#define RT_PERLIN_SMEM_WORDS RT_PERLIN_PERM_WORDS
+#endif
 struct PerlinTab {
     const uint32_t* s; // shared memory, RT_PERLIN_SMEM_WORDS words
     uint32_t lane;
@@ -46,26 +53,49 @@ struct PerlinTab {
 RT_DEV void perlin_stage(uint32_t* smem, uint32_t tid, uint32_t nthreads) {
     // 4 consecutive replica words hold the same pair: one 16-byte store per 4 words
     uint4* s4 = reinterpret_cast<uint4*>(smem);
-    for (uint32_t w = tid; w < RT_PERLIN_SMEM_WORDS / 4; w += nthreads) {
+    for (uint32_t w = tid; w < RT_PERLIN_PERM_WORDS / 4; w += nthreads) {
         uint32_t i = w >> 3;
         uint32_t v = uint32_t(k_perlin_perm[i]) | (uint32_t(k_perlin_perm[(i + 1) & 255]) << 8);
         s4[w] = make_uint4(v, v, v, v);
     }
+#ifdef RT_PERLIN_GTAB
+    // gradient h = hash & 15 (perlin_noise.h:173-181): u = h<8 ? x : y; v = h<4 ? y : (h==12||h==14 ? x : z);
+    // grad = (h&1 ? -u : u) + (h&2 ? -v : v)  ==  cx*x + cy*y + cz*z with two coefficients +-1 and one 0
+    float4* g4 = reinterpret_cast<float4*>(smem + RT_PERLIN_PERM_WORDS);
+    for (uint32_t e = tid; e < 16u * 32u; e += nthreads) {
+        const uint32_t h = e >> 5;
+        float c[3] = {0.f, 0.f, 0.f};
+        const int ua = h < 8u ? 0 : 1;
+        const int va = h < 4u ? 1 : ((h == 12u || h == 14u) ? 0 : 2);
+        c[ua] = (h & 1u) ? -1.f : 1.f;
+        c[va] = (h & 2u) ? -1.f : 1.f;
+        g4[e] = make_float4(c[0], c[1], c[2], 0.f);
+    }
+#endif
 }
 RT_DEV uint32_t perlin_pair(const PerlinTab& pt, uint32_t i) { return pt.s[((i & 255u) << 5) | pt.lane]; }
 
 // perlin_noise::grad (perlin_noise.h:173-181)
-RT_DEV float perlin_grad(uint32_t hash, float x, float y, float z) {
+#ifdef RT_PERLIN_GTAB
+// Table form: exact — the zero coefficient adds nothing and the two unit coefficients give the same single rounding
+// as +-u +-v — and 3 FP instructions + one LDS.128 instead of ~13 compare/select/logic instructions per corner.
+RT_DEV float perlin_grad(const PerlinTab& pt, uint32_t hash, float x, float y, float z) {
+    const float4 c = reinterpret_cast<const float4*>(pt.s + RT_PERLIN_PERM_WORDS)[((hash & 15u) << 5) | pt.lane];
+    return __fmaf_rn(c.z, z, __fmaf_rn(c.y, y, c.x * x));
+}
+#else
+RT_DEV float perlin_grad(const PerlinTab&, uint32_t hash, float x, float y, float z) {
     uint32_t h = hash & 15u;
     float u = h < 8u ? x : y;
     float v = h < 4u ? y : ((h == 12u || h == 14u) ? x : z);
     return ((h & 1u) == 0u ? u : -u) + ((h & 2u) == 0u ? v : -v);
 }
+#endif
 RT_DEV float perlin_ease(float t) { return t * t * t * (t * (t * 6.f - 15.f) + 10.f); } // :156-165
 RT_DEV float perlin_lerp(float t, float a, float b) { return a + t * (b - a); }         // :167-171
 
 // perlin_noise::noise (perlin_noise.h:46-105)
-RT_PERLIN_FN float perlin_noise(const PerlinTab& pt, V3 p) {
+RT_DEV float perlin_noise_body(const PerlinTab& pt, V3 p) {
     float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
     uint32_t xi = uint32_t(int(fx)) & 255u, yi = uint32_t(int(fy)) & 255u, zi = uint32_t(int(fz)) & 255u;
     float xf = p.x - fx, yf = p.y - fy, zf = p.z - fz;
@@ -82,15 +112,38 @@ RT_PERLIN_FN float perlin_noise(const PerlinTab& pt, V3 p) {
     float x1 = xf - 1.f, y1 = yf - 1.f, z1 = zf - 1.f;
     float res = perlin_lerp(
         w,
-        perlin_lerp(v, perlin_lerp(u, perlin_grad(gaa, xf, yf, zf), perlin_grad(gba, x1, yf, zf)),
-                    perlin_lerp(u, perlin_grad(gab, xf, y1, zf), perlin_grad(gbb, x1, y1, zf))),
-        perlin_lerp(v, perlin_lerp(u, perlin_grad(gaa >> 8, xf, yf, z1), perlin_grad(gba >> 8, x1, yf, z1)),
-                    perlin_lerp(u, perlin_grad(gab >> 8, xf, y1, z1), perlin_grad(gbb >> 8, x1, y1, z1))));
+        perlin_lerp(v, perlin_lerp(u, perlin_grad(pt, gaa, xf, yf, zf), perlin_grad(pt, gba, x1, yf, zf)),
+                    perlin_lerp(u, perlin_grad(pt, gab, xf, y1, zf), perlin_grad(pt, gbb, x1, y1, zf))),
+        perlin_lerp(v, perlin_lerp(u, perlin_grad(pt, gaa >> 8, xf, yf, z1), perlin_grad(pt, gba >> 8, x1, yf, z1)),
+                    perlin_lerp(u, perlin_grad(pt, gab >> 8, xf, y1, z1), perlin_grad(pt, gbb >> 8, x1, y1, z1))));
     return (res + 1.0f) / 2.0f;
 }
+RT_PERLIN_FN float perlin_noise(const PerlinTab& pt, V3 p) { return perlin_noise_body(pt, p); }
 
 // perlin_noise::turbulance_noise, implementation 3 (perlin_noise.h:142-153), defaults
 // lacunacity 2, gain .5, 6 octaves (perlin_noise.h:13-17)
+#ifdef RT_PERLIN_PAIR
+// two octaves per call: the two lattice walks (floor -> three dependent table levels -> eight gradients -> seven
+// lerps) are independent, so their fixed-latency chains interleave; the sum is still taken octave by octave
+struct F2 {
+    float a, b;
+};
+RT_PERLIN_FN F2 perlin_noise2(const PerlinTab& pt, V3 p, float f0, float f1) {
+    return F2{perlin_noise_body(pt, p * f0), perlin_noise_body(pt, p * f1)};
+}
+RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
+    float frequency = 1.f, sum = 0.f, amplitude = 1.f;
+    RT_PERLIN_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const F2 r = perlin_noise2(pt, p, frequency, frequency * 2.f);
+        sum += fabsf(r.a * 2.f - 1.f) * amplitude;
+        sum += fabsf(r.b * 2.f - 1.f) * (amplitude * 0.5f);
+        frequency *= 4.f;
+        amplitude *= 0.25f;
+    }
+    return sum;
+}
+#else
 RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
     float frequency = 1.f, sum = 0.f, amplitude = 1.f;
     RT_PERLIN_UNROLL
@@ -102,6 +155,7 @@ RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
     }
     return sum;
 }
+#endif
 
 // ------------------------------------------------------------------ textures ----
 RT_DEV DTexture load_tex(const DScene& sc, int32_t ix) {

@@ -271,6 +271,15 @@ RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfB
     return out_q;
 }
 
+// The frame is over when no path is alive and none can start any more; launches the host enqueued ahead of its
+// polling then have nothing to do.
+RT_DEV bool wf_frame_done(const uint32_t (&n_q)[NQ], unsigned long long path_base, unsigned long long npaths) {
+    uint32_t live = 0;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) live += k == Q_NEW ? 0u : n_q[k];
+    return path_base >= npaths && live == 0u;
+}
+
 // Work granularity, variant 1: a CTA takes 256 consecutive entries of ONE queue and aggregates its pushes in shared
 // memory: one global atomic per CTA chunk and target queue, two block-wide barriers per chunk.  Best when all
 // rays of a chunk cost the same (brute-force scenes): C1 runs 11 % faster this way than with warp chunks, whose
@@ -312,12 +321,13 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     // lowest-numbered one they get, and the noise queues come first; textured emitters may need it too).
     if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
     if (blockIdx.x >= total_chunks) return;
+    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
+    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+    if (wf_frame_done(n_q, path_base, npaths)) return;
     if (sc.has_noise && (blockIdx.x < chunk_end[1] || n_q[Q_EMIT] != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     if (threadIdx.x < 2 * NQ) (&s_count[0][0])[threadIdx.x] = 0u;
     __syncthreads();
 
-    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
-    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
     unsigned long long nrays = 0;
 
     // chunk -> (queue kind, first entry)
@@ -392,6 +402,9 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 #define WF_ROUNDS 1
 #endif
 #define WF_WCHUNK (32 * WF_ROUNDS)
+#ifndef RT_WF_BATCH
+#define RT_WF_BATCH 8u // launches enqueued between two looks at the polled queue sizes
+#endif
 #ifndef RT_PT_MIN_SPHERES
 #define RT_PT_MIN_SPHERES 4096u // persistent-lane kernel from this many primitives on (measured: see profiles/)
 #endif
@@ -442,11 +455,12 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
     const uint32_t warps_per_cta = WF_THREADS / 32;
     if (blockIdx.x * warps_per_cta >= total_chunks) return;
+    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
+    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+    if (wf_frame_done(n_q, path_base, npaths)) return;
     if (sc.has_noise && (chunk_end[1] != 0u || n_q[Q_EMIT] != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     __syncthreads(); // the only block-wide barrier of the kernel
 
-    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
-    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
     unsigned long long nrays = 0;
 
     // Chunks are handed out dynamically (heavy classes first) so no warp idles at the end of the launch; the
@@ -477,7 +491,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
             const bool valid = idx < n_kind;
             const uint32_t slot = valid ? __ldg(q_in + idx) : 0u;
             const int out_q = wf_process_entry<USE_BVH>(sc, rp, wb, pt, kind, valid, slot, path_base + idx, npix, npaths, accum, nrays);
-            outq_pack |= uint32_t(out_q + 1) << (4 * e);
+                outq_pack |= uint32_t(out_q + 1) << (4 * e);
         }
 
         // ---- queue push: ballots over all rounds -> ONE global atomic per target queue and warp chunk ----
@@ -831,7 +845,7 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     snapshot(0);
     int par = 0;
     while (true) {
-        enqueue(8u);
+        enqueue(RT_WF_BATCH);
         snapshot(par ^ 1);
         if (cudaEventSynchronize(ws->poll_ev[par]) != cudaSuccess) break;
         const uint32_t* c = ws->h_counts + par * 3 * NQ + (polled[par].it_after % 3) * NQ; // queues of the next iteration
