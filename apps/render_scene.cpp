@@ -5,12 +5,14 @@
 //
 //   render_scene [scene] [width height spp] [out] [earth.ppm]            (positional, as before)
 //   render_scene --scene <name | file.json> [--width W --height H --spp N --depth D --seed S]
-//                [--out render.jpg|.ppm] [--quality 100] [--earth assets/earth_stb.ppm]
+//                [--out render.jpg|.ppm] [--quality 100] [--earth assets/earth_stb.ppm] [--passes K]
 //     scene: earth_emitter (default) | book1_final | perlin_motion | random_spheres:N | a JSON document
 //            (include/rt/scene_json.hpp; the reference's compile-time scene and WIDTH/HEIGHT/SAMPLES_PER_PIXEL/SEED
 //            macros, main.cu:15,188-356, common.h:13-20, become runtime input)
 //     out:   *.jpg -> the device output stage (rt_render_jpeg: the same bytes stbi_write_jpg(…, 100) writes,
 //            main.cu:491); anything else -> binary PPM of the same pixels
+//     --passes K: progressive accumulation, K passes of --spp samples each into one accumulator; the output file is
+//            rewritten after every pass (PPM only)
 //
 // The earth texture is read from a binary PPM of the stb-decoded JPEG (see tools/make_assets.py).
 #include <cstdio>
@@ -38,6 +40,7 @@ static bool ends_with(const std::string& s, const char* suf) {
 int main(int argc, char** argv) {
     std::string scene_name = "earth_emitter", out_path = "render.jpg", earth_path = "assets/earth_stb.ppm";
     int quality = 100; // main.cu:491
+    int passes = 1;
     rt_render_params p;
     rt_default_render_params(&p); // 1200x600x100, depth 50, seed 1000, tmin 1e-5 (common.h:13-20, main.cu:15,45)
     bool size_given = false;
@@ -60,6 +63,7 @@ int main(int argc, char** argv) {
         else if (a == "--out") out_path = next("--out");
         else if (a == "--quality") quality = atoi(next("--quality"));
         else if (a == "--earth") earth_path = next("--earth");
+        else if (a == "--passes") passes = atoi(next("--passes"));
         else if (a == "--help" || a == "-h") {
             printf("render_scene --scene <name|file.json> [--width W --height H --spp N --depth D --seed S] [--out f.jpg|f.ppm] "
                    "[--quality Q] [--earth earth.ppm]\n");
@@ -118,7 +122,24 @@ int main(int argc, char** argv) {
            p.height, p.spp, info.n_spheres, info.n_nodes, info.bvh_mode, info.ms_build);
 
     rt_stats st;
-    if (ends_with(out_path, ".jpg") || ends_with(out_path, ".jpeg")) {
+    if (passes > 1) { // progressive: the frame on disk sharpens pass by pass
+        struct Sink {
+            const rt_render_params* p;
+            const char* path;
+        } sink{&p, out_path.c_str()};
+        std::vector<float> fb(size_t(p.width) * p.height * 3);
+        auto on_pass = [](int32_t pass, int32_t spp, const float* rgb, void* user) -> int {
+            const Sink* s = static_cast<const Sink*>(user);
+            std::vector<uint8_t> img(size_t(s->p->width) * s->p->height * 3);
+            if (rt_quantize_rgb8(rgb, s->p->width, s->p->height, img.data()) != RT_OK ||
+                rt_write_ppm(s->path, s->p->width, s->p->height, img.data()) != RT_OK)
+                return 1;
+            printf("pass %d: %d samples per pixel written to %s\n", pass, spp, s->path);
+            return 0;
+        };
+        CHECK(rt_render_progressive(ctx, scene, &p, passes, fb.data(), on_pass, &sink, &st));
+        printf("took %.0fus on the device for %d passes (%.1f Mpaths/s)\n", st.ms_total * 1e3, passes, st.paths / st.ms_total / 1e3);
+    } else if (ends_with(out_path, ".jpg") || ends_with(out_path, ".jpeg")) {
         // device output stage: finalise, flip, quantise and JPEG-encode on the GPU; only the file comes back
         std::vector<uint8_t> file(rt_jpeg_max_bytes(p.width, p.height));
         size_t n = 0;

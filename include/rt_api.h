@@ -265,6 +265,16 @@ rt_status rt_render_accum(rt_context* ctx, const rt_scene* scene, const rt_rende
 rt_status rt_render_accum_device(rt_context* ctx, const rt_scene* scene, const rt_render_params* p,
                                  void* accum_dev, rt_stats* stats);
 
+/* Progressive accumulation (the reference's README "interactive" roadmap item, README.md:25-26):
+ * `passes` passes of p->spp samples each are added to ONE accumulator; after every pass the frame is finalised
+ * (the accumulator carries the per-pixel sample count) into out_rgb (HOST, layout of rt_render) and `on_pass`
+ * (may be NULL) is called with the pass index and the samples per pixel so far; a non-zero return stops early.
+ * Pass k uses sample indices [offset + k*spp, offset + (k+1)*spp): the final frame is the frame rt_render
+ * produces with passes*spp samples, up to the order of float additions. */
+typedef int (*rt_progress_fn)(int32_t pass, int32_t spp_so_far, const float* rgb, void* user);
+rt_status rt_render_progressive(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, int32_t passes,
+                                float* out_rgb, rt_progress_fn on_pass, void* user, rt_stats* stats);
+
 /* Pixel finalisation of main.cu:124-127 on the device: col * rz(1/count) ->
  * saturate -> sqrt. out_rgb_dev: width*height*3 floats (reference layout) or NULL;
  * out_rgb8_dev: width*height*3 bytes, Y-flipped and quantised as main.cu:476-487, or NULL. */

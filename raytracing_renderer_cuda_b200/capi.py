@@ -128,6 +128,7 @@ _SIGNATURES = {
     "rt_render": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
     "rt_render_accum": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
     "rt_render_accum_device": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
+    "rt_render_progressive": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), C.c_int32, _VP, _VP, _VP, C.POINTER(rt_stats)]),
     "rt_tonemap_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
     "rt_reduce_tonemap_peers": (C.c_int, [_VP, C.POINTER(_VP), C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           _VP, _VP, _VP]),
@@ -350,6 +351,21 @@ class Scene:
         _check(self.lib, self.lib.rt_render_accum_device(self.ctx._h, self._h, C.byref(params), _VP(accum_ptr),
                                                          C.byref(st) if st is not None else None))
         return st
+
+    def render_progressive(self, params: rt_render_params, passes: int, on_pass=None):
+        """rt_render_progressive: `passes` x params.spp samples into one accumulator; on_pass(pass, spp_so_far, rgb[H,W,3])
+        is called after every pass (return True to stop).  Returns (final frame, stats)."""
+        out = np.empty((params.height, params.width, 3), dtype=np.float32)
+        CB = C.CFUNCTYPE(C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_float), _VP)
+
+        def _cb(k, spp, rgb, _user):
+            return 1 if (on_pass and on_pass(int(k), int(spp), out)) else 0
+
+        cb = CB(_cb)
+        st = rt_stats()
+        _check(self.lib, self.lib.rt_render_progressive(self.ctx._h, self._h, C.byref(params), passes, out.ctypes.data,
+                                                        C.cast(cb, _VP), None, C.byref(st)))
+        return out, st
 
     def render_jpeg(self, params: rt_render_params, quality: int = 100, out: np.ndarray | None = None):
         """rt_render_jpeg: render -> finalise -> flip/quantise -> JPEG on the device; returns (file bytes, stats)."""

@@ -895,4 +895,38 @@ rt_status rt_render_jpeg(rt_context* ctx, const rt_scene* scene, const rt_render
     return RT_OK;
 }
 
+rt_status rt_render_progressive(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, int32_t passes, float* out_rgb,
+                                rt_progress_fn on_pass, void* user, rt_stats* stats) {
+    ARG_CHECK(ctx && scene && out_rgb, "ctx/scene/out_rgb is NULL");
+    ARG_CHECK(passes >= 1, "passes must be >= 1");
+    rt_status st = check_params(p);
+    if (st != RT_OK) return st;
+    if ((st = make_current(ctx)) != RT_OK) return st;
+    const size_t npix = size_t(p->width) * size_t(p->height);
+    if ((st = ensure_accum(ctx, npix)) != RT_OK) return st;
+    if ((st = ensure_out(ctx, npix)) != RT_OK) return st;
+    CUDA_TRY(cudaMemsetAsync(ctx->accum, 0, npix * sizeof(float4), ctx->stream));
+    rt_stats total;
+    memset(&total, 0, sizeof total);
+    for (int32_t k = 0; k < passes; ++k) {
+        rt_render_params pk = *p;
+        pk.sample_offset = p->sample_offset + k * p->spp; // Philox keys use the global sample index: no sample repeats
+        rt_stats local;
+        if ((st = render_into(ctx, scene, &pk, ctx->accum, &local)) != RT_OK) return st;
+        // the accumulator carries the sample count per pixel, so the same finalisation works after every pass
+        rtd::launch_tonemap(ctx->accum, p->width, p->height, ctx->out_rgb, nullptr, ctx->stream);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out_rgb, ctx->out_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        total.paths += local.paths;
+        total.rays += local.rays;
+        total.ms_total += local.ms_total;
+        total.launches += local.launches + 1;
+        total.iterations += local.iterations;
+        if (on_pass && on_pass(k, (k + 1) * p->spp, out_rgb, user) != 0) break; // the caller asked to stop
+    }
+    if (stats) *stats = total;
+    return RT_OK;
+}
+
 } // extern "C"

@@ -270,7 +270,14 @@ RT_DEV Hit closest_hit_bvh_warp(const DScene& sc, const RayQ& q, float tmin, boo
     Trav t;
     trav_begin(sc, q, t);
     if (!has_ray) t.node = RT_TRAV_DONE;
+#ifdef RT_WARP_IFIF // A/B: one step per lane and iteration (inner node, then the leaf it may have reached), no postponing
+    while (__any_sync(0xffffffffu, t.node != RT_TRAV_DONE)) {
+        if (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner(sc, q, tmin, t, stack);
+        if (t.node < 0) trav_leaf(sc, q, tmin, t, stack);
+    }
+#else
     while (__any_sync(0xffffffffu, t.node != RT_TRAV_DONE)) trav_round_warp(sc, q, tmin, t, stack);
+#endif
     return t.best;
 }
 

@@ -315,3 +315,22 @@ def test_errors_are_statuses_not_exits(ctx, scene_descs):
         rt.Scene(ctx, capi.SceneDesc(C.pointer(bad), lib, keepalive=True))
     out = C.c_void_p()
     assert lib.rt_context_create(99, C.byref(out)) == 1  # device out of range
+
+
+def test_progressive_accumulation_converges_to_the_single_pass_frame(ctx, scene_descs):
+    """K passes into one accumulator == one pass with K times the samples (same Philox sample indices; only
+    the order of the float additions differs), and every intermediate frame is closer to it than the one before."""
+    sc = rt.Scene(ctx, scene_descs["earth_emitter"])
+    w, h = 240, 120
+    want, st1 = sc.render(rt.default_params(width=w, height=h, spp=32))
+    seen = []
+    got, st = sc.render_progressive(rt.default_params(width=w, height=h, spp=8), 4, lambda k, spp, rgb: seen.append((k, spp, rgb.copy())) and False)
+    assert [s[:2] for s in seen] == [(0, 8), (1, 16), (2, 24), (3, 32)]
+    assert st.paths == st1.paths and st.rays == st1.rays
+    assert np.abs(got - want).max() < 2e-6
+    psnrs = [capi.psnr(rgb, want) for _, _, rgb in seen]
+    assert psnrs[0] < psnrs[1] < psnrs[2] < psnrs[3]
+    # early stop: the callback's verdict ends the loop
+    calls = []
+    sc.render_progressive(rt.default_params(width=w, height=h, spp=4), 8, lambda k, spp, rgb: calls.append(k) or k == 1)
+    assert calls == [0, 1]
