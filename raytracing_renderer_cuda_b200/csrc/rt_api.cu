@@ -55,17 +55,6 @@ namespace {
         }                                     \
     } while (0)
 
-// round-toward-zero float subtraction on the host == __fsub_rz (used for c1 - c0 of
-// moving_sphere::center, sphere.h:51, which the reference evaluates with vec3 operator-)
-float host_sub_rz(float a, float b) {
-    const int old = std::fegetround();
-    std::fesetround(FE_TOWARDZERO);
-    volatile float va = a, vb = b;
-    volatile float r = va - vb;
-    std::fesetround(old);
-    return r;
-}
-
 } // namespace
 
 struct rt_context {
@@ -445,27 +434,41 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     for (uint32_t i = 0; i < n; ++i)
         if (desc->spheres[i].flags & RT_SPHERE_MOVING) order.push_back(i);
 
+    // ---- acceleration structure: which one ----
+    uint32_t mode = desc->bvh_mode;
+    if (mode == RT_BVH_AUTO) mode = n <= 12 ? RT_BVH_NONE : (n <= 200000 ? RT_BVH_HOST_SAH : RT_BVH_GPU_LBVH);
+    if (n < 2) mode = RT_BVH_NONE;
+
     std::vector<float4> ha(n), hb(n);
     std::vector<uint4> hc(n);
-    std::vector<rth::Box> boxes(n);
+    std::vector<rth::Box> boxes(mode == RT_BVH_HOST_SAH ? n : 0);
+    {
+        // c1 - c0 rounded toward zero (== __fsub_rz, vec3 operator- of moving_sphere::center, sphere.h:51).  The rounding
+        // mode is switched once around this loop, not per operation: at 10^6 spheres a per-call switch
+        // cost 150 ms of every scene upload.
+        const int old_round = std::fegetround();
+        std::fesetround(FE_TOWARDZERO);
+        for (uint32_t k = 0; k < n; ++k) {
+            const rt_sphere& sp = desc->spheres[order[k]];
+            volatile float dx = sp.center1[0], dy = sp.center1[1], dz = sp.center1[2];
+            dx = dx - sp.center0[0];
+            dy = dy - sp.center0[1];
+            dz = dz - sp.center0[2];
+            hb[k] = make_float4(dx, dy, dz, sp.time0);
+        }
+        std::fesetround(old_round);
+    }
     for (uint32_t k = 0; k < n; ++k) {
         const rt_sphere& sp = desc->spheres[order[k]];
         ha[k] = make_float4(sp.center0[0], sp.center0[1], sp.center0[2], sp.radius);
-        hb[k] = make_float4(host_sub_rz(sp.center1[0], sp.center0[0]), host_sub_rz(sp.center1[1], sp.center0[1]),
-                            host_sub_rz(sp.center1[2], sp.center0[2]), sp.time0);
         float dt = sp.time1 - sp.time0; // FADD(RN) in the reference's SASS (sphere.h:51)
         uint32_t dt_bits;
         memcpy(&dt_bits, &dt, 4);
         hc[k] = make_uint4(dt_bits, sp.material, sp.id, order[k]);
         const bool moving = (sp.flags & RT_SPHERE_MOVING) != 0;
-        if (desc->bvh_mode != RT_BVH_GPU_LBVH && desc->bvh_mode != RT_BVH_NONE)
-            boxes[k] = rth::sphere_box(sp.center0, moving ? sp.center1 : sp.center0, sp.radius);
+        if (mode == RT_BVH_HOST_SAH) boxes[k] = rth::sphere_box(sp.center0, moving ? sp.center1 : sp.center0, sp.radius);
     }
 
-    // ---- acceleration structure ----
-    uint32_t mode = desc->bvh_mode;
-    if (mode == RT_BVH_AUTO) mode = n <= 12 ? RT_BVH_NONE : (n <= 200000 ? RT_BVH_HOST_SAH : RT_BVH_GPU_LBVH);
-    if (n < 2) mode = RT_BVH_NONE;
     std::vector<rth::NodeHost> nodes;
     rth::BvhStats bstats;
     const auto t_build0 = std::chrono::steady_clock::now();

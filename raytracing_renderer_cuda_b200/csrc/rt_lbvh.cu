@@ -219,8 +219,10 @@ cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n_stat
     size_t tmp_bytes = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     auto cleanup = [&]() {
-        cudaFree(lo); cudaFree(hi); cudaFree(keys); cudaFree(keys_out); cudaFree(vals); cudaFree(vals_out);
-        cudaFree(parent_inner); cudaFree(parent_leaf); cudaFree(visits); cudaFree(scal); cudaFree(tmp);
+        // stream-ordered pool (the context keeps freed blocks): no device-wide synchronisation per scene build
+        void* all[] = {lo, hi, keys, keys_out, vals, vals_out, parent_inner, parent_leaf, visits, scal, tmp};
+        for (void* p : all)
+            if (p) cudaFreeAsync(p, st);
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
     };
@@ -232,18 +234,18 @@ cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n_stat
             return e;          \
         }                      \
     } while (0)
-    LB_TRY(cudaMalloc(&lo, n * sizeof(float4)));
-    LB_TRY(cudaMalloc(&hi, n * sizeof(float4)));
-    LB_TRY(cudaMalloc(&keys, n * sizeof(unsigned long long)));
-    LB_TRY(cudaMalloc(&keys_out, n * sizeof(unsigned long long)));
-    LB_TRY(cudaMalloc(&vals, n * sizeof(uint32_t)));
-    LB_TRY(cudaMalloc(&vals_out, n * sizeof(uint32_t)));
-    LB_TRY(cudaMalloc(&parent_inner, n * sizeof(int)));
-    LB_TRY(cudaMalloc(&parent_leaf, n * sizeof(int)));
-    LB_TRY(cudaMalloc(&visits, n * sizeof(unsigned)));
-    LB_TRY(cudaMalloc(&scal, 16 * sizeof(unsigned)));
+    LB_TRY(cudaMallocAsync(&lo, n * sizeof(float4), st));
+    LB_TRY(cudaMallocAsync(&hi, n * sizeof(float4), st));
+    LB_TRY(cudaMallocAsync(&keys, n * sizeof(unsigned long long), st));
+    LB_TRY(cudaMallocAsync(&keys_out, n * sizeof(unsigned long long), st));
+    LB_TRY(cudaMallocAsync(&vals, n * sizeof(uint32_t), st));
+    LB_TRY(cudaMallocAsync(&vals_out, n * sizeof(uint32_t), st));
+    LB_TRY(cudaMallocAsync(&parent_inner, n * sizeof(int), st));
+    LB_TRY(cudaMallocAsync(&parent_leaf, n * sizeof(int), st));
+    LB_TRY(cudaMallocAsync(&visits, n * sizeof(unsigned), st));
+    LB_TRY(cudaMallocAsync(&scal, 16 * sizeof(unsigned), st));
     LB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, vals_out, int(n), 0, 63, st));
-    LB_TRY(cudaMalloc(&tmp, tmp_bytes));
+    LB_TRY(cudaMallocAsync(&tmp, tmp_bytes, st));
     LB_TRY(cudaEventCreate(&e0));
     LB_TRY(cudaEventCreate(&e1));
 
