@@ -1,6 +1,7 @@
 // include/rt/scenes.hpp — the benchmark scenes of BASELINE.json, written against the
 // façade exactly the way the reference writes populate_scene_balls (main.cu:188-356).
 //   C1 earth_emitter  : restatement of main.cu:192-349 (8 primitives, camera :331-349)
+//   hdr_sphere        : restatement of the disabled populate_scene_hdr (main.cu:136-182)
 //   C2 book1_final    : Shirley book-1 cover scene, ~484 spheres
 //   C3 perlin_motion  : every texture kind + moving spheres + emitters, 145 primitives
 //   C4 random_spheres : N random spheres + ground (GPU LBVH case)
@@ -78,6 +79,37 @@ inline built earth_emitter(arena& A, const float* earth, int earth_w, int earth_
     b.list->set_id(9);
 
     vec3 lookfrom = vec3(-1, 1, 5);
+    vec3 lookat = vec3(0, 0, -1);
+    float dist_to_focus = (lookfrom - lookat).length();
+    float aperture = .25f;
+    b.cam = A.cam(lookfrom, lookat, vec3(0, 1, 0), 20.f, float(1200) / float(600), aperture, dist_to_focus, 0.f, 0.2f);
+    return b;
+}
+
+// The reference's second hard-coded scene, populate_scene_hdr (main.cu:136-182; compiled out there by SCENE_BALLS,
+// main.cu:17-18, and its textures/hdr.jpg is not shipped): a metal and a lambertian ball inside an r = 10 sphere that
+// emits an environment image; brute-force list (bvh == nullptr).  `env` is the stbi_loadf result the reference would
+// upload (it passes WIDTH*2 x HEIGHT*2 as the image size, main.cu:147: the dimensions of its hdr.jpg).
+inline built hdr_sphere(arena& A, const float* env, int env_w, int env_h) {
+    built b;
+    b.objects.resize(3);
+    hitable_object** objects = b.objects.data();
+
+    objects[0] = A.obj<sphere>(vec3(1., 0, -1), 1.f, A.mat<metal>(vec3(0.8, 0.2, 0.5), 0.05f));
+    objects[0]->set_id(0);
+
+    text* hdr_texture = A.tex<image_texture>(env, env_w, env_h);
+    // sphere 2
+    objects[1] = A.obj<sphere>(vec3(0, 0, 0), 10.f, A.mat<emitter>(hdr_texture));
+    objects[1]->set_id(1);
+
+    objects[2] = A.obj<sphere>(vec3(-1., 0, -1), 1.f, A.mat<lambertian>(A.tex<constant_texture>(vec3(0.6, 0.1, 0.1))));
+    objects[2]->set_id(2);
+
+    b.list = A.obj<hitable_list>(objects, nullptr, 3u);
+    b.list->set_id(3);
+
+    vec3 lookfrom = vec3(-1, 2, 9);
     vec3 lookat = vec3(0, 0, -1);
     float dist_to_focus = (lookfrom - lookat).length();
     float aperture = .25f;

@@ -295,7 +295,12 @@ rt_status rt_reduce_tonemap_peers(rt_context* ctx, const void* const* peer_accum
 /* Host restatement of the writer loop main.cu:475-488 (Y flip + int(255.999f*c)&255). */
 rt_status rt_quantize_rgb8(const float* rgb, int32_t width, int32_t height, uint8_t* out_rgb8);
 rt_status rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t* rgb8);
-rt_status rt_read_ppm_f32(const char* path, float** out_rgb, int32_t* width, int32_t* height); /* byte/255.f */
+rt_status rt_read_ppm_f32(const char* path, float** out_rgb, int32_t* width, int32_t* height); /* P6 or P5, byte/255.f */
+/* Image-texture ingest: the `channels`-component float image stbi_loadf returns (main.cu:376-380;
+ * the reference assumes 3, texture.h:118-132) as the RGB image rt_image carries: grey / grey+alpha replicate the
+ * grey value, RGBA drops alpha.  Any width x height is accepted by rt_scene_create (the reference passes the RENDER
+ * size as the texture size, main.cu:237). */
+rt_status rt_image_to_rgb(const float* data, int32_t width, int32_t height, int32_t channels, float* out_rgb);
 void rt_free(void* p);
 
 /* ---- output stage ------------------------------------------------------------------
@@ -320,7 +325,8 @@ rt_status rt_render_jpeg(rt_context* ctx, const rt_scene* scene, const rt_render
                          uint8_t* out_jpg, size_t cap, size_t* n_bytes, rt_stats* stats);
 
 /* Built-in scene generators written against the façade (BASELINE configs C1..C4):
- * "earth_emitter" (main.cu:188-356), "book1_final", "perlin_motion", "random_spheres".
+ * "earth_emitter" (main.cu:188-356), "hdr_sphere" (main.cu:136-182, needs an environment image), "book1_final",
+ * "perlin_motion", "random_spheres".
  * `image_rgb` (may be NULL unless the scene needs it) is the earth texture; `n` is
  * the primitive count for "random_spheres" (ignored otherwise). The returned desc owns
  * its arrays; release with rt_scene_desc_free. */

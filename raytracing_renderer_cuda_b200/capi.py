@@ -136,6 +136,7 @@ _SIGNATURES = {
     "rt_write_ppm": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _VP]),
     "rt_read_ppm_f32": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32)]),
+    "rt_image_to_rgb": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "rt_free": (None, [_VP]),
     "rt_jpeg_max_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rt_jpeg_encode_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, _VP, C.c_size_t, C.POINTER(C.c_size_t),
@@ -422,6 +423,18 @@ def jpeg_encode_device(ctx: Context, rgb8_ptr: int, width: int, height: int, qua
     _check(ctx.lib, ctx.lib.rt_jpeg_encode_device(ctx._h, _VP(rgb8_ptr), width, height, quality, out.ctypes.data, out.size,
                                                   C.byref(n), C.byref(ms)))
     return n.value, ms.value
+
+
+def image_to_rgb(data: np.ndarray) -> np.ndarray:
+    """rt_image_to_rgb: [H, W, C] float image with C in 1..4 -> [H, W, 3] (what image_texture indexes)."""
+    lib = load_library()
+    data = _f32(data)
+    if data.ndim == 2:
+        data = data[..., None]
+    h, w, c = data.shape
+    out = np.empty((h, w, 3), dtype=np.float32)
+    _check(lib, lib.rt_image_to_rgb(data.ctypes.data, w, h, c, out.ctypes.data))
+    return out
 
 
 def quantize_rgb8(rgb: np.ndarray) -> np.ndarray:

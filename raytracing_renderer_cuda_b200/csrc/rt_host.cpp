@@ -87,7 +87,8 @@ rt_status rt_read_ppm_f32(const char* path, float** out_rgb, int32_t* width, int
             }
         }
     };
-    bool ok = fread(magic, 1, 2, f) == 2 && magic[0] == 'P' && magic[1] == '6';
+    bool ok = fread(magic, 1, 2, f) == 2 && magic[0] == 'P' && (magic[1] == '6' || magic[1] == '5'); // P5: one channel
+    const int ch = magic[1] == '5' ? 1 : 3;
     if (ok) { skip(); ok = fscanf(f, "%d", &w) == 1; }
     if (ok) { skip(); ok = fscanf(f, "%d", &h) == 1; }
     if (ok) { skip(); ok = fscanf(f, "%d", &maxv) == 1; }
@@ -97,16 +98,42 @@ rt_status rt_read_ppm_f32(const char* path, float** out_rgb, int32_t* width, int
         return RT_ERR_IO;
     }
     size_t n = size_t(w) * size_t(h) * 3;
-    std::vector<uint8_t> bytes(n);
-    ok = fread(bytes.data(), 1, n, f) == n;
+    std::vector<uint8_t> bytes(size_t(w) * size_t(h) * size_t(ch));
+    ok = fread(bytes.data(), 1, bytes.size(), f) == bytes.size();
     fclose(f);
     if (!ok) return RT_ERR_IO;
     float* rgb = static_cast<float*>(malloc(n * sizeof(float)));
     if (!rgb) return RT_ERR_OOM;
-    for (size_t i = 0; i < n; ++i) rgb[i] = float(bytes[i]) / 255.0f;
+    if (ch == 3) {
+        for (size_t i = 0; i < n; ++i) rgb[i] = float(bytes[i]) / 255.0f;
+    } else { // grey -> RGB through the same conversion a 1-channel stbi_loadf result takes
+        std::vector<float> g(bytes.size());
+        for (size_t i = 0; i < g.size(); ++i) g[i] = float(bytes[i]) / 255.0f;
+        rt_image_to_rgb(g.data(), w, h, 1, rgb);
+    }
     *out_rgb = rgb;
     *width = w;
     *height = h;
+    return RT_OK;
+}
+
+// What stbi_loadf hands back for a file with `channels` components, as the 3-component image image_texture indexes
+// (texture.h:118-132 assumes RGB, main.cu:384 allocates w*h*ch): grey -> (g,g,g), grey+alpha -> (g,g,g), RGB -> copy,
+// RGBA -> alpha dropped (stb_image.h stbi__convert_format semantics for req_comp = 3).
+rt_status rt_image_to_rgb(const float* data, int32_t width, int32_t height, int32_t channels, float* out_rgb) {
+    if (!data || !out_rgb || width <= 0 || height <= 0 || channels < 1 || channels > 4) return RT_ERR_INVALID_ARG;
+    const size_t n = size_t(width) * size_t(height);
+    for (size_t i = 0; i < n; ++i) {
+        const float* p = data + i * size_t(channels);
+        float* o = out_rgb + i * 3;
+        if (channels <= 2) {
+            o[0] = o[1] = o[2] = p[0];
+        } else {
+            o[0] = p[0];
+            o[1] = p[1];
+            o[2] = p[2];
+        }
+    }
     return RT_OK;
 }
 
@@ -123,6 +150,9 @@ rt_status rt_builtin_scene(const char* name, const float* image_rgb, int32_t ima
         if (nm == "earth_emitter") {
             if (!image_rgb || image_w <= 0 || image_h <= 0) return RT_ERR_INVALID_ARG;
             b = rt::scenes::earth_emitter(A, image_rgb, image_w, image_h, bvh_mode);
+        } else if (nm == "hdr_sphere") {
+            if (!image_rgb || image_w <= 0 || image_h <= 0) return RT_ERR_INVALID_ARG;
+            b = rt::scenes::hdr_sphere(A, image_rgb, image_w, image_h);
         } else if (nm == "book1_final") {
             b = rt::scenes::book1_final(A, bvh_mode);
         } else if (nm == "perlin_motion") {

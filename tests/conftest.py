@@ -68,9 +68,23 @@ def cpu_golden():
 SCENES = ("earth_emitter", "book1_final", "perlin_motion")
 
 
+def make_env_image(w: int = 250, h: int = 130):
+    """Procedural environment image for the reference's second scene (populate_scene_hdr, main.cu:136-182; its
+    textures/hdr.jpg is not shipped).  Deliberately NOT the render size and not a multiple of 8: the reference's
+    image_texture takes any width x height (texture.h:116-132)."""
+    import numpy as np
+
+    v, u = np.mgrid[0:h, 0:w].astype(np.float32)
+    u, v = u / (w - 1), v / (h - 1)
+    sky = np.stack([0.3 + 0.5 * v, 0.45 + 0.4 * v, 0.9 - 0.3 * v], -1)
+    sun = np.exp(-(((u - 0.3) / 0.03) ** 2 + ((v - 0.35) / 0.05) ** 2))[..., None] * np.array([4.0, 3.6, 2.5], np.float32)
+    bands = (0.1 * np.sin(40 * u) * np.cos(25 * v))[..., None]
+    return np.ascontiguousarray(np.clip(sky + bands, 0, 1) + sun, dtype=np.float32)
+
+
 @pytest.fixture(scope="session")
 def scene_descs(earth):
     import raytracing_renderer_cuda_b200 as rt
 
     return {"earth_emitter": rt.SceneDesc.builtin("earth_emitter", earth), "book1_final": rt.SceneDesc.builtin("book1_final"),
-            "perlin_motion": rt.SceneDesc.builtin("perlin_motion")}
+            "perlin_motion": rt.SceneDesc.builtin("perlin_motion"), "hdr_sphere": rt.SceneDesc.builtin("hdr_sphere", make_env_image())}
