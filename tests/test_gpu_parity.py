@@ -334,3 +334,35 @@ def test_progressive_accumulation_converges_to_the_single_pass_frame(ctx, scene_
     calls = []
     sc.render_progressive(rt.default_params(width=w, height=h, spp=4), 8, lambda k, spp, rgb: calls.append(k) or k == 1)
     assert calls == [0, 1]
+
+
+def test_reference_frame_full_size_properties(ctx, scene_descs):
+    """BASELINE config C1 at its full size (1200x600x100, depth 50): properties that need no oracle run — every pixel
+    received exactly spp samples, wavefront and megakernel trace the same paths (same ray count, frames equal up to
+    the order of float additions), and the rays-per-path ratio is the scene's (1.98)."""
+    sc = rt.Scene(ctx, scene_descs["earth_emitter"])
+    p = rt.default_params()
+    assert (p.width, p.height, p.spp, p.max_depth, p.seed) == (1200, 600, 100, 50, 1000)
+    wf, st_wf = sc.render_accum(p)
+    mk, st_mk = sc.render_accum(rt.default_params(pipeline=capi.RT_PIPE_MEGAKERNEL))
+    assert np.array_equal(wf[..., 3], np.full((600, 1200), 100, np.float32)) and np.array_equal(mk[..., 3], wf[..., 3])
+    assert st_wf.paths == st_mk.paths == 72_000_000 and st_wf.rays == st_mk.rays
+    assert 1.95 < st_wf.rays / st_wf.paths < 2.02
+    assert np.allclose(wf[..., :3], mk[..., :3], rtol=1e-4, atol=1e-4)
+
+
+def test_million_sphere_scene_every_kernel_renders_the_same_image(ctx, monkeypatch):
+    """BASELINE config C4's scene (1 M spheres, GPU LBVH): the persistent-lane kernel (default here), the warp-chunk
+    kernel with speculative rounds and the megakernel's per-lane loop visit leaves in different orders; the closest hit
+    — hence the image — must not depend on it (far-bound margin of the slab test)."""
+    d = rt.SceneDesc.builtin("random_spheres", n=1_000_000)
+    sc = rt.Scene(ctx, d)
+    assert sc.info().bvh_mode == capi.RT_BVH_GPU_LBVH and sc.info().n_nodes == 1_000_000
+    w, h, spp = 640, 360, 2
+    ref, st_ref = sc.render_accum(rt.default_params(width=w, height=h, spp=spp, pipeline=capi.RT_PIPE_MEGAKERNEL))
+    for grain in ("pt", "warp"):
+        monkeypatch.setenv("RT_WF_GRAIN", grain)
+        got, st = sc.render_accum(rt.default_params(width=w, height=h, spp=spp))
+        assert st.rays == st_ref.rays, grain
+        assert np.array_equal(got[..., 3], ref[..., 3])
+        assert np.abs(got[..., :3] - ref[..., :3]).max() < 1e-5, grain
