@@ -268,6 +268,85 @@ __global__ void __launch_bounds__(JPG_DCT_THREADS)
     if (live) reinterpret_cast<int4*>(coef + size_t(b) * 64)[r] = reinterpret_cast<const int4*>(s_q[g])[r];
 }
 
+// 4:4:4 (quality > 90, the reference's setting): the three blocks of an MCU share their pixels, so one group of 8
+// threads loads the 8x8 tile ONCE (row r as six 32-bit words when the row is word-aligned) and runs the three
+// transforms from registers; the group's 3 x 64 coefficients leave as 384 contiguous bytes.
+__global__ void __launch_bounds__(JPG_DCT_THREADS)
+    k_jpeg_dct444(const uint8_t* __restrict__ rgb, int w, int h, int mcus_x, uint32_t n_mcus, const JpegTables* __restrict__ tab,
+                  int16_t* __restrict__ coef) {
+    __shared__ float s_t[3][JPG_DCT_THREADS / 8][8][9];
+    __shared__ __align__(16) int16_t s_q[JPG_DCT_THREADS / 8][3][64];
+    __shared__ float s_fd[2][64];
+    __shared__ uint8_t s_zz[64];
+    if (threadIdx.x < 128) (&s_fd[0][0])[threadIdx.x] = (&tab->fdtbl[0][0])[threadIdx.x];
+    if (threadIdx.x < 64) s_zz[threadIdx.x] = tab->zigzag[threadIdx.x];
+    __syncthreads();
+    const int g = threadIdx.x >> 3, r = threadIdx.x & 7;
+    const uint32_t mcu = blockIdx.x * (JPG_DCT_THREADS / 8) + g;
+    const bool live = mcu < n_mcus;
+    float d[3][8];
+    if (live) {
+        const int x0 = int(mcu % uint32_t(mcus_x)) * 8, y0 = int(mcu / uint32_t(mcus_x)) * 8;
+        const int y = y0 + r < h ? y0 + r : h - 1; // edge rows / columns are replicated (stb:1546-1551)
+        const uint8_t* row = rgb + (size_t(y) * w + x0) * 3;
+        uint8_t px[24];
+        if (x0 + 8 <= w && (reinterpret_cast<uintptr_t>(row) & 3u) == 0u) {
+            const uint32_t* r4 = reinterpret_cast<const uint32_t*>(row);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                const uint32_t v = __ldg(r4 + k);
+                px[4 * k] = uint8_t(v);
+                px[4 * k + 1] = uint8_t(v >> 8);
+                px[4 * k + 2] = uint8_t(v >> 16);
+                px[4 * k + 3] = uint8_t(v >> 24);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int x = x0 + c < w ? c : w - 1 - x0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) px[3 * c + k] = row[3 * x + k];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float R = px[3 * c], G = px[3 * c + 1], B = px[3 * c + 2];
+            d[0][c] = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(0.29900f, R), __fmul_rn(0.58700f, G)), __fmul_rn(0.11400f, B)), 128.f);
+            d[1][c] = __fadd_rn(__fsub_rn(__fmul_rn(-0.16874f, R), __fmul_rn(0.33126f, G)), __fmul_rn(0.50000f, B));
+            d[2][c] = __fsub_rn(__fsub_rn(__fmul_rn(0.50000f, R), __fmul_rn(0.41869f, G)), __fmul_rn(0.08131f, B));
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dct8(d[k]); // row r of component k
+#pragma unroll
+            for (int c = 0; c < 8; ++c) s_t[k][g][r][c] = d[k][c];
+        }
+    }
+    __syncwarp();
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[k][i] = s_t[k][g][i][r];
+            dct8(d[k]); // column r: d[k][i] = coefficient (row i, column r)
+            const int tq = k ? 1 : 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = i * 8 + r;
+                const float v = __fmul_rn(d[k][i], s_fd[tq][j]);
+                s_q[g][k][s_zz[j]] = int16_t(__float2int_rz(v < 0.f ? __fsub_rn(v, 0.5f) : __fadd_rn(v, 0.5f)));
+            }
+        }
+    }
+    __syncwarp();
+    if (live) {
+        int4* out = reinterpret_cast<int4*>(coef + size_t(mcu) * 192);
+        const int4* in = reinterpret_cast<const int4*>(&s_q[g][0][0]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) out[k * 8 + r] = in[k * 8 + r];
+    }
+}
+
 // ---- pass 2/4: entropy coding ----------------------------------------------------------------------------------
 // big-endian bit stream in 32-bit words: bit position p lives in word p >> 5 at bit 31 - (p & 31)
 __device__ __forceinline__ void put_bits(uint32_t* __restrict__ words, unsigned long long pos, uint32_t code, uint32_t len) {
@@ -297,8 +376,9 @@ __global__ void __launch_bounds__(JPG_ENT_THREADS)
     if (threadIdx.x < 24) (&s_dc[0][0])[threadIdx.x] = (&tab->dc[0][0])[threadIdx.x];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t b = blockIdx.x * (JPG_ENT_THREADS / 32) + (threadIdx.x >> 5);
-    if (b >= n_blocks) return; // warp-uniform
+    // persistent warps: the 2 KB of code tables are staged once per CTA, not once per 8 blocks
+    const uint32_t warps_total = gridDim.x * (JPG_ENT_THREADS / 32);
+    for (uint32_t b = blockIdx.x * (JPG_ENT_THREADS / 32) + (threadIdx.x >> 5); b < n_blocks; b += warps_total) {
     const int16_t* c = coef + size_t(b) * 64;
     const int c_lo = c[lane], c_hi = c[lane + 32];
     const int tq = subsample ? ((b % 6u) >= 4u ? 1 : 0) : ((b % 3u) ? 1 : 0);
@@ -355,36 +435,82 @@ __global__ void __launch_bounds__(JPG_ENT_THREADS)
     const uint32_t total = sum_lo + sum_hi + (need_eob ? (eob >> 16) : 0u);
     if (!WRITE) {
         if (lane == 0u) block_bits[b] = total;
-        return;
+        continue;
     }
+    // The block's bits are assembled in shared memory — aligned to the 32-bit words of the global stream — with shared
+    // atomics; whole words then leave with plain stores and only the (at most two) words shared with the neighbouring
+    // blocks need a global atomicOr.  (One global atomicOr per symbol cost 590 us on an 8K frame.)
+    __shared__ uint32_t s_bits[JPG_ENT_THREADS / 32][58]; // 27 bits x 64 symbols + 31 bits of lead-in
+    uint32_t* mine = s_bits[threadIdx.x >> 5];
+    __syncwarp(); // the previous block's words have been read out
+    mine[lane] = 0u;
+    if (lane < 26u) mine[32u + lane] = 0u;
+    __syncwarp();
     const unsigned long long base = block_off[b];
-    unsigned long long p = base + (inc_lo - tot_lo);
-    for (uint32_t z = 0; z < nzrl[0]; ++z, p += zrl >> 16) put_bits(words, p, zrl & 0xffffu, zrl >> 16);
-    put_bits(words, p, code[0], len[0]);
-    p = base + sum_lo + (inc_hi - tot_hi);
-    for (uint32_t z = 0; z < nzrl[1]; ++z, p += zrl >> 16) put_bits(words, p, zrl & 0xffffu, zrl >> 16);
-    put_bits(words, p, code[1], len[1]);
-    if (need_eob && lane == 0u) put_bits(words, base + sum_lo + sum_hi, eob & 0xffffu, eob >> 16);
+    const uint32_t lead = uint32_t(base) & 31u;
+    auto put_local = [&](uint32_t pos, uint32_t cbits, uint32_t clen) { // pos relative to the block's first bit
+        if (clen == 0u) return;
+        const uint32_t q = lead + pos, wi = q >> 5, off = q & 31u;
+        const unsigned long long v = (unsigned long long)cbits << (64u - off - clen);
+        atomicOr(mine + wi, uint32_t(v >> 32));
+        if (off + clen > 32u) atomicOr(mine + wi + 1, uint32_t(v));
+    };
+    uint32_t p = inc_lo - tot_lo;
+    for (uint32_t z = 0; z < nzrl[0]; ++z, p += zrl >> 16) put_local(p, zrl & 0xffffu, zrl >> 16);
+    put_local(p, code[0], len[0]);
+    p = sum_lo + (inc_hi - tot_hi);
+    for (uint32_t z = 0; z < nzrl[1]; ++z, p += zrl >> 16) put_local(p, zrl & 0xffffu, zrl >> 16);
+    put_local(p, code[1], len[1]);
+    if (need_eob && lane == 0u) put_local(sum_lo + sum_hi, eob & 0xffffu, eob >> 16);
+    __syncwarp();
+    const uint32_t end = lead + total, n_words = (end + 31u) >> 5;
+    uint32_t* out = words + (base >> 5);
+    for (uint32_t i = lane; i < n_words; i += 32u) {
+        const bool shared_word = (i == 0u && lead != 0u) || (i == n_words - 1u && (end & 31u) != 0u);
+        if (shared_word) atomicOr(out + i, mine[i]);
+        else out[i] = mine[i];
+    }
+    } // persistent loop
 }
 
 // ---- pass 5: byte stuffing ---------------------------------------------------------------------------------------
 #define JPG_STUFF_BYTES 32 // stream bytes per thread
-__device__ __forceinline__ uint32_t stream_byte(const uint32_t* __restrict__ words, unsigned long long i, unsigned long long total_bits) {
-    uint32_t v = (words[i >> 2] >> (24u - 8u * (uint32_t(i) & 3u))) & 255u;
-    // the last byte is padded with ones (stb:1494,1567: fillBits = 7 ones, only whole bytes leave the bit buffer)
-    if (i == (total_bits >> 3) && (total_bits & 7ull)) v |= 0xFFu >> (total_bits & 7ull);
-    return v;
+// A thread's 32 stream bytes as 8 words in MEMORY order (byte k of the chunk = bits 8(k&3).. of S[k>>2]); the last
+// byte of the stream is padded with ones (stb:1494,1567: fillBits = 7 ones, only whole bytes leave the bit buffer).
+__device__ __forceinline__ void load_chunk(const uint32_t* __restrict__ words, uint32_t t, unsigned long long total_bits, uint32_t (&S)[8]) {
+    const uint4* w4 = reinterpret_cast<const uint4*>(words) + size_t(t) * 2;
+    const uint4 a = __ldg(w4), b = __ldg(w4 + 1);
+    uint32_t W[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (total_bits & 7ull) {
+        const unsigned long long last = total_bits >> 3; // index of the partial byte
+        if ((last >> 5) == t) {
+            const uint32_t k = uint32_t(last) & 31u;
+            W[k >> 2] |= (0xFFu >> (total_bits & 7ull)) << (24u - 8u * (k & 3u));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) S[k] = __byte_perm(W[k], 0u, 0x0123); // big-endian stream word -> memory order
+}
+__device__ __forceinline__ uint32_t count_ff(const uint32_t (&S)[8], uint32_t n_valid) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t eq = __vcmpeq4(S[k], 0xFFFFFFFFu); // 0xFF in every byte that is 0xFF
+        if (4u * k + 4u > n_valid) eq &= n_valid > 4u * k ? (1u << (8u * (n_valid - 4u * k))) - 1u : 0u;
+        n += uint32_t(__popc(eq)) >> 3;
+    }
+    return n;
 }
 __global__ void __launch_bounds__(256) k_jpeg_ffcount(const uint32_t* __restrict__ words, const unsigned long long* __restrict__ total_bits_p,
                                                       uint32_t n_threads, unsigned long long* __restrict__ ff) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_threads) return;
     const unsigned long long total_bits = *total_bits_p, n_bytes = (total_bits + 7ull) >> 3;
-    unsigned long long i0 = (unsigned long long)t * JPG_STUFF_BYTES, i1 = i0 + JPG_STUFF_BYTES;
-    if (i1 > n_bytes) i1 = n_bytes;
-    uint32_t n = 0;
-    for (unsigned long long i = i0; i < i1; ++i) n += stream_byte(words, i, total_bits) == 255u;
-    ff[t] = n;
+    const unsigned long long i0 = (unsigned long long)t * JPG_STUFF_BYTES;
+    const uint32_t n_valid = uint32_t(n_bytes - i0 < JPG_STUFF_BYTES ? (n_bytes > i0 ? n_bytes - i0 : 0ull) : JPG_STUFF_BYTES);
+    uint32_t S[8];
+    load_chunk(words, t, total_bits, S);
+    ff[t] = count_ff(S, n_valid);
 }
 __global__ void __launch_bounds__(256) k_jpeg_stuff(const uint32_t* __restrict__ words, const unsigned long long* __restrict__ total_bits_p,
                                                     uint32_t n_threads, const unsigned long long* __restrict__ ff_off,
@@ -392,17 +518,40 @@ __global__ void __launch_bounds__(256) k_jpeg_stuff(const uint32_t* __restrict__
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_threads) return;
     const unsigned long long total_bits = *total_bits_p, n_bytes = (total_bits + 7ull) >> 3;
-    unsigned long long i0 = (unsigned long long)t * JPG_STUFF_BYTES, i1 = i0 + JPG_STUFF_BYTES;
-    if (i1 > n_bytes) i1 = n_bytes;
+    const unsigned long long i0 = (unsigned long long)t * JPG_STUFF_BYTES;
+    const uint32_t n_valid = uint32_t(n_bytes - i0 < JPG_STUFF_BYTES ? (n_bytes > i0 ? n_bytes - i0 : 0ull) : JPG_STUFF_BYTES);
+    uint32_t S[8];
+    load_chunk(words, t, total_bits, S);
     uint8_t* o = out + i0 + ff_off[t];
-    for (unsigned long long i = i0; i < i1; ++i) {
-        const uint32_t v = stream_byte(words, i, total_bits);
-        *o++ = uint8_t(v);
-        if (v == 255u) *o++ = 0;
+    if (n_valid == JPG_STUFF_BYTES && ff_off[t + 1] == ff_off[t]) {
+        // nothing to stuff (7 of 8 chunks): the 32 bytes move as aligned words, shifted to the destination's alignment
+        const uint32_t head = (4u - (uint32_t(reinterpret_cast<uintptr_t>(o)) & 3u)) & 3u;
+        if (head == 0u) {
+            uint4* o4 = reinterpret_cast<uint4*>(o); // 4-byte aligned is all that is known: store word by word
+            uint32_t* o1 = reinterpret_cast<uint32_t*>(o4);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o1[k] = S[k];
+        } else {
+            for (uint32_t k = 0; k < head; ++k) o[k] = uint8_t(S[0] >> (8u * k));
+            uint32_t* o1 = reinterpret_cast<uint32_t*>(o + head);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) o1[k] = __funnelshift_r(S[k], S[k + 1], 8u * head);
+            for (uint32_t k = 0; k < 4u - head; ++k) o[head + 28u + k] = uint8_t(S[7] >> (8u * (head + k)));
+        }
+    } else {
+        for (uint32_t k = 0; k < n_valid; ++k) {
+            const uint32_t v = (S[k >> 2] >> (8u * (k & 3u))) & 255u;
+            *o++ = uint8_t(v);
+            if (v == 255u) *o++ = 0;
+        }
+        if (t == n_threads - 1u) { // the thread that holds the end of the stream: EOI (stb:1570-1571)
+            o[0] = 0xFF;
+            o[1] = 0xD9;
+        }
     }
-    if (t == n_threads - 1u) { // the thread that holds the end of the stream: EOI (stb:1570-1571)
-        o[0] = 0xFF;
-        o[1] = 0xD9;
+    if (t == n_threads - 1u && n_valid == JPG_STUFF_BYTES && ff_off[t + 1] == ff_off[t]) {
+        o[32] = 0xFF;
+        o[33] = 0xD9;
     }
 }
 
@@ -512,9 +661,15 @@ cudaError_t jpeg_encode(JpegState* s, const uint8_t* rgb8_dev, int w, int h, int
 
     JPG_TRY(cudaEventRecord(s->ev[0], st));
     const unsigned dct_grid = unsigned((n_blocks + JPG_DCT_THREADS / 8 - 1) / (JPG_DCT_THREADS / 8));
-    k_jpeg_dct<<<dct_grid, JPG_DCT_THREADS, 0, st>>>(rgb8_dev, w, h, mcus_x, s->subsample ? 1 : 0, uint32_t(n_blocks), s->d_tab,
-                                                     s->coef);
-    const unsigned ent_grid = unsigned((n_blocks + JPG_ENT_THREADS / 32 - 1) / (JPG_ENT_THREADS / 32));
+    if (s->subsample) {
+        k_jpeg_dct<<<dct_grid, JPG_DCT_THREADS, 0, st>>>(rgb8_dev, w, h, mcus_x, 1, uint32_t(n_blocks), s->d_tab, s->coef);
+    } else {
+        const uint32_t n_mcus = uint32_t(n_blocks / 3);
+        k_jpeg_dct444<<<(n_mcus + JPG_DCT_THREADS / 8 - 1) / (JPG_DCT_THREADS / 8), JPG_DCT_THREADS, 0, st>>>(rgb8_dev, w, h, mcus_x, n_mcus,
+                                                                                                   s->d_tab, s->coef);
+    }
+    unsigned ent_grid = unsigned((n_blocks + JPG_ENT_THREADS / 32 - 1) / (JPG_ENT_THREADS / 32));
+    if (ent_grid > 148u * 8u) ent_grid = 148u * 8u; // persistent warps, 8 CTAs of 256 threads per SM
     JPG_TRY(cudaMemsetAsync(s->bits + n_blocks, 0, sizeof(unsigned long long), st));
     k_jpeg_entropy<false><<<ent_grid, JPG_ENT_THREADS, 0, st>>>(s->coef, uint32_t(n_blocks), s->subsample ? 1 : 0, s->d_tab, s->bits,
                                                                 nullptr, nullptr);
@@ -525,7 +680,7 @@ cudaError_t jpeg_encode(JpegState* s, const uint8_t* rgb8_dev, int w, int h, int
     JPG_TRY(cudaStreamSynchronize(st));
     const unsigned long long total_bits = s->h_pin[0];
     const size_t stream_bytes = size_t((total_bits + 7) >> 3);
-    const size_t n_words = (stream_bytes + 3) / 4 + 2;
+    const size_t n_words = ((stream_bytes + 31) / 32) * 8 + 8; // whole 32-byte chunks for the stuffing pass + entropy slack
     if (!grow(s->words, s->words_cap, n_words)) return cudaErrorMemoryAllocation;
     JPG_TRY(cudaMemsetAsync(s->words, 0, n_words * sizeof(uint32_t), st));
     k_jpeg_entropy<true><<<ent_grid, JPG_ENT_THREADS, 0, st>>>(s->coef, uint32_t(n_blocks), s->subsample ? 1 : 0, s->d_tab, nullptr,
