@@ -17,7 +17,7 @@ from pathlib import Path
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "librt_b200.so"
+LIB_PATH = Path(os.environ["RT_B200_LIB"]) if os.environ.get("RT_B200_LIB") else _PKG / "librt_b200.so"  # override: A/B library variants
 
 RT_INVALID_ID = 0xFFFFFFFF
 RT_OK = 0

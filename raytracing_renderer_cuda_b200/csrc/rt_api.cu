@@ -557,6 +557,26 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
             bstats.depth += uint32_t(big.size());
         }
     }
+    rtd::BvhNode4* dnodes4 = nullptr;
+    uint32_t n_nodes4 = 0, root4 = 0;
+    if (dnodes && n_nodes) { // the 4-wide form the persistent-lane kernel walks (half the dependent node fetches per ray)
+        if ((st = dev_alloc(s, &dnodes4, n_nodes / 2 + 64)) != RT_OK) return st;
+        rtd::BvhNode4* scratch = nullptr; // worst case (a degenerate chain) every binary node survives
+        CUDA_TRY(cudaMallocAsync(&scratch, size_t(n_nodes) * sizeof(rtd::BvhNode4), stream));
+        cudaError_t e = rtd::bvh_collapse4(dnodes, n_nodes, bvh_root, bstats.depth, scratch, &n_nodes4, &root4, stream);
+        if (e == cudaSuccess && n_nodes4 <= n_nodes / 2 + 64) {
+            e = cudaMemcpyAsync(dnodes4, scratch, size_t(n_nodes4) * sizeof(rtd::BvhNode4), cudaMemcpyDeviceToDevice, stream);
+        } else if (e == cudaSuccess) { // unusually deep tree: keep the big array itself
+            s->allocs.push_back(scratch);
+            dnodes4 = scratch;
+            scratch = nullptr;
+        }
+        if (scratch) cudaFreeAsync(scratch, stream);
+        if (e != cudaSuccess) {
+            set_error("4-wide BVH collapse failed: %s", cudaGetErrorString(e));
+            return RT_ERR_CUDA;
+        }
+    }
     if (bstats.depth > RT_BVH_STACK_DEPTH) {
         set_error("BVH depth %u exceeds the traversal stack (%d)", bstats.depth, RT_BVH_STACK_DEPTH);
         return RT_ERR_UNSUPPORTED;
@@ -638,6 +658,9 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     s->d.n_spheres = n;
     s->d.n_static = n_static;
     s->d.nodes = dnodes;
+    s->d.nodes4 = dnodes4;
+    s->d.n_nodes4 = n_nodes4;
+    s->d.root4 = root4;
     s->d.n_nodes = n_nodes;
     s->d.root = bvh_root;
     s->d.mats = dmats;

@@ -77,6 +77,16 @@ struct BvhNode {
     float4 rmax; // (R.max.xyz, unused)
 };
 
+// 128-byte 4-wide node: the two children of a binary node replaced by their own children (a leaf child stays).
+// Slot s: box (mn?.s, mx?.s), reference refs.s (>= 0 inner node — the index of the BINARY node it was made from —,
+// < 0 leaf ~prim, RT_BVH4_EMPTY unused).  Built from the binary array by k_collapse4 (rt_lbvh.cu).
+struct BvhNode4 {
+    float4 mnx, mny, mnz, mxx, mxy, mxz;
+    int4 refs;
+    int4 pad;
+};
+#define RT_BVH4_EMPTY 0x7fffffff
+
 #define RT_MAX_IMAGES 8
 #define RT_BVH_STACK_DEPTH 64 // per-thread traversal stack entries (rt_intersect.cuh)
 
@@ -88,6 +98,9 @@ struct DScene {
     uint32_t n_spheres;
     uint32_t n_static;
     const BvhNode* nodes; // nullptr => brute force
+    const BvhNode4* nodes4; // 4-wide form of the same tree (densely renumbered), nullptr if not built
+    uint32_t n_nodes4;
+    uint32_t root4;
     uint32_t n_nodes;
     uint32_t root;        // index of the BVH root node
     const DMaterial* mats;

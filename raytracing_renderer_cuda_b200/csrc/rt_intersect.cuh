@@ -194,7 +194,45 @@ RT_DEV void trav_begin(const DScene& sc, const RayQ& q, Trav& t) {
 #endif
 }
 // one inner-node visit (precondition: t.node >= 0 && t.node != RT_TRAV_DONE)
+template <bool WIDE = false>
 RT_DEV void trav_inner(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {
+  if (WIDE) {
+    // 4-wide node (BvhNode4): seven vector loads, four slab tests in SoA form, the hit children ordered by entry
+    // distance with a 5-comparator network; the nearest is walked next, the others are pushed farthest first.
+    const float4* np = reinterpret_cast<const float4*>(sc.nodes4 + t.node);
+    const float4 mnx = __ldg(np + 0), mny = __ldg(np + 1), mnz = __ldg(np + 2);
+    const float4 mxx = __ldg(np + 3), mxy = __ldg(np + 4), mxz = __ldg(np + 5);
+    const int4 refs = __ldg(reinterpret_cast<const int4*>(np + 6));
+    float key[4];
+    int ref[4] = {refs.x, refs.y, refs.z, refs.w};
+    const float lox[4] = {mnx.x, mnx.y, mnx.z, mnx.w}, loy[4] = {mny.x, mny.y, mny.z, mny.w}, loz[4] = {mnz.x, mnz.y, mnz.z, mnz.w};
+    const float hix[4] = {mxx.x, mxx.y, mxx.z, mxx.w}, hiy[4] = {mxy.x, mxy.y, mxy.z, mxy.w}, hiz[4] = {mxz.x, mxz.y, mxz.z, mxz.w};
+    int nhit = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        float tn;
+        const bool hit = slab(make_float4(lox[s], loy[s], loz[s], 0.f), make_float4(hix[s], hiy[s], hiz[s], 0.f), t.inv, t.noi, t.e, tmin,
+                              t.best.t, tn) && ref[s] != RT_BVH4_EMPTY;
+        key[s] = hit ? tn : __int_as_float(0x7f800000); // +inf: misses sort to the end
+        nhit += hit ? 1 : 0;
+    }
+#define RT_CSWAP(a, b)                       \
+    {                                        \
+        const bool sw = key[b] < key[a];     \
+        const float ka = key[a], kb = key[b]; \
+        const int ra = ref[a], rb = ref[b];  \
+        key[a] = sw ? kb : ka;               \
+        key[b] = sw ? ka : kb;               \
+        ref[a] = sw ? rb : ra;               \
+        ref[b] = sw ? ra : rb;               \
+    }
+    RT_CSWAP(0, 1) RT_CSWAP(2, 3) RT_CSWAP(0, 2) RT_CSWAP(1, 3) RT_CSWAP(1, 2)
+#undef RT_CSWAP
+    if (nhit > 3 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[3];
+    if (nhit > 2 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[2];
+    if (nhit > 1 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[1];
+    t.node = nhit ? ref[0] : (t.sp ? stack[--t.sp] : RT_TRAV_DONE);
+  } else {
     const float4* np = reinterpret_cast<const float4*>(sc.nodes + t.node);
     float4 lmin = __ldg(np + 0), lmax = __ldg(np + 1), rmin = __ldg(np + 2), rmax = __ldg(np + 3);
     float tl, tr;
@@ -212,6 +250,7 @@ RT_DEV void trav_inner(const DScene& sc, const RayQ& q, float tmin, Trav& t, int
     } else {
         t.node = t.sp ? stack[--t.sp] : RT_TRAV_DONE;
     }
+  }
 }
 // one leaf test (precondition: t.node < 0)
 RT_DEV void trav_leaf(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {

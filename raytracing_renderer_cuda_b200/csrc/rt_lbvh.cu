@@ -7,6 +7,7 @@
 #include "rt_lbvh.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace rtd {
 
@@ -204,7 +205,128 @@ __global__ void __launch_bounds__(256) k_depth(int n, const int* __restrict__ pa
     if ((threadIdx.x & 31) == 0) atomicMax(max_depth, d);
 }
 
+// Binary -> 4-wide: node i of the 4-wide array is binary node i with each inner child replaced by that child's two
+// children.  Every binary node is converted (one thread each, no topology walk); a traversal that starts at the root
+// only ever reaches the nodes two binary levels apart.
+__global__ void __launch_bounds__(256) k_collapse4(const BvhNode* __restrict__ nodes, uint32_t n_nodes, BvhNode4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const float4* np = reinterpret_cast<const float4*>(nodes + i);
+    const float4 lmin = np[0], lmax = np[1], rmin = np[2], rmax = np[3];
+    float lo[4][3], hi[4][3];
+    int ref[4];
+    int k = 0;
+    auto put = [&](int r, float4 a, float4 b) {
+        lo[k][0] = a.x; lo[k][1] = a.y; lo[k][2] = a.z;
+        hi[k][0] = b.x; hi[k][1] = b.y; hi[k][2] = b.z;
+        ref[k++] = r;
+    };
+    const int child[2] = {__float_as_int(lmin.w), __float_as_int(lmax.w)};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (child[c] >= 0) {
+            const float4* cp = reinterpret_cast<const float4*>(nodes + child[c]);
+            const float4 a = cp[0], b = cp[1], cc = cp[2], d = cp[3];
+            put(__float_as_int(a.w), a, b);
+            put(__float_as_int(b.w), cc, d);
+        } else {
+            put(child[c], c ? rmin : lmin, c ? rmax : lmax);
+        }
+    }
+    for (; k < 4;) put(RT_BVH4_EMPTY, make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f));
+    BvhNode4 o;
+    o.mnx = make_float4(lo[0][0], lo[1][0], lo[2][0], lo[3][0]);
+    o.mny = make_float4(lo[0][1], lo[1][1], lo[2][1], lo[3][1]);
+    o.mnz = make_float4(lo[0][2], lo[1][2], lo[2][2], lo[3][2]);
+    o.mxx = make_float4(hi[0][0], hi[1][0], hi[2][0], hi[3][0]);
+    o.mxy = make_float4(hi[0][1], hi[1][1], hi[2][1], hi[3][1]);
+    o.mxz = make_float4(hi[0][2], hi[1][2], hi[2][2], hi[3][2]);
+    o.refs = make_int4(ref[0], ref[1], ref[2], ref[3]);
+    o.pad = make_int4(0, 0, 0, 0);
+    out[i] = o;
+}
+
 } // namespace
+
+namespace {
+// nodes a walk from the root can reach in the 4-wide graph, level by level (level[i] = distance from the root + 1)
+__global__ void __launch_bounds__(256) k_mark4(const BvhNode4* __restrict__ n4, uint32_t n_nodes, uint32_t* __restrict__ level, uint32_t cur) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes || level[i] != cur) return;
+    const int4 r = n4[i].refs;
+    const int ref[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (ref[k] >= 0 && ref[k] != RT_BVH4_EMPTY) level[ref[k]] = cur + 1u;
+}
+__global__ void __launch_bounds__(256) k_used4(const uint32_t* __restrict__ level, uint32_t n_nodes, uint32_t* __restrict__ used) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) used[i] = level[i] ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_compact4(const BvhNode4* __restrict__ in, const uint32_t* __restrict__ level,
+                                                  const uint32_t* __restrict__ idx, uint32_t n_nodes, BvhNode4* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes || level[i] == 0u) return;
+    BvhNode4 n = in[i];
+    int* r = reinterpret_cast<int*>(&n.refs);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (r[k] >= 0 && r[k] != RT_BVH4_EMPTY) r[k] = int(idx[r[k]]);
+    out[idx[i]] = n;
+}
+} // namespace
+
+// 4-wide form of a finished binary tree.  Only every other level of the binary tree survives as a 4-wide node, so
+// the reachable nodes are marked from the root, numbered by an exclusive scan and written densely: the array a ray
+// walks is then as large as the binary one (n/2 nodes of 128 B) and can be pinned in L2 as a whole.
+cudaError_t bvh_collapse4(const BvhNode* nodes, uint32_t n_nodes, uint32_t root, uint32_t depth, BvhNode4* out, uint32_t* n_out,
+                          uint32_t* root_out, cudaStream_t st) {
+    *n_out = 0;
+    *root_out = 0;
+    if (n_nodes == 0) return cudaSuccess;
+    BvhNode4* wide = nullptr;
+    uint32_t *level = nullptr, *used = nullptr, *idx = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    auto cleanup = [&]() {
+        void* all[] = {wide, level, used, idx, tmp};
+        for (void* p : all)
+            if (p) cudaFreeAsync(p, st);
+    };
+#define C4_TRY(x)               \
+    do {                        \
+        cudaError_t e_ = (x);   \
+        if (e_ != cudaSuccess) { \
+            cleanup();          \
+            return e_;          \
+        }                       \
+    } while (0)
+    C4_TRY(cudaMallocAsync(&wide, size_t(n_nodes) * sizeof(BvhNode4), st));
+    C4_TRY(cudaMallocAsync(&level, size_t(n_nodes + 1) * sizeof(uint32_t), st));
+    C4_TRY(cudaMallocAsync(&used, size_t(n_nodes + 1) * sizeof(uint32_t), st));
+    C4_TRY(cudaMallocAsync(&idx, size_t(n_nodes + 1) * sizeof(uint32_t), st));
+    C4_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, used, idx, int(n_nodes + 1), st));
+    C4_TRY(cudaMallocAsync(&tmp, tmp_bytes, st));
+    const unsigned blocks = (n_nodes + 255) / 256;
+    k_collapse4<<<blocks, 256, 0, st>>>(nodes, n_nodes, wide);
+    C4_TRY(cudaMemsetAsync(level, 0, size_t(n_nodes + 1) * sizeof(uint32_t), st));
+    const uint32_t one = 1u;
+    C4_TRY(cudaMemcpyAsync(level + root, &one, sizeof one, cudaMemcpyHostToDevice, st));
+    for (uint32_t cur = 1; cur <= depth / 2 + 2; ++cur) k_mark4<<<blocks, 256, 0, st>>>(wide, n_nodes, level, cur);
+    k_used4<<<(n_nodes + 256) / 256, 256, 0, st>>>(level, n_nodes + 1, used); // level[n_nodes] == 0: the scan's total slot
+    C4_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, used, idx, int(n_nodes + 1), st));
+    k_compact4<<<blocks, 256, 0, st>>>(wide, level, idx, n_nodes, out);
+    C4_TRY(cudaGetLastError());
+    uint32_t h[2] = {0, 0};
+    C4_TRY(cudaMemcpyAsync(&h[0], idx + n_nodes, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    C4_TRY(cudaMemcpyAsync(&h[1], idx + root, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    C4_TRY(cudaStreamSynchronize(st));
+#undef C4_TRY
+    *n_out = h[0];
+    *root_out = h[1];
+    cleanup();
+    return cudaSuccess;
+}
 
 cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n_static, const uint32_t* ids, uint32_t n,
                        BvhNode* nodes, cudaStream_t st, float* ms, uint32_t* depth, float root_box[6]) {

@@ -14,4 +14,9 @@ namespace rtd {
 cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n_static, const uint32_t* ids_dev, uint32_t m,
                        BvhNode* nodes_dev, cudaStream_t st, float* ms, uint32_t* depth, float root_box[6]);
 
+// 4-wide form of a finished binary node array (host SAH or LBVH, incl. nodes appended above the root)
+// out: room for n_nodes entries; n_out: nodes written (the reachable ones, densely numbered); root_out: index of the root
+cudaError_t bvh_collapse4(const BvhNode* nodes, uint32_t n_nodes, uint32_t root, uint32_t depth, BvhNode4* out, uint32_t* n_out,
+                          uint32_t* root_out, cudaStream_t st);
+
 } // namespace rtd

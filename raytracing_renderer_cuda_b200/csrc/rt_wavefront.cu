@@ -658,6 +658,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
                 if (wf_begin(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
                     q = make_rayq(ln.r);
                     trav_begin(sc, q, t);
+                    t.node = int(sc.root4); // this kernel walks the 4-wide nodes
                     tracing = true;
                 }
             }
@@ -673,7 +674,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
         do {
             // One inner-node step for every lane that stands at an inner node; lanes that stand at a leaf (or just
             // arrived at one) test it once `leaf_lanes` of them wait, or when no lane can take an inner step.
-            if (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner(sc, q, rp.tmin, t, stack);
+            if (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner<true>(sc, q, rp.tmin, t, stack); // 4-wide nodes
             const unsigned at_leaf = __ballot_sync(0xffffffffu, t.node < 0);
             const unsigned can_go = __ballot_sync(0xffffffffu, t.node >= 0 && t.node != RT_TRAV_DONE);
             if (__popc(at_leaf) >= leaf_lanes || can_go == 0u) {
@@ -799,9 +800,10 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         }
         if (persist_max > 0 && window_max > 0) {
             cudaStreamAttrValue av{};
-            size_t bytes = size_t(sc.n_nodes) * sizeof(BvhNode);
+            const bool wide = grain == G_PT;
+            size_t bytes = size_t(wide ? sc.n_nodes4 : sc.n_nodes) * (wide ? sizeof(BvhNode4) : sizeof(BvhNode));
             if (bytes > size_t(window_max)) bytes = size_t(window_max);
-            av.accessPolicyWindow.base_ptr = const_cast<BvhNode*>(sc.nodes);
+            av.accessPolicyWindow.base_ptr = wide ? (void*)sc.nodes4 : (void*)sc.nodes;
             av.accessPolicyWindow.num_bytes = bytes;
             const float ratio = float(double(persist_max) * 0.9 / double(bytes));
             av.accessPolicyWindow.hitRatio = ratio < 1.f ? ratio : 1.f;

@@ -44,12 +44,14 @@ def test_cuda_matches_oracle_on_ragged_and_edge_sizes(ctx, quality):
 def test_reference_frame_byte_exact(ctx, scene_descs):
     """C1 through the whole device output stage: rt_render_jpeg == stb(quantise(flip(rt_render)))."""
     sc = rt.Scene(ctx, scene_descs["earth_emitter"])
-    p = rt.default_params(width=1200, height=600, spp=4)
+    # one sample per pixel: every pixel is a single float addition, so two renders of the frame are bit-identical
+    # (with more samples the order of the atomic adds may flip a last bit, and with it a byte of the file)
+    p = rt.default_params(width=1200, height=600, spp=1)
     img, _ = sc.render(p)
     rgb8 = capi.quantize_rgb8(img)  # main.cu:475-488 on the host
     f, st = sc.render_jpeg(p, 100)
     assert f.tobytes() == oa.oracle_jpeg(rgb8, 100)
-    assert st.paths == 1200 * 600 * 4 and st.ms_d2h > 0
+    assert st.paths == 1200 * 600 and st.ms_d2h > 0
     from PIL import Image
 
     dec = np.asarray(Image.open(io.BytesIO(f.tobytes())).convert("RGB"))
