@@ -658,7 +658,9 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
                 if (wf_begin(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
                     q = make_rayq(ln.r);
                     trav_begin(sc, q, t);
+#ifndef RT_PT_BINARY
                     t.node = int(sc.root4); // this kernel walks the 4-wide nodes
+#endif
                     tracing = true;
                 }
             }
@@ -674,7 +676,11 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
         do {
             // One inner-node step for every lane that stands at an inner node; lanes that stand at a leaf (or just
             // arrived at one) test it once `leaf_lanes` of them wait, or when no lane can take an inner step.
+#ifdef RT_PT_BINARY // A/B: the binary tree
+            if (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner<false>(sc, q, rp.tmin, t, stack);
+#else
             if (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner<true>(sc, q, rp.tmin, t, stack); // 4-wide nodes
+#endif
             const unsigned at_leaf = __ballot_sync(0xffffffffu, t.node < 0);
             const unsigned can_go = __ballot_sync(0xffffffffu, t.node >= 0 && t.node != RT_TRAV_DONE);
             if (__popc(at_leaf) >= leaf_lanes || can_go == 0u) {
