@@ -144,6 +144,21 @@ RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
     return sum;
 }
 #else
+#if !defined(RT_PERLIN_INLINE) && !defined(RT_PERLIN_TURB_CALLS)
+// ONE out-of-line call per 6-octave evaluation with the noise body inlined in its loop (six calls of perlin_noise cost
+// 1-2 % more on C1/C3: gpurun_out/ab_turbfn.log)
+static __device__ __noinline__ float perlin_turbulence(const PerlinTab& pt, V3 p) {
+    float frequency = 1.f, sum = 0.f, amplitude = 1.f;
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+        float r = perlin_noise_body(pt, p * frequency);
+        sum += fabsf(r * 2.f - 1.f) * amplitude;
+        frequency *= 2.f;
+        amplitude *= 0.5f;
+    }
+    return sum;
+}
+#else
 RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
     float frequency = 1.f, sum = 0.f, amplitude = 1.f;
     RT_PERLIN_UNROLL
@@ -155,6 +170,7 @@ RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
     }
     return sum;
 }
+#endif
 #endif
 
 // ------------------------------------------------------------------ textures ----
