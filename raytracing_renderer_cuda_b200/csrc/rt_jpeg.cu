@@ -8,19 +8,23 @@
 // quality (oracle: oracle/jpeg_oracle.cpp, pinned against the real stb through oracle/_ref).
 //
 // The sequential encoder (one MCU after the other through a 24-bit bit buffer, stb_image_write.h:1223-1238)
-// becomes five data-parallel passes:
-//   k_jpeg_dct      8 threads per 8x8 block: colour transform (stb:1513-1515 / :1552-1554, chroma subsampling
-//                   :1526-1535 for quality <= 90), the float AAN DCT of stb:1240-1286 on rows, a shared-memory
-//                   transpose, the same DCT on columns, quantisation + zigzag (stb:1314-1323) -> int16[64]
-//   k_jpeg_entropy<false>  one warp per block: every lane codes two zigzag positions; zero runs come from
-//                   ballots of the non-zero mask (stb:1325-1365) -> bit length of the block
+// becomes data-parallel passes:
+//   k_jpeg_dct444   (quality > 90, 4:4:4) 8 threads per MCU: the 8x8 tile is loaded once, colour transform
+//                   (stb:1552-1554), stb's float AAN DCT (stb:1240-1286) on rows, a shared-memory transpose, the same
+//                   DCT on columns, quantisation + zigzag (stb:1314-1323) -> int16[3][64]; while the coefficients are
+//                   still in shared memory the same threads compute the bit length of each block's AC symbols
+//   k_jpeg_dcbits   adds the DC symbol (needs the previous block of the component) -> bit length per block
+//   k_jpeg_dct + k_jpeg_entropy<false>   the same two steps for 4:2:0 (quality <= 90, chroma averaged as stb:1526-1535)
 //   cub::DeviceScan exclusive sum -> bit offset of every block
-//   k_jpeg_entropy<true>   same symbols again, written at their final bit position with atomicOr
+//   k_jpeg_entropy<true>   one persistent warp per block, two zigzag positions per lane, zero runs from ballots of the
+//                   non-zero mask (stb:1325-1365); the block's bits are assembled in shared memory and leave as words
 //   k_jpeg_ffcount / scan / k_jpeg_stuff   the 0xFF -> 0xFF 0x00 byte stuffing of stb:1229-1232 as a
-//                   count / scan / scatter, the 1-padding of the last byte (stb:1567) and the EOI marker
+//                   count / scan / scatter of 32-byte chunks, the 1-padding of the last byte (stb:1567) and the EOI marker
 // All float arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) in stb's operation order, which
 // is what a host compiler emits for the reference; the quantiser truncates like its (int) cast.
-// Bound: HBM (3 B/pixel read, 6 B/pixel of int16 coefficients written and read twice, ~1-3 B/pixel of stream).
+// Bound: HBM by design (3 B/pixel read, 6 B/pixel of int16 coefficients written and read once, ~1-2 B/pixel of stream);
+// measured 1.13 ms for an 8K frame = 88 GB/s of pixels — the bit-scatter pass (k_jpeg_entropy<true>, 58 % of the time) is
+// instruction-bound, not bandwidth-bound.
 #include <cub/device/device_scan.cuh>
 
 #include <cstring>
@@ -273,13 +277,15 @@ __global__ void __launch_bounds__(JPG_DCT_THREADS)
 // transforms from registers; the group's 3 x 64 coefficients leave as 384 contiguous bytes.
 __global__ void __launch_bounds__(JPG_DCT_THREADS)
     k_jpeg_dct444(const uint8_t* __restrict__ rgb, int w, int h, int mcus_x, uint32_t n_mcus, const JpegTables* __restrict__ tab,
-                  int16_t* __restrict__ coef) {
+                  int16_t* __restrict__ coef, uint32_t* __restrict__ ac_bits) {
     __shared__ float s_t[3][JPG_DCT_THREADS / 8][8][9];
     __shared__ __align__(16) int16_t s_q[JPG_DCT_THREADS / 8][3][64];
     __shared__ float s_fd[2][64];
     __shared__ uint8_t s_zz[64];
+    __shared__ uint8_t s_aclen[2][256]; // code lengths of the AC symbols (the codes themselves are only needed when writing)
     if (threadIdx.x < 128) (&s_fd[0][0])[threadIdx.x] = (&tab->fdtbl[0][0])[threadIdx.x];
     if (threadIdx.x < 64) s_zz[threadIdx.x] = tab->zigzag[threadIdx.x];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_aclen[0][0])[i] = uint8_t((&tab->ac[0][0])[i] >> 16);
     __syncthreads();
     const int g = threadIdx.x >> 3, r = threadIdx.x & 7;
     const uint32_t mcu = blockIdx.x * (JPG_DCT_THREADS / 8) + g;
@@ -345,6 +351,60 @@ __global__ void __launch_bounds__(JPG_DCT_THREADS)
 #pragma unroll
         for (int k = 0; k < 3; ++k) out[k * 8 + r] = in[k * 8 + r];
     }
+    // Bit length of the AC part of each block while its coefficients are still in shared memory (saves the separate
+    // length pass over 6 B/pixel): thread r owns zigzag positions 8r .. 8r+7; the block's non-zero mask is assembled
+    // with three butterfly steps inside the group of 8; runs and categories as in k_jpeg_entropy (stb:1336-1364).
+    // All 32 lanes take part in the shuffles; dead groups (past the last MCU) carry zeros.
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int tq = k ? 1 : 0;
+        int v[8];
+        uint32_t m8 = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = live ? int(s_q[g][k][8 * r + j]) : 0;
+            if (v[j] != 0 && (r | j) != 0) m8 |= 1u << j; // position 0 is the DC coefficient
+        }
+        uint32_t lo = r < 4 ? m8 << (8 * r) : 0u, hi = r >= 4 ? m8 << (8 * (r - 4)) : 0u;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+            hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+        }
+        const unsigned long long mask = ((unsigned long long)hi << 32) | lo;
+        const uint32_t zrl_len = s_aclen[tq][0xF0];
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (m8 & (1u << j)) {
+                const uint32_t pos = 8u * r + j;
+                const unsigned long long below = mask & ((1ull << pos) - 1ull);
+                const uint32_t prev = below ? 63u - uint32_t(__clzll((long long)below)) : 0u;
+                const uint32_t run = pos - prev - 1u;
+                const int a = v[j] < 0 ? -v[j] : v[j];
+                const uint32_t nb = 32u - uint32_t(__clz(a));
+                bits += (run >> 4) * zrl_len + s_aclen[tq][((run & 15u) << 4) + nb] + nb;
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+        if (live && r == 0) ac_bits[size_t(mcu) * 3 + k] = bits + ((mask >> 63) ? 0u : uint32_t(s_aclen[tq][0x00]));
+    }
+}
+
+// DC part of the block lengths (stb:1325-1334): needs the previous block of the same component, so it runs after the DCT
+__global__ void __launch_bounds__(256) k_jpeg_dcbits(const int16_t* __restrict__ coef, const uint32_t* __restrict__ ac_bits, uint32_t n_blocks,
+                                                     const JpegTables* __restrict__ tab, unsigned long long* __restrict__ block_bits) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const int tq = (b % 3u) ? 1 : 0;
+    const int diff = int(coef[size_t(b) * 64]) - (b >= 3u ? int(coef[size_t(b - 3u) * 64]) : 0);
+    uint32_t n = 0u;
+    if (diff != 0) {
+        const int a = diff < 0 ? -diff : diff;
+        n = 32u - uint32_t(__clz(a));
+    }
+    block_bits[b] = (unsigned long long)(ac_bits[b] + (tab->dc[tq][n] >> 16) + n);
 }
 
 // ---- pass 2/4: entropy coding ----------------------------------------------------------------------------------
@@ -577,6 +637,8 @@ struct JpegState {
     int hdr_w = 0, hdr_h = 0;
     int16_t* coef = nullptr;
     size_t coef_cap = 0;
+    uint32_t* ac_bits = nullptr; // [n_blocks] AC part of the lengths (4:4:4 path)
+    size_t ac_bits_cap = 0;
     unsigned long long* bits = nullptr; // [n_blocks + 1] lengths, then (in place of a second array) ...
     size_t bits_cap = 0;
     unsigned long long* offs = nullptr; // [n_blocks + 1] exclusive sums; offs[n_blocks] = total bits
@@ -612,6 +674,7 @@ void jpeg_destroy(JpegState* s) {
     cudaFree(s->d_tab);
     cudaFree(s->coef);
     cudaFree(s->bits);
+    cudaFree(s->ac_bits);
     cudaFree(s->offs);
     cudaFree(s->words);
     cudaFree(s->ff);
@@ -665,14 +728,17 @@ cudaError_t jpeg_encode(JpegState* s, const uint8_t* rgb8_dev, int w, int h, int
         k_jpeg_dct<<<dct_grid, JPG_DCT_THREADS, 0, st>>>(rgb8_dev, w, h, mcus_x, 1, uint32_t(n_blocks), s->d_tab, s->coef);
     } else {
         const uint32_t n_mcus = uint32_t(n_blocks / 3);
+        if (!grow(s->ac_bits, s->ac_bits_cap, n_blocks)) return cudaErrorMemoryAllocation;
         k_jpeg_dct444<<<(n_mcus + JPG_DCT_THREADS / 8 - 1) / (JPG_DCT_THREADS / 8), JPG_DCT_THREADS, 0, st>>>(rgb8_dev, w, h, mcus_x, n_mcus,
-                                                                                                   s->d_tab, s->coef);
+                                                                                                   s->d_tab, s->coef, s->ac_bits);
     }
     unsigned ent_grid = unsigned((n_blocks + JPG_ENT_THREADS / 32 - 1) / (JPG_ENT_THREADS / 32));
     if (ent_grid > 148u * 8u) ent_grid = 148u * 8u; // persistent warps, 8 CTAs of 256 threads per SM
     JPG_TRY(cudaMemsetAsync(s->bits + n_blocks, 0, sizeof(unsigned long long), st));
-    k_jpeg_entropy<false><<<ent_grid, JPG_ENT_THREADS, 0, st>>>(s->coef, uint32_t(n_blocks), s->subsample ? 1 : 0, s->d_tab, s->bits,
-                                                                nullptr, nullptr);
+    if (s->subsample)
+        k_jpeg_entropy<false><<<ent_grid, JPG_ENT_THREADS, 0, st>>>(s->coef, uint32_t(n_blocks), 1, s->d_tab, s->bits, nullptr, nullptr);
+    else
+        k_jpeg_dcbits<<<unsigned((n_blocks + 255) / 256), 256, 0, st>>>(s->coef, s->ac_bits, uint32_t(n_blocks), s->d_tab, s->bits);
     tmp_bytes = s->scan_tmp_cap;
     JPG_TRY(cub::DeviceScan::ExclusiveSum(s->scan_tmp, tmp_bytes, s->bits, s->offs, int(n_blocks + 1), st));
     // total bits -> host: sizes the word buffer and the stuffing grid
