@@ -351,9 +351,12 @@ def run_ours(args) -> None:
         achieved = flop_launch / dur_launch_s / 1e12
         hbm_achieved = rays_rank * STATE_BYTES_PER_RAY / (ms_kernel_span / 1e3) / 1e9
         traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        ncu_static = None  # what that capture says about issue utilisation / lanes / stalls (static: not measured by this run)
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
-            traffic = (json.loads(tp.read_text()).get(args.config) or {}).get("bytes_per_launch")
+            ent = json.loads(tp.read_text()).get(args.config) or {}
+            traffic = ent.get("bytes_per_launch")
+            ncu_static = ent.get("ncu")
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -365,7 +368,7 @@ def run_ours(args) -> None:
                        "l2": "flushed between timed steps (256 MiB fill, outside the timed spans)",
                        "timing": "sum of per-step CUDA-event spans on the launching stream, max over ranks"},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": traffic, "kernel": ("k_wf_step_pt" if int(info.n_spheres) >= 4096 else "k_wf_step_warp") if int(info.n_nodes) else "k_wf_step_cta", "launches_per_step": n_step_launches,
+                         "traffic": traffic, "ncu": ncu_static, "kernel": ("k_wf_step_pt" if int(info.n_spheres) >= 4096 else "k_wf_step_warp") if int(info.n_nodes) else "k_wf_step_cta", "launches_per_step": n_step_launches,
                          "avg_launch_ms": dur_launch_s * 1e3, "flop_per_ray": FLOP_PER_RAY[args.config],
                          "peak_source": f"148 SM x 128 lanes x 2 flop x {peaks['sm_max_mhz']:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peaks['source']})",
                          "note": "no dense contraction and L2-resident state: the bounding roofline is FP32 issue (SURVEY.md 8d), not hbm/tensor",
