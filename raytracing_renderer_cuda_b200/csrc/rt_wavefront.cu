@@ -35,6 +35,16 @@ namespace rtd {
 enum : int { Q_NEW = 0, Q_LAMB_CONST, Q_LAMB_NOISE1, Q_LAMB_NOISE6, Q_LAMB_IMAGE, Q_METAL, Q_DIEL, Q_EMIT, NQ };
 #define Q_NONE (-1)
 #define WF_THREADS 256
+// Programmatic dependent launch: iteration i+1 is launched while iteration i drains, so its CTAs are resident and
+// waiting (griddepcontrol.wait returns once the previous grid has completed and its writes are visible) instead
+// of paying the launch latency between two of the ~70 dependent launches of a frame.  WF_NO_PDL disables it.
+#ifndef WF_NO_PDL
+#define WF_PDL_PROLOGUE()                                      \
+    asm volatile("griddepcontrol.launch_dependents;");          \
+    asm volatile("griddepcontrol.wait;" ::: "memory")
+#else
+#define WF_PDL_PROLOGUE()
+#endif
 #ifndef WF_MINBLOCKS
 #define WF_MINBLOCKS 4 // 64 registers/thread: 32 warps per SM (A/B on C1: 15.4 ms at 2, 13.5 at 3, 12.6 at 4)
 #endif
@@ -288,6 +298,7 @@ template <bool USE_BVH>
 __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     k_wf_step_cta(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
+    WF_PDL_PROLOGUE();
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t s_count[2][NQ]; // double-buffered by chunk parity: two barriers per chunk instead of four
     __shared__ uint32_t s_base[2][NQ];
@@ -422,6 +433,7 @@ template <bool USE_BVH>
 __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     k_wf_step_warp(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
+    WF_PDL_PROLOGUE();
     extern __shared__ __align__(16) uint32_t smem[];
 
     const PerlinTab pt{smem, threadIdx.x & 31u};
@@ -542,6 +554,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
     k_wf_step_pt(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
                  int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter, int refill, int leaf_lanes) {
+    WF_PDL_PROLOGUE();
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t s_nq[NQ], s_cend[NQ];
 
@@ -819,17 +832,35 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         }
     }
 
+    // every step launch carries the programmatic-stream-serialization attribute (see WF_PDL_PROLOGUE)
+    auto launch = [&](auto kernel, auto... args) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(WF_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+#ifndef WF_NO_PDL
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+#else
+        attr[0].val.programmaticStreamSerializationAllowed = 0;
+#endif
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kernel, args...);
+    };
     uint32_t it = 0;
     auto enqueue = [&](uint32_t count) {
         for (uint32_t k = 0; k < count; ++k, ++it) {
             if (grain == G_PT) {
-                k_wf_step_pt<<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
+                launch(k_wf_step_pt, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
             } else if (warp_grain) {
-                if (use_bvh) k_wf_step_warp<true><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
-                else k_wf_step_warp<false><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
+                if (use_bvh) launch(k_wf_step_warp<true>, sc, rp, wb, int(it), accum, ray_counter);
+                else launch(k_wf_step_warp<false>, sc, rp, wb, int(it), accum, ray_counter);
             } else {
-                if (use_bvh) k_wf_step_cta<true><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
-                else k_wf_step_cta<false><<<grid, WF_THREADS, smem, st>>>(sc, rp, wb, int(it), accum, ray_counter);
+                if (use_bvh) launch(k_wf_step_cta<true>, sc, rp, wb, int(it), accum, ray_counter);
+                else launch(k_wf_step_cta<false>, sc, rp, wb, int(it), accum, ray_counter);
             }
             ++*launches;
         }
