@@ -324,6 +324,34 @@ rt_status rt_write_jpg(rt_context* ctx, const char* path, int32_t width, int32_t
 rt_status rt_render_jpeg(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, int32_t quality,
                          uint8_t* out_jpg, size_t cap, size_t* n_bytes, rt_stats* stats);
 
+/* ---- JPEG reader --------------------------------------------------------------------
+ * Replaces stbi_loadf(path, &w, &h, &ch, 0) with ldr_to_hdr gamma = scale = 1 (main.cu:376-380; vendored stb_image
+ * v2.26) for baseline and progressive 8-bit JPEG files with 1 or 3 components: the Huffman decoding stays on the
+ * host (a serial bit stream), dequantisation + IDCT + chroma up-sampling + YCbCr->RGB + byte/255.f run on the GPU.
+ * The float image equals stb's bit for bit. */
+typedef struct rt_jpeg_component {
+    int32_t h, v, tq;             /* sampling factors, quantiser index */
+    int32_t x, y;                 /* effective pixels of the component */
+    int32_t w2, h2;               /* plane size padded to whole MCUs */
+    int32_t blocks_w, blocks_h;   /* w2 / 8, h2 / 8 */
+    const int16_t* coeff;         /* blocks_w * blocks_h * 64 coefficients, row-major inside a block, not dequantised */
+} rt_jpeg_component;
+typedef struct rt_jpeg_coefficients {
+    int32_t width, height, n_comp, h_max, v_max, progressive, is_rgb;
+    rt_jpeg_component comp[3];
+    uint16_t dequant[4][64];      /* row-major order */
+} rt_jpeg_coefficients;
+/* host half only (no device needed): the decoded coefficient planes; release with rt_jpeg_coefficients_free */
+rt_status rt_jpeg_parse(const uint8_t* file, size_t n_bytes, rt_jpeg_coefficients** out);
+void rt_jpeg_coefficients_free(rt_jpeg_coefficients* c);
+/* whole reader: *out_pixels = malloc'd width*height*channels floats (channels 3, or 1 for a grey file), first row =
+ * top of the picture; release with rt_free.  ms_device (may be NULL): device time of the pixel stages. */
+rt_status rt_jpeg_decode(rt_context* ctx, const uint8_t* file, size_t n_bytes, float** out_pixels, int32_t* width,
+                         int32_t* height, int32_t* channels, float* ms_device);
+/* file -> RGB floats for rt_image: JPEG through rt_jpeg_decode (+ rt_image_to_rgb for grey files), P5/P6 through
+ * rt_read_ppm_f32 */
+rt_status rt_image_load(rt_context* ctx, const char* path, float** out_rgb, int32_t* width, int32_t* height);
+
 /* Built-in scene generators written against the façade (BASELINE configs C1..C4):
  * "earth_emitter" (main.cu:188-356), "hdr_sphere" (main.cu:136-182, needs an environment image), "book1_final",
  * "perlin_motion", "random_spheres".

@@ -7,6 +7,8 @@
 #include <vector>
 #define STB_IMAGE_WRITE_IMPLEMENTATION
 #include "libs/stb/stb_image_write.h"
+#define STB_IMAGE_IMPLEMENTATION
+#include "libs/stb/stb_image.h"
 
 static void sink(void* ctx, void* data, int size) {
     auto* v = static_cast<std::vector<uint8_t>*>(ctx);
@@ -20,4 +22,28 @@ extern "C" size_t ref_stb_write_jpg(const uint8_t* rgb, int w, int h, int qualit
     if (v.size() > cap) return 0;
     memcpy(out, v.data(), v.size());
     return v.size();
+}
+
+// stbi_load_from_memory(file, n, &w, &h, &ch, 0): the 8-bit decode underneath stbi_loadf (main.cu:376-380; the float image
+// is byte / 255.f with the gamma = scale = 1 the reference sets).  Returns channels (0 on failure); out must hold w*h*ch.
+extern "C" int ref_stb_load_jpg(const uint8_t* file, int n, uint8_t* out, size_t cap, int* w, int* h) {
+    int ch = 0;
+    stbi_uc* px = stbi_load_from_memory(file, n, w, h, &ch, 0);
+    if (!px) return 0;
+    const size_t bytes = size_t(*w) * size_t(*h) * size_t(ch);
+    if (bytes <= cap) memcpy(out, px, bytes);
+    stbi_image_free(px);
+    return bytes <= cap ? ch : 0;
+}
+// and the float path itself, exactly as the reference calls it
+extern "C" int ref_stb_loadf_jpg(const uint8_t* file, int n, float* out, size_t cap_floats, int* w, int* h) {
+    int ch = 0;
+    stbi_ldr_to_hdr_scale(1.0f);
+    stbi_ldr_to_hdr_gamma(1.0f);
+    float* px = stbi_loadf_from_memory(file, n, w, h, &ch, 0);
+    if (!px) return 0;
+    const size_t cnt = size_t(*w) * size_t(*h) * size_t(ch);
+    if (cnt <= cap_floats) memcpy(out, px, cnt * sizeof(float));
+    stbi_image_free(px);
+    return cnt <= cap_floats ? ch : 0;
 }

@@ -28,6 +28,8 @@ void orc_camera_ray(const orc_scene* s, float s_, float t_, unsigned long long s
 /* jpeg_oracle.cpp: stbi_write_jpg(..., comp 3, quality) (main.cu:491) into memory; returns the file size
  * (out == NULL: size only), 0 if cap is too small */
 size_t orc_jpeg_encode(const uint8_t* rgb8, int width, int height, int quality, uint8_t* out, size_t cap);
+/* jpeg_decode_oracle.cpp: pixel stages of stb_image's JPEG reader; out = height*width*(3 or 1) bytes; 0 on success */
+int orc_jpeg_pixels(const rt_jpeg_coefficients* c, uint8_t* out);
 #ifdef __cplusplus
 }
 #endif

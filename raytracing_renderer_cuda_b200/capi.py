@@ -53,6 +53,16 @@ class rt_texture(C.Structure):
                 ("color1", C.c_float * 3), ("color2", C.c_float * 3), ("density", C.c_float), ("hardness", C.c_float)]
 
 
+class rt_jpeg_component(C.Structure):
+    _fields_ = [("h", C.c_int32), ("v", C.c_int32), ("tq", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("w2", C.c_int32),
+                ("h2", C.c_int32), ("blocks_w", C.c_int32), ("blocks_h", C.c_int32), ("coeff", C.POINTER(C.c_int16))]
+
+
+class rt_jpeg_coefficients(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("n_comp", C.c_int32), ("h_max", C.c_int32), ("v_max", C.c_int32),
+                ("progressive", C.c_int32), ("is_rgb", C.c_int32), ("comp", rt_jpeg_component * 3), ("dequant", (C.c_uint16 * 64) * 4)]
+
+
 class rt_image(C.Structure):
     _fields_ = [("rgb", C.POINTER(C.c_float)), ("width", C.c_int32), ("height", C.c_int32)]
 
@@ -136,6 +146,11 @@ _SIGNATURES = {
     "rt_write_ppm": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _VP]),
     "rt_read_ppm_f32": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32)]),
+    "rt_jpeg_parse": (C.c_int, [_VP, C.c_size_t, C.POINTER(C.POINTER(rt_jpeg_coefficients))]),
+    "rt_jpeg_coefficients_free": (None, [C.POINTER(rt_jpeg_coefficients)]),
+    "rt_jpeg_decode": (C.c_int, [_VP, _VP, C.c_size_t, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
+    "rt_image_load": (C.c_int, [_VP, C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rt_image_to_rgb": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "rt_free": (None, [_VP]),
     "rt_jpeg_max_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
@@ -179,7 +194,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 
 
 def check_layout(lib: C.CDLL) -> None:
-    for cls in (rt_sphere, rt_material, rt_texture, rt_image, rt_camera, rt_scene_desc, rt_render_params, rt_stats,
+    for cls in (rt_jpeg_component, rt_jpeg_coefficients, rt_sphere, rt_material, rt_texture, rt_image, rt_camera, rt_scene_desc, rt_render_params, rt_stats,
                 rt_scene_info, rt_ray, rt_hit, rt_shade_sample):
         want = lib.rt_abi_sizeof(cls.__name__.encode())
         if want != C.sizeof(cls):
@@ -423,6 +438,30 @@ def jpeg_encode_device(ctx: Context, rgb8_ptr: int, width: int, height: int, qua
     _check(ctx.lib, ctx.lib.rt_jpeg_encode_device(ctx._h, _VP(rgb8_ptr), width, height, quality, out.ctypes.data, out.size,
                                                   C.byref(n), C.byref(ms)))
     return n.value, ms.value
+
+
+def jpeg_parse(file_bytes: bytes):
+    """rt_jpeg_parse: host half of the JPEG reader.  Returns the owning pointer (free with jpeg_coefficients_free)."""
+    lib = load_library()
+    buf = np.frombuffer(file_bytes, dtype=np.uint8)
+    out = C.POINTER(rt_jpeg_coefficients)()
+    _check(lib, lib.rt_jpeg_parse(buf.ctypes.data, buf.size, C.byref(out)))
+    return out
+
+
+def jpeg_coefficients_free(ptr) -> None:
+    load_library().rt_jpeg_coefficients_free(ptr)
+
+
+def jpeg_decode(ctx: "Context", file_bytes: bytes):
+    """rt_jpeg_decode: stbi_loadf(file, &w, &h, &ch, 0) (main.cu:376-380): returns ([H, W, ch] float32, device ms)."""
+    buf = np.frombuffer(file_bytes, dtype=np.uint8)
+    px = C.POINTER(C.c_float)()
+    w, h, ch, ms = C.c_int32(), C.c_int32(), C.c_int32(), C.c_float()
+    _check(ctx.lib, ctx.lib.rt_jpeg_decode(ctx._h, buf.ctypes.data, buf.size, C.byref(px), C.byref(w), C.byref(h), C.byref(ch), C.byref(ms)))
+    out = np.ctypeslib.as_array(px, (h.value, w.value, ch.value)).copy()
+    ctx.lib.rt_free(px)
+    return out, ms.value
 
 
 def image_to_rgb(data: np.ndarray) -> np.ndarray:

@@ -15,6 +15,7 @@
 
 #include "rt_bvh_host.hpp"
 #include "rt_jpeg.cuh"
+#include "rt_jpeg_decode.cuh"
 #include "rt_kernels.cuh"
 #include "rt_lbvh.cuh"
 
@@ -952,6 +953,119 @@ rt_status rt_render_progressive(rt_context* ctx, const rt_scene* scene, const rt
         if (on_pass && on_pass(k, (k + 1) * p->spp, out_rgb, user) != 0) break; // the caller asked to stop
     }
     if (stats) *stats = total;
+    return RT_OK;
+}
+
+namespace {
+struct OwnedCoefficients { // rt_jpeg_coefficients that owns its planes; `pub` must stay the first member
+    rt_jpeg_coefficients pub;
+    rtj::CoefficientImage img;
+};
+} // namespace
+
+rt_status rt_jpeg_parse(const uint8_t* file, size_t n_bytes, rt_jpeg_coefficients** out) {
+    ARG_CHECK(file && out, "file/out is NULL");
+    *out = nullptr;
+    OwnedCoefficients* oc = new (std::nothrow) OwnedCoefficients();
+    if (!oc) return RT_ERR_OOM;
+    if (!rtj::decode_coefficients(file, n_bytes, oc->img)) {
+        set_error("JPEG: %s", oc->img.error.c_str());
+        delete oc;
+        return RT_ERR_INVALID_ARG;
+    }
+    rt_jpeg_coefficients& p = oc->pub;
+    memset(&p, 0, sizeof p);
+    p.width = oc->img.width;
+    p.height = oc->img.height;
+    p.n_comp = oc->img.n_comp;
+    p.h_max = oc->img.h_max;
+    p.v_max = oc->img.v_max;
+    p.progressive = oc->img.progressive ? 1 : 0;
+    p.is_rgb = oc->img.is_rgb ? 1 : 0;
+    for (int k = 0; k < oc->img.n_comp; ++k) {
+        const rtj::Component& c = oc->img.comp[k];
+        p.comp[k] = rt_jpeg_component{c.h, c.v, c.tq, c.x, c.y, c.w2, c.h2, c.blocks_w, c.blocks_h, c.coeff.data()};
+    }
+    memcpy(p.dequant, oc->img.dequant, sizeof p.dequant);
+    *out = &oc->pub;
+    return RT_OK;
+}
+
+void rt_jpeg_coefficients_free(rt_jpeg_coefficients* c) {
+    if (c) delete reinterpret_cast<OwnedCoefficients*>(c);
+}
+
+rt_status rt_jpeg_decode(rt_context* ctx, const uint8_t* file, size_t n_bytes, float** out_pixels, int32_t* width, int32_t* height,
+                         int32_t* channels, float* ms_device) {
+    ARG_CHECK(ctx && file && out_pixels && width && height && channels, "ctx/file/out pointers are NULL");
+    *out_pixels = nullptr;
+    rt_status st = make_current(ctx);
+    if (st != RT_OK) return st;
+    rtj::CoefficientImage img;
+    if (!rtj::decode_coefficients(file, n_bytes, img)) {
+        set_error("JPEG: %s", img.error.c_str());
+        return RT_ERR_INVALID_ARG;
+    }
+    const int ch = img.n_comp == 1 ? 1 : 3;
+    const size_t n = size_t(img.width) * size_t(img.height) * size_t(ch);
+    float* d_out = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_out, n * sizeof(float), ctx->stream));
+    cudaError_t e = rtd::jpeg_pixels_device(img, d_out, ctx->stream, ms_device);
+    float* host = e == cudaSuccess ? static_cast<float*>(malloc(n * sizeof(float))) : nullptr;
+    if (e == cudaSuccess && host) {
+        e = cudaMemcpyAsync(host, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFreeAsync(d_out, ctx->stream);
+    if (e != cudaSuccess) {
+        free(host);
+        set_error("jpeg_decode: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return RT_ERR_CUDA;
+    }
+    if (!host) return RT_ERR_OOM;
+    *out_pixels = host;
+    *width = img.width;
+    *height = img.height;
+    *channels = ch;
+    return RT_OK;
+}
+
+rt_status rt_image_load(rt_context* ctx, const char* path, float** out_rgb, int32_t* width, int32_t* height) {
+    ARG_CHECK(path && out_rgb && width && height, "path/out pointers are NULL");
+    *out_rgb = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        set_error("cannot open %s", path);
+        return RT_ERR_IO;
+    }
+    std::vector<uint8_t> bytes;
+    uint8_t buf[65536];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) bytes.insert(bytes.end(), buf, buf + n);
+    fclose(f);
+    if (bytes.size() >= 2 && bytes[0] == 'P' && (bytes[1] == '6' || bytes[1] == '5')) return rt_read_ppm_f32(path, out_rgb, width, height);
+    ARG_CHECK(ctx != nullptr, "a JPEG file needs a context (the pixel stages run on the device)");
+    float* px = nullptr;
+    int32_t ch = 0;
+    rt_status st = rt_jpeg_decode(ctx, bytes.data(), bytes.size(), &px, width, height, &ch, nullptr);
+    if (st != RT_OK) return st;
+    if (ch == 3) {
+        *out_rgb = px;
+        return RT_OK;
+    }
+    float* rgb = static_cast<float*>(malloc(size_t(*width) * size_t(*height) * 3 * sizeof(float)));
+    if (!rgb) {
+        free(px);
+        return RT_ERR_OOM;
+    }
+    st = rt_image_to_rgb(px, *width, *height, ch, rgb);
+    free(px);
+    if (st != RT_OK) {
+        free(rgb);
+        return st;
+    }
+    *out_rgb = rgb;
     return RT_OK;
 }
 

@@ -286,3 +286,29 @@ def jpeg_test_image(kind: str, w: int, h: int, seed: int = 0) -> np.ndarray:
     else:
         raise ValueError(kind)
     return np.ascontiguousarray(img)
+
+
+def oracle_jpeg_pixels(coeffs_ptr) -> np.ndarray:
+    """oracle/jpeg_decode_oracle.cpp: coefficient planes (capi.jpeg_parse) -> [H, W, ch] bytes."""
+    L = C.CDLL(str(ORACLE_SO))
+    L.orc_jpeg_pixels.restype = C.c_int
+    L.orc_jpeg_pixels.argtypes = [_VP, _VP]
+    c = coeffs_ptr.contents
+    ch = 1 if c.n_comp == 1 else 3
+    out = np.zeros((c.height, c.width, ch), dtype=np.uint8)
+    assert L.orc_jpeg_pixels(C.cast(coeffs_ptr, _VP), out.ctypes.data) == 0
+    return out
+
+
+def ref_stb_load_jpeg(file_bytes: bytes) -> np.ndarray:
+    """oracle/_ref/libref_stb.so: stbi_load_from_memory(..., 0) of the reference's vendored stb_image.h -> [H, W, ch] bytes."""
+    L = C.CDLL(str(REFSTB_SO))
+    L.ref_stb_load_jpg.restype = C.c_int
+    L.ref_stb_load_jpg.argtypes = [_VP, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    buf = np.frombuffer(file_bytes, dtype=np.uint8)
+    cap = 64 << 20
+    out = np.zeros(cap, dtype=np.uint8)
+    w, h = C.c_int(), C.c_int()
+    ch = L.ref_stb_load_jpg(buf.ctypes.data, buf.size, out.ctypes.data, cap, C.byref(w), C.byref(h))
+    assert ch > 0, "stb could not decode the file"
+    return out[:w.value * h.value * ch].reshape(h.value, w.value, ch).copy()
