@@ -14,7 +14,8 @@
 //     --passes K: progressive accumulation, K passes of --spp samples each into one accumulator; the output file is
 //            rewritten after every pass (PPM only)
 //
-// The earth texture is read from a binary PPM of the stb-decoded JPEG (see tools/make_assets.py).
+// The earth texture: --earth textures/earth.jpg (decoded by rt_image_load exactly as stbi_loadf does) or a binary PPM
+// of the stb-decoded bytes (assets/earth_stb.ppm, written by __graft_entry__.build()).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -80,6 +81,8 @@ int main(int argc, char** argv) {
     if (pos.size() > 4) out_path = pos[4];
     if (pos.size() > 5) earth_path = pos[5];
 
+    rt_context* ctx = nullptr;
+    CHECK(rt_context_create(0, &ctx));
     rt::arena A;
     rt::scenes::built b;
     float* earth = nullptr;
@@ -90,7 +93,9 @@ int main(int argc, char** argv) {
         if (!size_given) p = from_doc; // command-line sizes win over the document's "render" block
     } else if (scene_name == "earth_emitter") {
         int32_t ew = 0, eh = 0;
-        CHECK(rt_read_ppm_f32(earth_path.c_str(), &earth, &ew, &eh)); // stbi_loadf equivalent: byte/255.f (main.cu:376-380)
+        // stbi_loadf (main.cu:376-380): a .jpg goes through the JPEG reader (host Huffman + device pixel stages, the same
+        // floats stb returns), a .ppm/.pgm is read directly
+        CHECK(rt_image_load(ctx, earth_path.c_str(), &earth, &ew, &eh));
         b = rt::scenes::earth_emitter(A, earth, ew, eh);
     } else if (scene_name == "book1_final") {
         b = rt::scenes::book1_final(A);
@@ -112,9 +117,7 @@ int main(int argc, char** argv) {
         desc = fs.desc();
     }
 
-    rt_context* ctx = nullptr;
     rt_scene* scene = nullptr;
-    CHECK(rt_context_create(0, &ctx));
     CHECK(rt_scene_create(ctx, &desc, &scene));
     rt_scene_info info;
     CHECK(rt_scene_get_info(scene, &info));

@@ -70,3 +70,20 @@ def test_round_trip_with_the_device_writer(ctx):
     back, _ = capi.jpeg_decode(ctx, capi.jpeg_encode(ctx, img, 100))
     assert back.shape == (200, 320, 3)
     assert np.abs(back * 255.0 - img.astype(np.float32)).max() <= 6.0
+
+
+@pytest.mark.skipif(not EARTH_JPG.exists(), reason="needs the reference's earth.jpg (oracle/_ref travels to the GPU box)")
+def test_cpp_app_reads_the_jpeg_texture_like_the_reference_main(tmp_path):
+    """apps/render_scene with --earth textures/earth.jpg (what the reference's main() opens, main.cu:134,380) renders the
+    same frame as with the pre-decoded PPM: one sample per pixel, so the two frames are bit-identical."""
+    import subprocess
+
+    app = ROOT / "apps" / "render_scene"
+    outs = []
+    for earth_arg in (str(EARTH_JPG), str(ROOT / "assets" / "earth_stb.ppm")):
+        out = tmp_path / f"f{len(outs)}.ppm"
+        r = subprocess.run([str(app), "--scene", "earth_emitter", "--width", "300", "--height", "150", "--spp", "1", "--out", str(out),
+                            "--earth", earth_arg], capture_output=True, text=True, cwd=str(ROOT))
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1]
