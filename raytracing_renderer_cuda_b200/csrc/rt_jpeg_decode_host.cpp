@@ -1,8 +1,9 @@
 // rt_jpeg_decode_host.cpp — marker parsing and Huffman decoding of a JPEG file on the host (see the header).
 // Follows the decoder the reference uses, stb_image v2.26 (vendored at src/libs/stb/stb_image.h; cited as "stb:"), so that
 // the coefficients — and with the device stages of rt_jpeg_decode.cu the pixels — are the ones stbi_loadf produces
-// (main.cu:376-380).  stb's 9-bit look-up tables (stb:1920-1940,1986-2010) are an acceleration with identical results and
-// are not reproduced: every code is found by the canonical maxcode search (stb:2060-2084).
+// (main.cu:376-380).  Codes of up to 9 bits are found through a look-up table like stb's (stb:1986-2000), longer ones by
+// the canonical maxcode search (stb:2060-2084); stb's combined run/value table for small AC coefficients (stb:2002-2028) is
+// an acceleration with identical results and is not reproduced.
 #include "rt_jpeg_decode_host.hpp"
 
 #include <cstring>
@@ -21,6 +22,8 @@ struct Huffman { // stb:1875-1886, 1942-1984
     uint8_t size[257];
     uint32_t maxcode[18];
     int delta[17];
+    uint16_t code[256];
+    uint8_t fast[512]; // top 9 bits of the stream -> index into values[], 255 = longer code
     bool build(const int* count) {
         int k = 0;
         for (int i = 0; i < 16; ++i)
@@ -35,16 +38,21 @@ struct Huffman { // stb:1875-1886, 1942-1984
         for (j = 1; j <= 16; ++j) {
             delta[j] = k - int(code);
             if (size[k] == j) {
-                while (size[k] == j) {
-                    ++k;
-                    ++code;
-                }
+                while (size[k] == j) this->code[k++] = uint16_t(code++);
                 if (code - 1 >= (1u << j)) return false;
             }
             maxcode[j] = code << (16 - j);
             code <<= 1;
         }
         maxcode[j] = 0xffffffffu;
+        memset(fast, 255, sizeof fast);
+        for (int i = 0; i < k; ++i) {
+            const int sz = size[i];
+            if (sz <= 9) {
+                const int c = this->code[i] << (9 - sz), m = 1 << (9 - sz);
+                for (int q = 0; q < m; ++q) fast[c + q] = uint8_t(i);
+            }
+        }
         return true;
     }
 };
@@ -114,9 +122,17 @@ struct Decoder {
     }
     int huff_decode(const Huffman& h) { // stb:2033-2085
         if (code_bits < 16) grow();
+        const int f = h.fast[code_buffer >> 23];
+        if (f < 255) {
+            const int sz = h.size[f];
+            if (sz > code_bits) return -1;
+            code_buffer <<= sz;
+            code_bits -= sz;
+            return h.values[f];
+        }
         const uint32_t temp = code_buffer >> 16;
         int k;
-        for (k = 1;; ++k)
+        for (k = 10;; ++k)
             if (temp < h.maxcode[k]) break;
         if (k == 17) {
             code_bits -= 16;
