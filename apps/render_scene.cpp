@@ -89,7 +89,7 @@ int main(int argc, char** argv) {
     rt_scene_desc* json_desc = nullptr;
     if (ends_with(scene_name, ".json")) {
         rt_render_params from_doc = p;
-        CHECK(rt_scene_desc_from_json_file(scene_name.c_str(), &from_doc, &json_desc));
+        CHECK(rt_scene_desc_from_json_file(ctx, scene_name.c_str(), &from_doc, &json_desc));
         if (!size_given) p = from_doc; // command-line sizes win over the document's "render" block
     } else if (scene_name == "earth_emitter") {
         int32_t ew = 0, eh = 0;

@@ -364,10 +364,11 @@ void rt_scene_desc_free(rt_scene_desc* desc);
 /* Runtime scene front-end (replaces the compile-time scene of populate_scene_balls, main.cu:188-356,
  * and the WIDTH/HEIGHT/SAMPLES_PER_PIXEL/SEED macros, common.h:13-20, main.cu:15): a JSON document (format:
  * include/rt/scene_json.hpp) -> the same façade objects a C++ caller creates -> flattened description.
- * `base_dir` resolves relative image files (binary PPM); `render` (may be NULL) is updated from the "render"
- * block.  Errors: RT_ERR_INVALID_ARG with the parser's message in rt_last_error().  Release with rt_scene_desc_free. */
-rt_status rt_scene_desc_from_json(const char* json_text, const char* base_dir, rt_render_params* render, rt_scene_desc** out);
-rt_status rt_scene_desc_from_json_file(const char* path, rt_render_params* render, rt_scene_desc** out);
+ * `base_dir` resolves relative image files (P5/P6, or JPEG through rt_image_load when `ctx` is not NULL: the pixel
+ * stages of the JPEG reader run on the device); `render` (may be NULL) is updated from the "render" block.  Errors: RT_ERR_INVALID_ARG with the parser's message in rt_last_error().  Release with rt_scene_desc_free. */
+rt_status rt_scene_desc_from_json(rt_context* ctx, const char* json_text, const char* base_dir, rt_render_params* render,
+                                  rt_scene_desc** out);
+rt_status rt_scene_desc_from_json_file(rt_context* ctx, const char* path, rt_render_params* render, rt_scene_desc** out);
 /* flat binary scene file shared with the reference harness (oracle/ref_harness.cu) */
 rt_status rt_scene_desc_save(const rt_scene_desc* desc, const char* path);
 rt_status rt_scene_desc_load(const char* path, rt_scene_desc** out);

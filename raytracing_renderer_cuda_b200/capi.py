@@ -163,9 +163,9 @@ _SIGNATURES = {
     "rt_builtin_scene": (C.c_int, [C.c_char_p, _VP, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32,
                                    C.POINTER(C.POINTER(rt_scene_desc))]),
     "rt_scene_desc_free": (None, [C.POINTER(rt_scene_desc)]),
-    "rt_scene_desc_from_json": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(rt_render_params),
+    "rt_scene_desc_from_json": (C.c_int, [_VP, C.c_char_p, C.c_char_p, C.POINTER(rt_render_params),
                                           C.POINTER(C.POINTER(rt_scene_desc))]),
-    "rt_scene_desc_from_json_file": (C.c_int, [C.c_char_p, C.POINTER(rt_render_params), C.POINTER(C.POINTER(rt_scene_desc))]),
+    "rt_scene_desc_from_json_file": (C.c_int, [_VP, C.c_char_p, C.POINTER(rt_render_params), C.POINTER(C.POINTER(rt_scene_desc))]),
     "rt_scene_desc_save": (C.c_int, [C.POINTER(rt_scene_desc), C.c_char_p]),
     "rt_scene_desc_load": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(rt_scene_desc))]),
 }
@@ -239,19 +239,19 @@ class SceneDesc:
         return cls(out, lib)
 
     @classmethod
-    def from_json(cls, text: str, base_dir: str = "", params: "rt_render_params | None" = None) -> "SceneDesc":
-        """rt_scene_desc_from_json: the runtime scene front-end (format: include/rt/scene_json.hpp)."""
+    def from_json(cls, text: str, base_dir: str = "", params: "rt_render_params | None" = None, ctx: "Context | None" = None) -> "SceneDesc":
+        """rt_scene_desc_from_json: the runtime scene front-end (format: include/rt/scene_json.hpp).  JPEG image files need `ctx`."""
         lib = load_library()
         out = C.POINTER(rt_scene_desc)()
-        _check(lib, lib.rt_scene_desc_from_json(text.encode(), str(base_dir).encode(), C.byref(params) if params is not None else None,
+        _check(lib, lib.rt_scene_desc_from_json(ctx._h if ctx is not None else None, text.encode(), str(base_dir).encode(), C.byref(params) if params is not None else None,
                                                 C.byref(out)))
         return cls(out, lib)
 
     @classmethod
-    def from_json_file(cls, path: str, params: "rt_render_params | None" = None) -> "SceneDesc":
+    def from_json_file(cls, path: str, params: "rt_render_params | None" = None, ctx: "Context | None" = None) -> "SceneDesc":
         lib = load_library()
         out = C.POINTER(rt_scene_desc)()
-        _check(lib, lib.rt_scene_desc_from_json_file(str(path).encode(), C.byref(params) if params is not None else None, C.byref(out)))
+        _check(lib, lib.rt_scene_desc_from_json_file(ctx._h if ctx is not None else None, str(path).encode(), C.byref(params) if params is not None else None, C.byref(out)))
         return cls(out, lib)
 
     def save(self, path: str) -> None:

@@ -178,17 +178,18 @@ rt_status rt_builtin_scene(const char* name, const float* image_rgb, int32_t ima
 }
 
 // Runtime scene front-end: JSON text -> façade objects -> flattened description.
-rt_status rt_scene_desc_from_json(const char* json_text, const char* base_dir, rt_render_params* render, rt_scene_desc** out) {
+rt_status rt_scene_desc_from_json(rt_context* ctx, const char* json_text, const char* base_dir, rt_render_params* render,
+                                  rt_scene_desc** out) {
     if (!json_text || !out) return RT_ERR_INVALID_ARG;
     *out = nullptr;
     OwnedDesc* od = nullptr;
     try {
         rt::arena A;
         rt::scenes::json_scene js;
-        auto load = [](const std::string& path, std::vector<float>& rgb, int& w, int& h) {
+        auto load = [ctx](const std::string& path, std::vector<float>& rgb, int& w, int& h) {
             float* p = nullptr;
             int32_t ww = 0, hh = 0;
-            if (rt_read_ppm_f32(path.c_str(), &p, &ww, &hh) != RT_OK) return false;
+            if (rt_image_load(ctx, path.c_str(), &p, &ww, &hh) != RT_OK) return false; // PPM/PGM, or JPEG when ctx != NULL
             rgb.assign(p, p + size_t(ww) * size_t(hh) * 3);
             free(p);
             w = ww;
@@ -213,7 +214,7 @@ rt_status rt_scene_desc_from_json(const char* json_text, const char* base_dir, r
     }
 }
 
-rt_status rt_scene_desc_from_json_file(const char* path, rt_render_params* render, rt_scene_desc** out) {
+rt_status rt_scene_desc_from_json_file(rt_context* ctx, const char* path, rt_render_params* render, rt_scene_desc** out) {
     if (!path || !out) return RT_ERR_INVALID_ARG;
     *out = nullptr;
     FILE* f = fopen(path, "rb");
@@ -229,7 +230,7 @@ rt_status rt_scene_desc_from_json_file(const char* path, rt_render_params* rende
     std::string dir(path);
     const size_t slash = dir.find_last_of('/');
     dir = slash == std::string::npos ? std::string() : dir.substr(0, slash);
-    return rt_scene_desc_from_json(text.c_str(), dir.c_str(), render, out);
+    return rt_scene_desc_from_json(ctx, text.c_str(), dir.c_str(), render, out);
 }
 
 void rt_scene_desc_free(rt_scene_desc* desc) {

@@ -87,3 +87,22 @@ def test_cpp_app_reads_the_jpeg_texture_like_the_reference_main(tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
         outs.append(out.read_bytes())
     assert outs[0] == outs[1]
+
+
+@pytest.mark.skipif(not EARTH_JPG.exists(), reason="needs the reference's earth.jpg (oracle/_ref travels to the GPU box)")
+def test_json_scene_with_a_jpeg_texture(ctx, earth, tmp_path):
+    """A scene document may name a JPEG file once the front-end has a context: C1 with textures/earth.jpg flattens to
+    the same description as the hard-coded scene with the stb-decoded asset."""
+    import ctypes as C
+    import json
+
+    doc = json.loads((ROOT / "assets" / "scenes" / "earth_emitter.json").read_text())
+    doc["textures"]["earth"]["file"] = str(EARTH_JPG)
+    d = rt.SceneDesc.from_json(json.dumps(doc), ctx=ctx)
+    b = rt.SceneDesc.builtin("earth_emitter", earth)
+    ia, ib = d.desc.images[0], b.desc.images[0]
+    assert (ia.width, ia.height) == (ib.width, ib.height) == (1200, 600)
+    n = 1200 * 600 * 3
+    assert np.array_equal(np.ctypeslib.as_array(ia.rgb, (n,)), np.ctypeslib.as_array(ib.rgb, (n,)))
+    with pytest.raises(capi.RtError):
+        rt.SceneDesc.from_json(json.dumps(doc))  # without a context a JPEG cannot be read
