@@ -22,9 +22,9 @@
 //                   count / scan / scatter of 32-byte chunks, the 1-padding of the last byte (stb:1567) and the EOI marker
 // All float arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) in stb's operation order, which
 // is what a host compiler emits for the reference; the quantiser truncates like its (int) cast.
-// Bound: HBM by design (3 B/pixel read, 6 B/pixel of int16 coefficients written and read once, ~1-2 B/pixel of stream);
-// measured 1.13 ms for an 8K frame = 88 GB/s of pixels — the bit-scatter pass (k_jpeg_entropy<true>, 58 % of the time) is
-// instruction-bound, not bandwidth-bound.
+// Bound (ncu, profiles/r01_jpeg_ncu.md): instruction issue — k_jpeg_dct444 issues at 80 % of peak, k_jpeg_entropy<true> at
+// 67 % with 23 of 32 lanes active — not HBM (3 B/pixel read, 6 B/pixel of int16 coefficients written and read once,
+// ~1-2 B/pixel of stream: 6-11 % of the DRAM bandwidth).  Measured 1.13 ms for an 8K frame, 0.09 ms for 1200x600.
 #include <cub/device/device_scan.cuh>
 
 #include <cstring>
