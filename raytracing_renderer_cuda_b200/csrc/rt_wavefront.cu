@@ -360,9 +360,8 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
         const bool valid = idx < n_q[kind];
         const int kind_now = kind;
 
-        // Software pipeline over chunks: the slot index of this CTA's NEXT chunk is requested now and its
-        // 64-byte record is prefetched into L2 at the bottom of this iteration, so the next iteration starts
-        // with its dependent load chain (queue -> record -> sphere) already in flight.
+        // Software pipeline over chunks: the slot index of this CTA's NEXT chunk is requested now, so the next
+        // iteration starts with the first link of its dependent load chain (queue -> record -> sphere) done.
         uint32_t slot_next = 0u;
         bool valid_next = false;
         if (chunk + gridDim.x < total_chunks) {
@@ -385,7 +384,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
                 local = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
             }
         }
-#ifndef WF_NO_PREFETCH
+#ifdef WF_PREFETCH // measured with 16 Mi slots: the records come from DRAM either way and the hint costs 1.2 % (ab_misc.log)
         if (valid_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(wb.rec + slot_next));
 #endif
         __syncthreads();
