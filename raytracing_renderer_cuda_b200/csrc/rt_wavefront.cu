@@ -290,8 +290,9 @@ RT_DEV bool wf_frame_done(const uint32_t (&n_q)[NQ], unsigned long long path_bas
     return path_base >= npaths && live == 0u;
 }
 
-// Work granularity, variant 1: a CTA takes 256 consecutive entries of ONE queue and aggregates its pushes in shared
-// memory: one global atomic per CTA chunk and target queue, two block-wide barriers per chunk.  Best when all
+// Work granularity, variant 1: a CTA takes 256 consecutive entries of ONE queue (chunks are drawn from a ticket counter)
+// and aggregates its pushes in shared memory: one global atomic per CTA chunk and target queue, two block-wide barriers
+// per chunk.  Best when all
 // rays of a chunk cost the same (brute-force scenes): C1 runs 11 % faster this way than with warp chunks, whose
 // four-fold atomic traffic (~1 atomic per 3.5 ns and queue counter) saturates the L2 atomic units.
 template <bool USE_BVH>
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     const uint32_t* cnt_cur = wb.counts + (it % 3) * NQ;
     uint32_t* cnt_next = wb.counts + ((it + 1) % 3) * NQ;
     if (blockIdx.x == 0 && threadIdx.x < NQ) wb.counts[((it + 2) % 3) * NQ + threadIdx.x] = 0; // next iteration's target
+    if (blockIdx.x == 0 && threadIdx.x == 0) wb.tickets[(it + 2) % 3] = 0u;                     // and its ticket counter
     const unsigned long long path_base = wb.next_path[it & 1]; // paths started by earlier iterations
     const int par_cur = it & 1, par_next = par_cur ^ 1;
 
@@ -354,21 +356,17 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     uint32_t first;
     locate(blockIdx.x, kind, first);
     uint32_t slot = (first + threadIdx.x < n_q[kind]) ? __ldg(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
-
-    for (uint32_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    // Chunks are drawn from a ticket counter (the first gridDim.x are implicit: chunk = blockIdx.x), so a CTA that got
+    // cheap chunks simply takes more of them: against handing chunks out by stride, C1 9.46 -> 9.05 ms per frame.
+    // Thread 0 draws the ticket of the NEXT chunk at the top of a trip; the two barriers of the trip publish it.
+    __shared__ uint32_t s_next_chunk[2];
+    uint32_t* ticket = wb.tickets + (it % 3);
+    uint32_t next_chunk = 0u;
+    for (uint32_t chunk = blockIdx.x; chunk < total_chunks; chunk = next_chunk) {
+        if (threadIdx.x == 0) s_next_chunk[cpar] = gridDim.x + atomicAdd(ticket, 1u);
         const uint32_t idx = first + threadIdx.x;
         const bool valid = idx < n_q[kind];
         const int kind_now = kind;
-
-        // Software pipeline over chunks: the slot index of this CTA's NEXT chunk is requested now, so the next
-        // iteration starts with the first link of its dependent load chain (queue -> record -> sphere) done.
-        uint32_t slot_next = 0u;
-        bool valid_next = false;
-        if (chunk + gridDim.x < total_chunks) {
-            locate(chunk + gridDim.x, kind, first);
-            valid_next = first + threadIdx.x < n_q[kind];
-            if (valid_next) slot_next = __ldg(wf_queue(wb, par_cur, kind) + first + threadIdx.x);
-        }
 
         const int out_q = wf_process_entry<USE_BVH>(sc, rp, wb, pt, kind_now, valid, slot, path_base + idx, npix, npaths, accum, nrays);
 
@@ -384,9 +382,6 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
                 local = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
             }
         }
-#ifdef WF_PREFETCH // measured with 16 Mi slots: the records come from DRAM either way and the hint costs 1.2 % (ab_misc.log)
-        if (valid_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(wb.rec + slot_next));
-#endif
         __syncthreads();
         if (threadIdx.x < NQ) {
             uint32_t c = s_count[cpar][threadIdx.x];
@@ -396,7 +391,13 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
         __syncthreads();
         if (out_q != Q_NONE) wf_queue(wb, par_next, out_q)[s_base[cpar][out_q] + local] = slot;
         cpar ^= 1u;
-        slot = slot_next;
+        // (requesting the next chunk's slot indices a chunk ahead, and prefetching their records, was measured: 2.6 % and
+        // 1.2 % slower with 16 Mi slots — gpurun_out/ab_pipe.log, ab_misc.log)
+        next_chunk = s_next_chunk[cpar ^ 1u]; // (cpar was flipped above) written before the two barriers of this trip
+        if (next_chunk < total_chunks) {
+            locate(next_chunk, kind, first);
+            slot = first + threadIdx.x < n_q[kind] ? __ldg(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
+        }
     }
 
     for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
@@ -412,6 +413,9 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 #define WF_ROUNDS 1
 #endif
 #define WF_WCHUNK (32 * WF_ROUNDS)
+#ifndef WF_CTA_WAVES
+#define WF_CTA_WAVES 1u // CTA-chunk kernel: grid = this many waves of resident CTAs; chunks are ticketed, so one wave is enough
+#endif
 #ifndef RT_WF_BATCH
 #define RT_WF_BATCH 8u // launches enqueued between two looks at the polled queue sizes
 #endif
@@ -799,7 +803,7 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         const unsigned need = (slots + WF_WCHUNK * (WF_THREADS / 32) - 1) / (WF_WCHUNK * (WF_THREADS / 32)) + NQ;
         grid = need < cap ? need : cap;
     } else { // two waves of CTAs, chunks by stride
-        const unsigned cap = unsigned(sm_count) * 8u;
+        const unsigned cap = unsigned(sm_count) * WF_CTA_WAVES * WF_MINBLOCKS;
         const unsigned need = (slots + WF_THREADS - 1) / WF_THREADS + NQ;
         grid = need < cap ? need : cap;
     }
