@@ -5,12 +5,15 @@
 //
 //   render_scene [scene] [width height spp] [out] [earth.ppm]            (positional, as before)
 //   render_scene --scene <name | file.json> [--width W --height H --spp N --depth D --seed S]
-//                [--out render.jpg|.ppm] [--quality 100] [--earth assets/earth_stb.ppm] [--passes K]
+//                [--out render.jpg|.ppm] [--quality 100] [--earth assets/earth_stb.ppm] [--passes K] [--emitter-sampling]
 //     scene: earth_emitter (default) | book1_final | perlin_motion | random_spheres:N | a JSON document
 //            (include/rt/scene_json.hpp; the reference's compile-time scene and WIDTH/HEIGHT/SAMPLES_PER_PIXEL/SEED
 //            macros, main.cu:15,188-356, common.h:13-20, become runtime input)
 //     out:   *.jpg -> the device output stage (rt_render_jpeg: the same bytes stbi_write_jpg(…, 100) writes,
 //            main.cu:491); anything else -> binary PPM of the same pixels
+//     --emitter-sampling: RT_RENDER_EMITTER_SAMPLING — lambertian hits aim half of their scatter directions at the
+//            emitter spheres and weight the path accordingly (the reference README's "Improve Sampling on emitter
+//            objects", README.md:27-28); same expected image, less noise where emitters light the scene
 //     --passes K: progressive accumulation, K passes of --spp samples each into one accumulator; the output file is
 //            rewritten after every pass (PPM only)
 //
@@ -42,6 +45,7 @@ int main(int argc, char** argv) {
     std::string scene_name = "earth_emitter", out_path = "render.jpg", earth_path = "assets/earth_stb.ppm";
     int quality = 100; // main.cu:491
     int passes = 1;
+    bool emitter_sampling = false;
     rt_render_params p;
     rt_default_render_params(&p); // 1200x600x100, depth 50, seed 1000, tmin 1e-5 (common.h:13-20, main.cu:15,45)
     bool size_given = false;
@@ -65,9 +69,10 @@ int main(int argc, char** argv) {
         else if (a == "--quality") quality = atoi(next("--quality"));
         else if (a == "--earth") earth_path = next("--earth");
         else if (a == "--passes") passes = atoi(next("--passes"));
+        else if (a == "--emitter-sampling") emitter_sampling = true;
         else if (a == "--help" || a == "-h") {
             printf("render_scene --scene <name|file.json> [--width W --height H --spp N --depth D --seed S] [--out f.jpg|f.ppm] "
-                   "[--quality Q] [--earth earth.ppm]\n");
+                   "[--quality Q] [--earth earth.ppm] [--passes K] [--emitter-sampling]\n");
             return 0;
         } else pos.push_back(a);
     }
@@ -91,6 +96,7 @@ int main(int argc, char** argv) {
         rt_render_params from_doc = p;
         CHECK(rt_scene_desc_from_json_file(ctx, scene_name.c_str(), &from_doc, &json_desc));
         if (!size_given) p = from_doc; // command-line sizes win over the document's "render" block
+        p.flags = from_doc.flags;
     } else if (scene_name == "earth_emitter") {
         int32_t ew = 0, eh = 0;
         // stbi_loadf (main.cu:376-380): a .jpg goes through the JPEG reader (host Huffman + device pixel stages, the same
@@ -117,6 +123,7 @@ int main(int argc, char** argv) {
         desc = fs.desc();
     }
 
+    if (emitter_sampling) p.flags |= RT_RENDER_EMITTER_SAMPLING;
     rt_scene* scene = nullptr;
     CHECK(rt_scene_create(ctx, &desc, &scene));
     rt_scene_info info;

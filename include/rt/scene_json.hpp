@@ -16,7 +16,7 @@
 //                    | {"type":"moving_sphere","center0":[..],"center1":[..],"time0":0,"time1":1,"radius":0.2,"material":..} ],
 //     "bvh": "auto" | "none" | "sah" | "lbvh",          (none = hitable_list without a bvh_node, hitable_list.h:66-78)
 //     "render": { "width":1200, "height":600, "spp":100, "max_depth":50, "seed":1000, "tmin":1e-5,
-//                 "world":[1,0.8,0.7], "bloom":0.1 } }
+//                 "world":[1,0.8,0.7], "bloom":0.1, "emitter_sampling":0 } }
 // Textures and materials are created in document order; objects get ids in array order unless "id" is given.
 #pragma once
 
@@ -307,6 +307,10 @@ inline void scene_from_json(const std::string& doc_text, const std::string& base
             render->tmin = num(*r, "tmin", render->tmin);
             render->bloom = num(*r, "bloom", render->bloom);
             vec(*r, "world", vec3(render->world[0], render->world[1], render->world[2])).store(render->world);
+            // "emitter_sampling": 1 -> RT_RENDER_EMITTER_SAMPLING (the reference README's roadmap item, README.md:27-28)
+            if (num(*r, "emitter_sampling", (render->flags & RT_RENDER_EMITTER_SAMPLING) ? 1.0 : 0.0) != 0.0)
+                render->flags |= RT_RENDER_EMITTER_SAMPLING;
+            else render->flags &= ~RT_RENDER_EMITTER_SAMPLING;
         }
     }
 }

@@ -77,6 +77,16 @@ enum {
     RT_PIPE_MEGAKERNEL = 2 /* one thread runs a whole path (reference structure, main.cu:35-74) */
 };
 
+/* rt_render_params.flags.  Everything here changes the ESTIMATOR (not its expectation), so it is off by default
+ * and off in every parity run against the reference. */
+#define RT_RENDER_EMITTER_SAMPLING 1u /* importance-sample the emitters at lambertian hits (the reference README's roadmap
+                                        * item "Improve Sampling on emitter objects", README.md:27-28): the scatter
+                                        * direction is drawn from a 50/50 mixture of the reference's n + unit-ball
+                                        * distribution (material.h:112) and uniform cones towards the emitter spheres;
+                                        * the path value is weighted by p_reference / p_mixture (<= 2), so the image
+                                        * converges to the frame rendered without the flag */
+#define RT_MAX_LIGHTS 16u             /* emitter spheres that are importance-sampled (first ones in list order) */
+
 #define RT_SPHERE_MOVING 1u /* built by moving_sphere(...) (sphere.h:30-58) */
 #define RT_SPHERE_INSIDE 2u /* sphere(..., inside=true); stored, no effect (sphere.h:27,133-138) */
 
@@ -159,6 +169,7 @@ typedef struct rt_render_params {
     float world[3];        /* (1, .8, .7) */
     float bloom;           /* 0.1f */
     uint32_t pipeline;     /* RT_PIPE_* */
+    uint32_t flags;        /* RT_RENDER_*, 0 = the reference's estimator */
 } rt_render_params;
 
 typedef struct rt_stats {

@@ -78,6 +78,7 @@ struct orc_scene {
     std::vector<std::vector<float>> images;
     std::vector<int32_t> image_wh;
     Camera cam;
+    std::vector<uint32_t> lights; // emitter spheres in list order, at most RT_MAX_LIGHTS (RT_RENDER_EMITTER_SAMPLING)
 };
 
 namespace {
@@ -396,6 +397,83 @@ Ray camera_ray(const orc_scene& sc, Sampler& sm, int i, int j, int width, int he
     return r;
 }
 
+// ------------------------------------------------------------------ emitter importance sampling ----
+// Not in the reference (its README names it as future work, README.md:27-28): the restatement of the product's
+// RT_RENDER_EMITTER_SAMPLING estimator (csrc/rt_shade.cuh; include/rt_api.h).  In color() a path that reaches an emitter
+// is worth emit + bloom, whatever it did before (main.cu:49-55).  The reference's lambertian direction n + uniform-in-ball
+// (material.h:112) has the direction density p_ref = 2 cos^3(theta) / pi, so the value of a lambertian hit splits into
+//   Int p_ref [next hit is a listed emitter] (emit + bloom)  +  Int p_ref [anything else] (rest of color()).
+// The first integral is estimated by one shadow/emission ray aimed uniformly into the cone of an emitter sphere
+// chosen by solid angle (|d| from the reference's conditional law 2 cos(theta) cbrt(u)), worth (p_ref / p_sel)(emit + bloom)
+// when its closest hit is a listed emitter; the second by the reference's scattered ray, which counts 0 when its next
+// hit is a listed emitter.  Plain float arithmetic.
+struct LightCone {
+    V3 axis;
+    float one_minus_cos;
+};
+LightCone light_cone(const orc_scene& sc, uint32_t k, V3 p, float time) {
+    const rt_sphere& s = sc.spheres[sc.lights[k]];
+    V3 c = (s.flags & RT_SPHERE_MOVING) ? moving_center(s, time) : mk(s.center0[0], s.center0[1], s.center0[2]);
+    const float lx = c.x - p.x, ly = c.y - p.y, lz = c.z - p.z;
+    const float d2 = lx * lx + ly * ly + lz * lz, r2 = s.radius * s.radius;
+    LightCone lc;
+    if (!(d2 > r2)) {
+        lc.axis = mk(0.f, 0.f, 1.f);
+        lc.one_minus_cos = 2.f;
+    } else {
+        const float inv = 1.f / sqrtf(d2);
+        lc.axis = V3{lx * inv, ly * inv, lz * inv};
+        const float s2 = r2 / d2;
+        lc.one_minus_cos = fmaxf(s2 / (1.f + sqrtf(1.f - s2)), 1e-12f);
+    }
+    return lc;
+}
+bool is_listed_emitter(const orc_scene& sc, uint32_t prim) {
+    for (uint32_t k : sc.lights)
+        if (k == prim) return true; // the list holds emitter spheres only
+    return false;
+}
+// returns p_ref / p_sel and the shadow ray's direction; 0 = below the horizon (p_ref = 0), no ray.  The emitter is
+// chosen with probability proportional to its solid angle: p_sel = (cones holding w) / (total solid angle).
+float sample_light_direction(const orc_scene& sc, V3 p, V3 n, float time, U4 rl, V3& d) {
+    const uint32_t n_lights = uint32_t(sc.lights.size());
+    const float inv_n = 1.f / sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    float total = 0.f;
+    for (uint32_t j = 0; j < n_lights; ++j) total += light_cone(sc, j, p, time).one_minus_cos;
+    const float pick = u01(rl.x) * total;
+    LightCone lc = light_cone(sc, 0u, p, time);
+    uint32_t k = 0;
+    float below = 0.f;
+    for (uint32_t j = 0; j + 1u < n_lights && !(pick <= below + lc.one_minus_cos); ++j) {
+        below += lc.one_minus_cos;
+        k = j + 1u;
+        lc = light_cone(sc, k, p, time);
+    }
+    const float cz = 1.f - u01(rl.y) * lc.one_minus_cos;
+    const float sz = sqrtf(fmaxf(0.f, 1.f - cz * cz));
+    const float ang = 6.283185307179586f * u01(rl.z);
+    const float sn = sinf(ang), cs = cosf(ang);
+    const V3 ax = lc.axis;
+    const float sg = ax.z >= 0.f ? 1.f : -1.f;
+    const float ka = -1.f / (sg + ax.z), kb = ax.x * ax.y * ka;
+    const V3 t1 = V3{1.f + sg * ax.x * ax.x * ka, sg * kb, -sg * ax.x};
+    const V3 t2 = V3{kb, sg + ax.y * ax.y * ka, -ax.y};
+    const float e1 = sz * cs, e2 = sz * sn;
+    const V3 w = V3{e1 * t1.x + e2 * t2.x + cz * ax.x, e1 * t1.y + e2 * t2.y + cz * ax.y, e1 * t1.z + e2 * t2.z + cz * ax.z};
+    const float cos_t = (w.x * n.x + w.y * n.y + w.z * n.z) * inv_n;
+    if (!(cos_t > 0.f)) return 0.f;
+    const float len = 2.f * cos_t * fminf(cbrtf(u01(rl.w)), 0.99999994f);
+    d = V3{w.x * len, w.y * len, w.z * len};
+    const float p_ref = 0.6366197723675814f * cos_t * cos_t * cos_t;
+    float holding = 0.f;
+    for (uint32_t j = 0; j < n_lights; ++j) {
+        const LightCone lj = light_cone(sc, j, p, time);
+        const float off = 1.f - (w.x * lj.axis.x + w.y * lj.axis.y + w.z * lj.axis.z);
+        if (j == k || lj.one_minus_cos >= 2.f || off <= lj.one_minus_cos) holding += 1.f;
+    }
+    return p_ref * 6.283185307179586f * total / holding;
+}
+
 // ------------------------------------------------------------------ materials (material.h) ----
 // Returns false when the path ends at this hit (emitter, absorbed metal ray).
 bool scatter(const orc_scene& sc, const rt_material& m, const Ray& rin, const Hit& h, Sampler& sm, uint32_t bounce,
@@ -450,23 +528,50 @@ inline V3 emit(const orc_scene& sc, const rt_material& m, const Hit& h) {
 }
 
 // ------------------------------------------------------------------ color() (main.cu:35-74) ----
+// The shadow/emission ray of a lambertian hit (RT_RENDER_EMITTER_SAMPLING, product sampler only).
+V3 emitter_sample(const orc_scene& sc, const Hit& at, float time, Sampler& sm, uint32_t bounce, const rt_render_params& rp, int arith,
+                  unsigned long long* rays) {
+    V3 d;
+    const float w = sample_light_direction(sc, at.p, at.n, time, rng_block(sm, bounce, 2), d);
+    if (w == 0.f) return mk(0.f, 0.f, 0.f);
+    Hit h;
+    ++*rays;
+    if (!scene_hit(sc, Ray{at.p, d, time}, rp.tmin, FLT_MAX, arith, h)) return mk(0.f, 0.f, 0.f);
+    const rt_material& m = sc.materials[sc.spheres[h.prim].material];
+    if (m.kind != RT_MAT_EMITTER || !is_listed_emitter(sc, h.prim)) return mk(0.f, 0.f, 0.f);
+    if (!h.uv_set) sphere_uv(h.n, h.u, h.v);
+    const V3 e = emit(sc, m, h) + mk(rp.bloom, rp.bloom, rp.bloom);
+    return V3{e.x * w, e.y * w, e.z * w};
+}
+
 V3 color(const orc_scene& sc, Ray r, Sampler& sm, const rt_render_params& rp, int arith, unsigned long long* rays) {
     V3 A = mk(rp.world[0], rp.world[1], rp.world[2]);
     const V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
+    const bool nee = sm.mode == 1 && (rp.flags & RT_RENDER_EMITTER_SAMPLING) && !sc.lights.empty();
+    V3 direct = mk(0.f, 0.f, 0.f); // shadow/emission rays of the path; x + 0.f is exact without the flag
+    bool nee_vertex = false;       // `r` leaves a lambertian hit that traced its shadow ray
+    auto total = [&direct](V3 v) { return V3{v.x + direct.x, v.y + direct.y, v.z + direct.z}; };
     for (int bounce = 1; bounce <= rp.max_depth; ++bounce) {
         Hit h;
         ++*rays;
-        if (!scene_hit(sc, r, rp.tmin, FLT_MAX, arith, h)) return A;
+        if (!scene_hit(sc, r, rp.tmin, FLT_MAX, arith, h)) return total(A);
         if (sm.mode == 1 && !h.uv_set) sphere_uv(h.n, h.u, h.v); // the product derives u/v from n for every sphere kind
         const rt_material& m = sc.materials[sc.spheres[h.prim].material];
+        if (nee_vertex && m.kind == RT_MAT_EMITTER && is_listed_emitter(sc, h.prim)) return total(mk(0.f, 0.f, 0.f));
         Ray next;
         V3 att;
         V3 e = emit(sc, m, h) + bloom;
-        if (!scatter(sc, m, r, h, sm, uint32_t(bounce), att, next)) return e;
+        if (!scatter(sc, m, r, h, sm, uint32_t(bounce), att, next)) return total(e);
+        nee_vertex = false;
+        if (nee && m.kind == RT_MAT_LAMBERTIAN && bounce < rp.max_depth) { // the shadow ray stands for trace bounce + 1
+            const V3 c = emitter_sample(sc, h, r.time, sm, uint32_t(bounce), rp, arith, rays);
+            direct = V3{direct.x + c.x, direct.y + c.y, direct.z + c.z};
+            nee_vertex = true;
+        }
         A = e + att * A;
         r = next;
     }
-    return mk(0.f, 0.f, 0.f);
+    return total(mk(0.f, 0.f, 0.f));
 }
 
 void store3(float* out, V3 v) {
@@ -492,6 +597,8 @@ orc_scene* orc_scene_create(const rt_scene_desc* d) {
         s->image_wh.push_back(im.height);
     }
     s->cam = make_camera(d->camera);
+    for (uint32_t i = 0; i < d->n_spheres && s->lights.size() < RT_MAX_LIGHTS; ++i)
+        if (d->materials[d->spheres[i].material].kind == RT_MAT_EMITTER) s->lights.push_back(i);
     return s;
 }
 
@@ -626,6 +733,20 @@ int orc_refract(const float v[3], const float n[3], float mu, float out[3]) {
 }
 float orc_shlick(float cosine, float ri) { return shlick(cosine, ri); }
 void orc_sphere_uv(const float n[3], float* u, float* v) { sphere_uv(mk(n[0], n[1], n[2]), *u, *v); }
+// The shadow ray of a lambertian hit at (p, n, time) with the Philox key (pixel = index, sample 0, bounce 1): direction
+// and p_ref / p_sel (0: none).  Unit hook of the emitter-sampling tests.
+float orc_light_sample(const orc_scene* s, const float p[3], const float n[3], float time, uint32_t seed, uint32_t index,
+                       float dir[3]) {
+    Sampler sm;
+    sm.mode = 1;
+    sm.seed = seed;
+    sm.pixel = index;
+    sm.sample = 0;
+    V3 d = mk(0.f, 0.f, 0.f);
+    const float w = sample_light_direction(*s, mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), time, rng_block(sm, 1, 2), d);
+    store3(dir, d);
+    return w;
+}
 void orc_camera_ray(const orc_scene* s, float s_, float t_, unsigned long long seed, rt_ray* out) {
     // camera::get_ray (camera.h:33-38) with a caller-seeded sequential generator
     orng_state st;

@@ -25,6 +25,9 @@ int orc_refract(const float v[3], const float n[3], float mu, float out[3]);
 float orc_shlick(float cosine, float ri);
 void orc_sphere_uv(const float n[3], float* u, float* v);
 void orc_camera_ray(const orc_scene* s, float s_, float t_, unsigned long long seed, rt_ray* out);
+/* RT_RENDER_EMITTER_SAMPLING: the shadow ray of a lambertian hit, returns p_ref / p_sel (the scene must hold an emitter) */
+float orc_light_sample(const orc_scene* s, const float p[3], const float n[3], float time, uint32_t seed, uint32_t index,
+                       float dir[3]);
 /* jpeg_oracle.cpp: stbi_write_jpg(..., comp 3, quality) (main.cu:491) into memory; returns the file size
  * (out == NULL: size only), 0 if cap is too small */
 size_t orc_jpeg_encode(const uint8_t* rgb8, int width, int height, int quality, uint8_t* out, size_t cap);

@@ -30,6 +30,8 @@ RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_EMITTER = 0, 1, 2, 3
  RT_TEX_IMAGE) = range(7)
 RT_BVH_AUTO, RT_BVH_NONE, RT_BVH_HOST_SAH, RT_BVH_GPU_LBVH = 0, 1, 2, 3
 RT_PIPE_AUTO, RT_PIPE_WAVEFRONT, RT_PIPE_MEGAKERNEL = 0, 1, 2
+RT_RENDER_EMITTER_SAMPLING = 1  # rt_render_params.flags
+RT_MAX_LIGHTS = 16
 RT_SPHERE_MOVING, RT_SPHERE_INSIDE = 1, 2
 
 
@@ -84,7 +86,7 @@ class rt_scene_desc(C.Structure):
 class rt_render_params(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("sample_offset", C.c_int32),
                 ("max_depth", C.c_int32), ("seed", C.c_uint32), ("tmin", C.c_float), ("world", C.c_float * 3),
-                ("bloom", C.c_float), ("pipeline", C.c_uint32)]
+                ("bloom", C.c_float), ("pipeline", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class rt_stats(C.Structure):

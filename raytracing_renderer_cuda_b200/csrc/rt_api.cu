@@ -176,6 +176,7 @@ rt_status check_params(const rt_render_params* p) {
     ARG_CHECK(p->spp >= 0 && p->sample_offset >= 0, "spp/sample_offset must be >= 0");
     ARG_CHECK(p->max_depth >= 0 && p->max_depth < (1 << 23), "max_depth out of range");
     ARG_CHECK(p->pipeline <= RT_PIPE_MEGAKERNEL, "bad pipeline");
+    ARG_CHECK((p->flags & ~RT_RENDER_EMITTER_SAMPLING) == 0u, "unknown render flags");
     ARG_CHECK(uint64_t(p->width) * uint64_t(p->height) < (1ull << 32), "frame has more than 2^32 pixels");
     return RT_OK;
 }
@@ -193,6 +194,7 @@ rtd::DRenderParams to_device_params(const rt_render_params& p) {
     d.world_g = p.world[1];
     d.world_b = p.world[2];
     d.bloom = p.bloom;
+    d.flags = p.flags;
     return d;
 }
 
@@ -336,6 +338,7 @@ void rt_default_render_params(rt_render_params* p) {
     p->world[2] = .7f;
     p->bloom = 0.1f; // main.cu:49
     p->pipeline = RT_PIPE_AUTO;
+    p->flags = 0; // the reference's estimator
 }
 
 rt_status rt_context_create(int device, rt_context** out) {
@@ -670,6 +673,15 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     for (const auto& t : ht)
         if (t.kind == RT_TEX_NOISE_PERLIN || t.kind == RT_TEX_NOISE_TURBULANCE || t.kind == RT_TEX_NOISE_MARBLE || t.kind == RT_TEX_WOOD) s->d.has_noise = 1;
     make_camera(desc->camera, s->d.cam);
+    // emitter spheres for RT_RENDER_EMITTER_SAMPLING: device primitive indices in the caller's list order
+    s->d.n_lights = 0;
+    {
+        std::vector<uint32_t> where(n); // list ordinal -> device index
+        for (uint32_t k = 0; k < n; ++k) where[order[k]] = k;
+        for (uint32_t i = 0; i < n && s->d.n_lights < RT_MAX_LIGHTS; ++i)
+            if (desc->materials[desc->spheres[i].material].kind == RT_MAT_EMITTER) s->d.lights[s->d.n_lights++] = where[i];
+        for (uint32_t k = s->d.n_lights; k < RT_MAX_LIGHTS; ++k) s->d.lights[k] = 0;
+    }
 
     const auto t_end = std::chrono::steady_clock::now();
     s->info.n_spheres = n;
@@ -749,7 +761,9 @@ rt_status rt_shade_probe(rt_context* ctx, const rt_scene* scene, const rt_ray* r
     cudaError_t e = cudaMallocAsync(&d_out, n * sizeof(rt_shade_sample), ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
-        rtd::launch_shade_probe(scene->d, to_device_params(*p), d_rays, n, use_bvh != 0, d_out, ctx->stream);
+        rtd::DRenderParams rp = to_device_params(*p);
+        rp.flags = 0; // the probe reports the reference estimator's terms (rt_shade_sample carries no path weight)
+        rtd::launch_shade_probe(scene->d, rp, d_rays, n, use_bvh != 0, d_out, ctx->stream);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * sizeof(rt_shade_sample), cudaMemcpyDeviceToHost, ctx->stream);

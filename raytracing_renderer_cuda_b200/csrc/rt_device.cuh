@@ -108,6 +108,8 @@ struct DScene {
     uint32_t has_noise;   // any Perlin-based texture (noise / wood): the kernels stage the permutation table
     DImage images[RT_MAX_IMAGES];
     DCamera cam;
+    uint32_t n_lights;              // emitter spheres (RT_RENDER_EMITTER_SAMPLING), at most RT_MAX_LIGHTS
+    uint32_t lights[RT_MAX_LIGHTS]; // their primitive indices, in the caller's list order
 };
 
 struct DRenderParams {
@@ -118,6 +120,7 @@ struct DRenderParams {
     float tmin;
     float world_r, world_g, world_b;
     float bloom;
+    uint32_t flags; // RT_RENDER_*
 };
 
 struct Ray {

@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) k_shade_probe(const __grid_constant__ DSc
         Ray next;
         next.o = next.d = mk(0.f, 0.f, 0.f);
         next.time = 0.f;
-        bool cont = shade_terms(sc, rp, pt, q, h, uint32_t(i), 0u, 1u, E, att, next);
+        V3 direct = mk(0.f, 0.f, 0.f); // the probe evaluates the reference estimator: the host entry clears rp.flags
+        bool nee_vertex;
+        uint32_t shadow_rays = 0;
+        bool cont = shade_terms(sc, rp, pt, q, h, uint32_t(i), 0u, 1u, E, att, next, direct, nee_vertex, shadow_rays);
         o.id = __ldg(&sc.sph_c[h.prim]).z;
         o.continues = cont ? 1u : 0u;
         o.t = h.t;
@@ -118,6 +121,9 @@ __global__ void __launch_bounds__(256) k_render_mega(const __grid_constant__ DSc
         Ray r = camera_ray(sc, rp, pixel, sample);
         V3 A = mk(rp.world_r, rp.world_g, rp.world_b); // main.cu:40
         V3 result = mk(0.f, 0.f, 0.f);                 // exceeded recursion (main.cu:70)
+        V3 direct = mk(0.f, 0.f, 0.f);                 // shadow/emission rays of the path (RT_RENDER_EMITTER_SAMPLING)
+        bool nee_vertex = false;                       // the ray being traced left a lambertian hit that traced one
+        uint32_t shadow_rays = 0;
         for (int bounce = 1; bounce <= rp.max_depth; ++bounce) {
             RayQ q = make_rayq(r);
             Hit h = closest_hit(sc, q, rp.tmin, use_bvh != 0);
@@ -127,13 +133,18 @@ __global__ void __launch_bounds__(256) k_render_mega(const __grid_constant__ DSc
                 break;
             }
             Ray next;
-            if (!shade_hit(sc, rp, pt, q, h, pixel, sample, uint32_t(bounce), A, next)) {
+            if (nee_vertex && is_listed_emitter(sc, h.prim)) { // counted by the shadow ray of the previous hit
+                result = mk(0.f, 0.f, 0.f);
+                break;
+            }
+            if (!shade_hit(sc, rp, pt, q, h, pixel, sample, uint32_t(bounce), A, next, direct, nee_vertex, shadow_rays)) {
                 result = A;
                 break;
             }
             r = next;
         }
-        atomicAdd(&accum[pixel], make_float4(result.x, result.y, result.z, 1.f)); // RED.E.ADD.F32x4 (sm_90+)
+        nrays += shadow_rays;
+        atomicAdd(&accum[pixel], make_float4(result.x + direct.x, result.y + direct.y, result.z + direct.z, 1.f)); // RED.E.ADD.F32x4 (sm_90+)
     }
     // one counter update per warp
     for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);

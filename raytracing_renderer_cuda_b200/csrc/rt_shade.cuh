@@ -319,6 +319,114 @@ RT_DEV void scatter_lambertian(const RayQ& q, V3 p, V3 n, U4 r, Ray& out) {
     out.time = q.time;
 }
 
+// ---- emitter importance sampling (RT_RENDER_EMITTER_SAMPLING; the reference README's roadmap item, README.md:27-28) ----
+// In color() (main.cu:39-57) a path that reaches an emitter is worth emit + bloom, whatever it did before.  At a
+// lambertian hit the reference draws d = n + uniform-in-ball (material.h:112), whose direction density about the
+// normal is p_ref(w) = 2 cos^3(theta) / pi (the chord of the unit ball centred at n along w is 2 cos(theta); |d|
+// along it has a density proportional to t^2).  The value of the vertex splits into
+//     V = Int p_ref [next hit is a listed emitter] (emit + bloom)  +  Int p_ref [anything else] (rest of color())
+// With the flag on, the first integral is estimated by ONE extra "shadow/emission" ray per lambertian hit, aimed
+// uniformly into the cone of an emitter sphere chosen by solid angle (|d| from the reference's conditional law given w,
+// 2 cos(theta) cbrt(u): tmin is in units of |d|), worth (p_ref / p_sel) (emit + bloom) if its closest hit is an
+// emitter; the second by the reference's own scattered ray, which now counts 0 when its next hit is a listed
+// emitter.  Same expectation, weights p_ref / p_sel of the order of an emitter's solid angle — never above the
+// reference estimator's own range.  Ordinary colour-math FP32; nothing here is compared bit for bit.
+struct LightCone {
+    V3 axis;             // unit vector from p to the emitter's centre
+    float one_minus_cos; // w is inside the cone  <=>  1 - dot(w, axis) <= one_minus_cos   (2 = every direction)
+};
+RT_DEV LightCone light_cone(const DScene& sc, uint32_t k, V3 p, float time) {
+    const uint32_t prim = sc.lights[k];
+    const float4 a = __ldg(&sc.sph_a[prim]);
+    V3 c = mk(a.x, a.y, a.z);
+    if (prim >= sc.n_static) c = moving_center(a, __ldg(&sc.sph_b[prim]), __uint_as_float(__ldg(&sc.sph_c[prim]).x), time);
+    const float lx = c.x - p.x, ly = c.y - p.y, lz = c.z - p.z;
+    const float d2 = lx * lx + ly * ly + lz * lz, r2 = a.w * a.w;
+    LightCone lc;
+    if (!(d2 > r2)) { // on or inside the emitter: every direction reaches it
+        lc.axis = mk(0.f, 0.f, 1.f);
+        lc.one_minus_cos = 2.f;
+    } else {
+        const float inv = 1.f / sqrtf(d2);
+        lc.axis = V3{lx * inv, ly * inv, lz * inv};
+        const float s2 = r2 / d2; // sin^2 of the half angle
+        lc.one_minus_cos = fmaxf(s2 / (1.f + sqrtf(1.f - s2)), 1e-12f);
+    }
+    return lc;
+}
+// Is `prim` one of the emitter spheres the shadow rays sample?  (All of them unless the scene has more than RT_MAX_LIGHTS.)
+RT_DEV bool light_listed(const DScene& sc, uint32_t prim) {
+    bool listed = false;
+    for (uint32_t k = 0; k < sc.n_lights; ++k) listed = listed || sc.lights[k] == prim;
+    return listed;
+}
+// The shadow ray's direction `d` (with the reference's |d| law) at a lambertian hit (p, n); `rl` = Philox block (bounce, 2).
+// Emitter k is chosen with probability proportional to its solid angle, the direction uniformly inside its cone, so
+// p_sel(w) = (number of cones holding w) / (total solid angle) and p_ref / p_sel <= p_ref x total solid angle.
+// Returns p_ref / p_sel, or 0 when the direction leaves below the horizon (p_ref = 0 there: no ray is traced).
+RT_DEV float sample_light_direction(const DScene& sc, V3 p, V3 n, float time, U4 rl, V3& d) {
+    const float inv_n = 1.f / sqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    float total = 0.f; // sum of (1 - cos half-angle) = total solid angle / 2 pi
+    for (uint32_t j = 0; j < sc.n_lights; ++j) total += light_cone(sc, j, p, time).one_minus_cos;
+    const float pick = u01(rl.x) * total;
+    LightCone lc = light_cone(sc, 0u, p, time);
+    uint32_t k = 0;
+    float below = 0.f;
+    for (uint32_t j = 0; j + 1u < sc.n_lights && !(pick <= below + lc.one_minus_cos); ++j) { // walk the cumulative sum
+        below += lc.one_minus_cos;
+        k = j + 1u;
+        lc = light_cone(sc, k, p, time);
+    }
+    const float cz = 1.f - u01(rl.y) * lc.one_minus_cos; // cos of the angle to the axis, uniform over the cap
+    const float sz = sqrtf(fmaxf(0.f, 1.f - cz * cz));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u01(rl.z), &sn, &cs);
+    const V3 ax = lc.axis; // orthonormal basis around it (Duff et al. 2017)
+    const float sg = ax.z >= 0.f ? 1.f : -1.f;
+    const float ka = -1.f / (sg + ax.z), kb = ax.x * ax.y * ka;
+    const V3 t1 = V3{1.f + sg * ax.x * ax.x * ka, sg * kb, -sg * ax.x};
+    const V3 t2 = V3{kb, sg + ax.y * ax.y * ka, -ax.y};
+    const float e1 = sz * cs, e2 = sz * sn;
+    const V3 w = V3{e1 * t1.x + e2 * t2.x + cz * ax.x, e1 * t1.y + e2 * t2.y + cz * ax.y, e1 * t1.z + e2 * t2.z + cz * ax.z};
+    const float cos_t = (w.x * n.x + w.y * n.y + w.z * n.z) * inv_n;
+    if (!(cos_t > 0.f)) return 0.f;
+    const float len = 2.f * cos_t * fminf(cbrtf(u01(rl.w)), 0.99999994f);
+    d = V3{w.x * len, w.y * len, w.z * len};
+    const float p_ref = 0.6366197723675814f * cos_t * cos_t * cos_t; // 2 cos^3 / pi
+    float holding = 0.f; // cones that hold w (the chosen one does by construction)
+    for (uint32_t j = 0; j < sc.n_lights; ++j) {
+        const LightCone lj = light_cone(sc, j, p, time);
+        const float off = 1.f - (w.x * lj.axis.x + w.y * lj.axis.y + w.z * lj.axis.z);
+        if (j == k || lj.one_minus_cos >= 2.f || off <= lj.one_minus_cos) holding += 1.f;
+    }
+    return p_ref * 6.283185307179586f * total / holding;
+}
+// The shadow/emission ray of one lambertian hit: (p_ref / p_sel) (emit + bloom) if its closest hit is a listed emitter.
+RT_DEV V3 emitter_sample(const DScene& sc, const DRenderParams& rp, const PerlinTab& pt, V3 p, V3 n, float time, uint32_t pixel,
+                         uint32_t sample, uint32_t bounce, uint32_t& rays) {
+    V3 d;
+    const float w = sample_light_direction(sc, p, n, time, rng_block(rp.seed, pixel, sample, bounce, 2), d);
+    if (w == 0.f) return mk(0.f, 0.f, 0.f);
+    Ray r;
+    r.o = p;
+    r.d = d;
+    r.time = time;
+    const RayQ q = make_rayq(r);
+    const Hit h = closest_hit(sc, q, rp.tmin, true);
+    ++rays;
+    if (h.prim == RT_INVALID_ID) return mk(0.f, 0.f, 0.f);
+    const DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
+    if (m.kind != RT_MAT_EMITTER || !light_listed(sc, h.prim)) return mk(0.f, 0.f, 0.f);
+    V3 hp, hn;
+    hit_surface(sc, q, h, hp, hn);
+    const V3 e = texture_value(sc, pt, m.tex, hn, hp) * m.param + mk(rp.bloom, rp.bloom, rp.bloom); // emitter::emit + bloom
+    return V3{e.x * w, e.y * w, e.z * w};
+}
+RT_DEV bool is_listed_emitter(const DScene& sc, uint32_t prim) {
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(sc.mats + __ldg(&sc.sph_c[prim]).y));
+    return __float_as_uint(m0.x) == RT_MAT_EMITTER && light_listed(sc, prim);
+}
+
 // metal::scatter (material.h:118-131): draws the ball sample even at roughness 0, ray time
 // resets to 0 (ray.h:12 default), absorbed when dot(out, n) <= 0
 RT_DEV bool scatter_metal(const RayQ& q, V3 p, V3 n, float roughness, U4 r, Ray& out) {
@@ -360,13 +468,17 @@ RT_DEV void scatter_dielectric(const RayQ& q, V3 p, V3 n, float ri, U4 r, Ray& o
 // The terms of one integrator step at an accepted hit — the body of color()'s loop (main.cu:45-55):
 //   E = m.emit(h) + bloom;  `att`/`out` = what m.scatter(...) produces.  Returns false when scatter() does
 // (emitter, absorbed metal ray): the path's value is then E.  `bounce` counts from 1 for the RNG key.
+// RT_RENDER_EMITTER_SAMPLING: a lambertian hit also traces its shadow/emission ray — `direct` receives that ray's
+// contribution, `rays` counts it, and `nee_vertex` tells the caller that a listed emitter hit by `out` is worth 0.
 RT_DEV bool shade_terms(const DScene& sc, const DRenderParams& rp, const PerlinTab& pt, const RayQ& q, Hit h,
-                        uint32_t pixel, uint32_t sample, uint32_t bounce, V3& E, V3& att, Ray& out) {
+                        uint32_t pixel, uint32_t sample, uint32_t bounce, V3& E, V3& att, Ray& out, V3& direct, bool& nee_vertex,
+                        uint32_t& rays) {
     V3 p, n;
     hit_surface(sc, q, h, p, n);
     DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
     V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
     att = mk(0.f, 0.f, 0.f);
+    nee_vertex = false;
     if (m.kind == RT_MAT_EMITTER) { // emitter::emit / scatter (material.h:42-52)
         E = texture_value(sc, pt, m.tex, n, p) * m.param + bloom;
         return false;
@@ -376,6 +488,12 @@ RT_DEV bool shade_terms(const DScene& sc, const DRenderParams& rp, const PerlinT
     if (m.kind == RT_MAT_LAMBERTIAN) {
         scatter_lambertian(q, p, n, r, out);
         att = texture_value(sc, pt, m.tex, n, p);
+        // (the reference traces at most max_depth rays per path, main.cu:42: the shadow ray stands for trace bounce + 1)
+        if ((rp.flags & RT_RENDER_EMITTER_SAMPLING) && sc.n_lights > 0u && int(bounce) < rp.max_depth) {
+            const V3 c = emitter_sample(sc, rp, pt, p, n, q.time, pixel, sample, bounce, rays);
+            direct = V3{direct.x + c.x, direct.y + c.y, direct.z + c.z};
+            nee_vertex = true;
+        }
         return true;
     }
     att = mk(m.ax, m.ay, m.az);
@@ -386,9 +504,9 @@ RT_DEV bool shade_terms(const DScene& sc, const DRenderParams& rp, const PerlinT
 
 // A <- E + att*A (main.cu:51) or A <- E when the path ends.  Returns true if the path continues.
 RT_DEV bool shade_hit(const DScene& sc, const DRenderParams& rp, const PerlinTab& pt, const RayQ& q, Hit h,
-                      uint32_t pixel, uint32_t sample, uint32_t bounce, V3& A, Ray& out) {
+                      uint32_t pixel, uint32_t sample, uint32_t bounce, V3& A, Ray& out, V3& direct, bool& nee_vertex, uint32_t& rays) {
     V3 E, att;
-    if (!shade_terms(sc, rp, pt, q, h, pixel, sample, bounce, E, att, out)) {
+    if (!shade_terms(sc, rp, pt, q, h, pixel, sample, bounce, E, att, out, direct, nee_vertex, rays)) {
         A = E;
         return false;
     }

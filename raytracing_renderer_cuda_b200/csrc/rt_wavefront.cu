@@ -115,11 +115,15 @@ struct WfLane {
     uint32_t slot, pixel, sample, bounce;
     V3 A;
     Ray r;
+    bool nee_vertex;      // NEE instantiations: ln.r leaves a lambertian hit that traced its shadow/emission ray
+    uint32_t shadow_rays; // ... and how many such rays wf_begin traced (0 or 1)
 };
 
 // First half of one queue entry: shade the pending hit of `slot` (or generate the camera ray of path `path`) and
 // scatter.  Returns true when a new ray (ln.r) has to be extended.  Otherwise the entry is finished here —
 // emitter, absorbed ray, depth limit, or no path left — and `out_q` says where the slot goes (Q_NEW / Q_NONE).
+// NEE = RT_RENDER_EMITTER_SAMPLING (a separate instantiation: the reference estimator's kernels do not change).
+template <bool NEE>
 RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind, bool valid,
                      uint32_t slot, unsigned long long path, unsigned long long npix, unsigned long long npaths,
                      float4* __restrict__ accum, WfLane& ln, int& out_q) {
@@ -129,6 +133,8 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
     bool finished = false;  // path ended: add `A` to the pixel
     bool slot_free = false; // hand the slot to Q_NEW
     V3 A = mk(0.f, 0.f, 0.f);
+    bool nee_vertex = false;
+    uint32_t shadow_rays = 0;
     uint32_t pixel = 0, sample = 0, bounce = 0;
     Ray r;
     r.o = r.d = mk(0.f, 0.f, 0.f);
@@ -190,6 +196,11 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
                     else if (kind == Q_LAMB_NOISE6) att = t.kind == RT_TEX_NOISE_MARBLE ? tex_marble(pt, t, p) : tex_turbulence(pt, t, p);
                     else att = tex_image(sc, t, n);
                     scatter_lambertian(q, p, n, rn, r);
+                    if (NEE && int(bounce) < rp.max_depth) { // the hit's shadow/emission ray (rt_shade.cuh), traced right here
+                        const V3 c = emitter_sample(sc, rp, pt, p, n, q.time, pixel, sample, bounce, shadow_rays);
+                        if (c.x != 0.f || c.y != 0.f || c.z != 0.f) atomicAdd(&accum[pixel], make_float4(c.x, c.y, c.z, 0.f));
+                        nee_vertex = true;
+                    }
                 }
                 if (!scattered) { // absorbed (material.h:129-130): the path's value is E (main.cu:53-54)
                     A = E;
@@ -210,6 +221,8 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
     }
     if (finished) atomicAdd(&accum[pixel], make_float4(A.x, A.y, A.z, 1.f));
     out_q = slot_free ? int(Q_NEW) : Q_NONE;
+    ln.nee_vertex = nee_vertex;
+    ln.shadow_rays = shadow_rays;
     ln.slot = slot;
     ln.pixel = pixel;
     ln.sample = sample;
@@ -221,6 +234,7 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
 
 // Second half: the closest hit `h` of ln.r is known.  Miss / constant emitter: the path ends (accumulate, slot to
 // Q_NEW); otherwise the record is stored and the slot goes to the shading queue of the hit.  Returns that queue.
+template <bool NEE>
 RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, float4* __restrict__ accum, WfLane& ln,
                      const RayQ& q, Hit h) {
     WfRecord* rec = wb.rec + ln.slot;
@@ -234,7 +248,10 @@ RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers&
         int32_t leaf;
         V3 value;
         out_q = classify_hit(sc, rp, q, h, leaf, value);
-        if (out_q == Q_NONE) { // constant emitter: terminate here
+        if (NEE && ln.nee_vertex && (out_q == Q_NONE || out_q == Q_EMIT) && light_listed(sc, h.prim)) {
+            A = mk(0.f, 0.f, 0.f); // this emitter was counted by the shadow ray of the hit the ray comes from
+            finished = true;
+        } else if (out_q == Q_NONE) { // constant emitter: terminate here
             A = value;
             finished = true;
         } else {
@@ -253,13 +270,14 @@ RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers&
 
 // One whole queue entry (the CTA-chunk and warp-chunk kernels): begin, closest hit, finish.  Called by all 32 lanes of
 // the warp (the BVH traversal is warp-cooperative); `valid` = false for lanes past the end of the queue.
-template <bool USE_BVH>
+template <bool USE_BVH, bool NEE>
 RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind,
                             bool valid, uint32_t slot, unsigned long long path, unsigned long long npix,
                             unsigned long long npaths, float4* __restrict__ accum, unsigned long long& nrays) {
     WfLane ln;
     int out_q;
-    const bool has_ray = wf_begin(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q);
+    const bool has_ray = wf_begin<NEE>(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q);
+    if (NEE) nrays += ln.shadow_rays;
     if (USE_BVH) {
         const RayQ q = make_rayq(ln.r);
 #ifdef WF_NO_SPEC // A/B: the per-lane loop
@@ -270,13 +288,13 @@ RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfB
 #endif
         if (has_ray) {
             ++nrays;
-            out_q = wf_finish(sc, rp, wb, accum, ln, q, h);
+            out_q = wf_finish<NEE>(sc, rp, wb, accum, ln, q, h);
         }
     } else if (has_ray) {
         const RayQ q = make_rayq(ln.r);
         const Hit h = closest_hit_list(sc, q, rp.tmin);
         ++nrays;
-        out_q = wf_finish(sc, rp, wb, accum, ln, q, h);
+        out_q = wf_finish<NEE>(sc, rp, wb, accum, ln, q, h);
     }
     return out_q;
 }
@@ -295,7 +313,7 @@ RT_DEV bool wf_frame_done(const uint32_t (&n_q)[NQ], unsigned long long path_bas
 // per chunk.  Best when all
 // rays of a chunk cost the same (brute-force scenes): C1 runs 11 % faster this way than with warp chunks, whose
 // four-fold atomic traffic (~1 atomic per 3.5 ns and queue counter) saturates the L2 atomic units.
-template <bool USE_BVH>
+template <bool USE_BVH, bool NEE>
 __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     k_wf_step_cta(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
@@ -368,7 +386,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
         const bool valid = idx < n_q[kind];
         const int kind_now = kind;
 
-        const int out_q = wf_process_entry<USE_BVH>(sc, rp, wb, pt, kind_now, valid, slot, path_base + idx, npix, npaths, accum, nrays);
+        const int out_q = wf_process_entry<USE_BVH, NEE>(sc, rp, wb, pt, kind_now, valid, slot, path_base + idx, npix, npaths, accum, nrays);
 
         // ---- queue push: warp ballot -> shared counters -> one global atomic per queue ----
         uint32_t local = 0;
@@ -432,7 +450,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 #define RT_PT_REFILL_DEFAULT 16
 #endif
 
-template <bool USE_BVH>
+template <bool USE_BVH, bool NEE>
 __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     k_wf_step_warp(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
@@ -505,7 +523,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
             const uint32_t idx = first + uint32_t(e) * 32u + lane;
             const bool valid = idx < n_kind;
             const uint32_t slot = valid ? __ldg(q_in + idx) : 0u;
-            const int out_q = wf_process_entry<USE_BVH>(sc, rp, wb, pt, kind, valid, slot, path_base + idx, npix, npaths, accum, nrays);
+            const int out_q = wf_process_entry<USE_BVH, NEE>(sc, rp, wb, pt, kind, valid, slot, path_base + idx, npix, npaths, accum, nrays);
                 outq_pack |= uint32_t(out_q + 1) << (4 * e);
         }
 
@@ -554,6 +572,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 // 775-820 (11 of 32), this kernel 880-940.  On C2/C3 (a few hundred spheres, shading a third of the work) the
 // partial-width shading of refilled lanes costs more than the traversal gains (C2: 10.3 -> 7.1 Grays/s), so the
 // kernel is used from RT_PT_MIN_SPHERES primitives on.
+template <bool NEE>
 __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
     k_wf_step_pt(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
                  int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter, int refill, int leaf_lanes) {
@@ -642,7 +661,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             int out_q = Q_NONE;
             if (tracing && t.node == RT_TRAV_DONE) {
                 ++nrays;
-                out_q = wf_finish(sc, rp, wb, accum, ln, q, t.best);
+                out_q = wf_finish<NEE>(sc, rp, wb, accum, ln, q, t.best);
                 tracing = false;
             }
             push(out_q, ln.slot);
@@ -671,7 +690,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             if (!tracing && rank < navail) {
                 const uint32_t idx = pos + rank;
                 const uint32_t slot = __ldg(q_in + idx);
-                if (wf_begin(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
+                if (wf_begin<NEE>(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
                     q = make_rayq(ln.r);
                     trav_begin(sc, q, t);
 #ifndef RT_PT_BINARY
@@ -679,6 +698,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
 #endif
                     tracing = true;
                 }
+                if (NEE) nrays += ln.shadow_rays;
             }
             push(out_q, ln.slot);
             pos += min(uint32_t(__popc(idle)), navail);
@@ -767,13 +787,21 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     // scenes without Perlin textures leave the 32 KB table out: 128 KB more L1 per SM for BVH nodes
     const size_t smem = sc.has_noise ? smem_full : 0;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_wf_step_cta<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
-        cudaFuncSetAttribute(k_wf_step_cta<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
-        cudaFuncSetAttribute(k_wf_step_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
-        cudaFuncSetAttribute(k_wf_step_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
-        cudaFuncSetAttribute(k_wf_step_pt, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_full));
+        const int a = int(smem_full);
+        cudaFuncSetAttribute(k_wf_step_cta<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+        cudaFuncSetAttribute(k_wf_step_cta<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+        cudaFuncSetAttribute(k_wf_step_warp<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+        cudaFuncSetAttribute(k_wf_step_warp<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+        cudaFuncSetAttribute(k_wf_step_pt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+        cudaFuncSetAttribute(k_wf_step_cta<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+        cudaFuncSetAttribute(k_wf_step_cta<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+        cudaFuncSetAttribute(k_wf_step_warp<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+        cudaFuncSetAttribute(k_wf_step_warp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+        cudaFuncSetAttribute(k_wf_step_pt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
         attr_set = true;
     }
+    // emitter importance sampling: a scene without emitters renders with the reference estimator's kernels
+    const bool nee = (rp.flags & RT_RENDER_EMITTER_SAMPLING) != 0u && sc.n_lights > 0u;
     // slots in use: never more than there are paths
     WfBuffers wb = ws->b;
     const uint32_t slots = uint32_t(npaths < wb.pool ? npaths : wb.pool);
@@ -857,13 +885,24 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     auto enqueue = [&](uint32_t count) {
         for (uint32_t k = 0; k < count; ++k, ++it) {
             if (grain == G_PT) {
-                launch(k_wf_step_pt, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
+                if (nee) launch(k_wf_step_pt<true>, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
+                else launch(k_wf_step_pt<false>, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
             } else if (warp_grain) {
-                if (use_bvh) launch(k_wf_step_warp<true>, sc, rp, wb, int(it), accum, ray_counter);
-                else launch(k_wf_step_warp<false>, sc, rp, wb, int(it), accum, ray_counter);
+                if (nee) {
+                    if (use_bvh) launch(k_wf_step_warp<true, true>, sc, rp, wb, int(it), accum, ray_counter);
+                    else launch(k_wf_step_warp<false, true>, sc, rp, wb, int(it), accum, ray_counter);
+                } else {
+                    if (use_bvh) launch(k_wf_step_warp<true, false>, sc, rp, wb, int(it), accum, ray_counter);
+                    else launch(k_wf_step_warp<false, false>, sc, rp, wb, int(it), accum, ray_counter);
+                }
             } else {
-                if (use_bvh) launch(k_wf_step_cta<true>, sc, rp, wb, int(it), accum, ray_counter);
-                else launch(k_wf_step_cta<false>, sc, rp, wb, int(it), accum, ray_counter);
+                if (nee) {
+                    if (use_bvh) launch(k_wf_step_cta<true, true>, sc, rp, wb, int(it), accum, ray_counter);
+                    else launch(k_wf_step_cta<false, true>, sc, rp, wb, int(it), accum, ray_counter);
+                } else {
+                    if (use_bvh) launch(k_wf_step_cta<true, false>, sc, rp, wb, int(it), accum, ray_counter);
+                    else launch(k_wf_step_cta<false, false>, sc, rp, wb, int(it), accum, ray_counter);
+                }
             }
             ++*launches;
         }

@@ -50,6 +50,8 @@ class Oracle:
         L.orc_shlick.argtypes = [C.c_float, C.c_float]
         L.orc_sphere_uv.argtypes = [_F3, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_camera_ray.argtypes = [_VP, C.c_float, C.c_float, C.c_ulonglong, _VP]
+        L.orc_light_sample.restype = C.c_float
+        L.orc_light_sample.argtypes = [_VP, _F3, _F3, C.c_float, C.c_uint32, C.c_uint32, _F3]
 
     def scene(self, desc: capi.SceneDesc) -> "OracleScene":
         return OracleScene(self, desc)
@@ -113,6 +115,12 @@ class OracleScene:
         out = _F3()
         self.L.orc_texture_value(self._h, tex, u, v, _f3(p), out)
         return np.array(out[:], np.float32)
+
+    def light_sample(self, p, n, time: float, seed: int, index: int):
+        """RT_RENDER_EMITTER_SAMPLING: the shadow ray of a lambertian hit -> (direction, p_ref / p_sel)."""
+        d = _F3()
+        w = self.L.orc_light_sample(self._h, _f3(p), _f3(n), time, seed, index, d)
+        return np.array(d[:], np.float32), float(w)
 
     def camera_ray(self, s: float, t: float, seed: int) -> np.ndarray:
         r = np.zeros(1, capi.RAY_DTYPE)
