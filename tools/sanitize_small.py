@@ -19,8 +19,10 @@ for name, kw in (("earth_emitter", dict(image=load_earth())), ("book1_final", {}
         else:
             os.environ["RT_WF_GRAIN"] = grain
         img, st = sc.render(rt.default_params(width=97, height=41, spp=3))
+        img, st = sc.render(rt.default_params(width=61, height=33, spp=2, flags=capi.RT_RENDER_EMITTER_SAMPLING))
     os.environ.pop("RT_WF_GRAIN", None)
     img, st = sc.render(rt.default_params(width=64, height=32, spp=2, pipeline=capi.RT_PIPE_MEGAKERNEL))
+    img, st = sc.render(rt.default_params(width=64, height=32, spp=2, pipeline=capi.RT_PIPE_MEGAKERNEL, flags=capi.RT_RENDER_EMITTER_SAMPLING))
     f, st = sc.render_jpeg(rt.default_params(width=97, height=41, spp=2), 100)
     f2, st = sc.render_jpeg(rt.default_params(width=50, height=30, spp=1), 60)
     sc.render_progressive(rt.default_params(width=40, height=20, spp=1), 2)
