@@ -33,14 +33,42 @@ __device__ const uint8_t k_perlin_perm[256] = {
     242, 193, 238, 210, 144, 12,  191, 179, 162, 241, 81,  51,  145, 235, 249, 14,  239, 107, 49,  192, 214, 31,
     181, 199, 106, 157, 184, 84,  204, 176, 115, 121, 50,  45,  127, 4,   150, 254, 138, 236, 205, 93,  222, 114,
     67,  29,  24,  72,  243, 141, 128, 195, 78,  66,  215, 61,  156, 180};
+#ifdef RT_PERLIN_GLOBAL
+// A/B: the pair table (perm[i] | perm[i + 1] << 8) read straight from global memory through L1 (1 KB), no staging
+__device__ const uint32_t k_perlin_pairs[256] = {
+    0xa097, 0x89a0, 0x5b89, 0x5a5b, 0x0f5a, 0x830f, 0x0d83, 0xc90d, 0x5fc9, 0x605f, 0x3560, 0xc235, 0xe9c2, 0x07e9, 0xe107, 0x8ce1,
+    0x248c, 0x6724, 0x1e67, 0x451e, 0x8e45, 0x088e, 0x6308, 0x2563, 0xf025, 0x15f0, 0x0a15, 0x170a, 0xbe17, 0x06be, 0x9406, 0xf794,
+    0x78f7, 0xea78, 0x4bea, 0x004b, 0x1a00, 0xc51a, 0x3ec5, 0x5e3e, 0xfc5e, 0xdbfc, 0xcbdb, 0x75cb, 0x2375, 0x0b23, 0x200b, 0x3920,
+    0xb139, 0x21b1, 0x5821, 0xed58, 0x95ed, 0x3895, 0x5738, 0xae57, 0x14ae, 0x7d14, 0x887d, 0xab88, 0xa8ab, 0x44a8, 0xaf44, 0x4aaf,
+    0xa54a, 0x47a5, 0x8647, 0x8b86, 0x308b, 0x1b30, 0xa61b, 0x4da6, 0x924d, 0x9e92, 0xe79e, 0x53e7, 0x6f53, 0xe56f, 0x7ae5, 0x3c7a,
+    0xd33c, 0x85d3, 0xe685, 0xdce6, 0x69dc, 0x5c69, 0x295c, 0x3729, 0x2e37, 0xf52e, 0x28f5, 0xf428, 0x66f4, 0x8f66, 0x368f, 0x4136,
+    0x1941, 0x3f19, 0xa13f, 0x01a1, 0xd801, 0x50d8, 0x4950, 0xd149, 0x4cd1, 0x844c, 0xbb84, 0xd0bb, 0x59d0, 0x1259, 0xa912, 0xc8a9,
+    0xc4c8, 0x87c4, 0x8287, 0x7482, 0xbc74, 0x9fbc, 0x569f, 0xa456, 0x64a4, 0x6d64, 0xc66d, 0xadc6, 0xbaad, 0x03ba, 0x4003, 0x3440,
+    0xd934, 0xe2d9, 0xfae2, 0x7cfa, 0x7b7c, 0x057b, 0xca05, 0x26ca, 0x9326, 0x7693, 0x7e76, 0xff7e, 0x52ff, 0x5552, 0xd455, 0xcfd4,
+    0xcecf, 0x3bce, 0xe33b, 0x2fe3, 0x102f, 0x3a10, 0x113a, 0xb611, 0xbdb6, 0x1cbd, 0x2a1c, 0xdf2a, 0xb7df, 0xaab7, 0xd5aa, 0x77d5,
+    0xf877, 0x98f8, 0x0298, 0x2c02, 0x9a2c, 0xa39a, 0x46a3, 0xdd46, 0x99dd, 0x6599, 0x9b65, 0xa79b, 0x2ba7, 0xac2b, 0x09ac, 0x8109,
+    0x1681, 0x2716, 0xfd27, 0x13fd, 0x6213, 0x6c62, 0x6e6c, 0x4f6e, 0x714f, 0xe071, 0xe8e0, 0xb2e8, 0xb9b2, 0x70b9, 0x6870, 0xda68,
+    0xf6da, 0x61f6, 0xe461, 0xfbe4, 0x22fb, 0xf222, 0xc1f2, 0xeec1, 0xd2ee, 0x90d2, 0x0c90, 0xbf0c, 0xb3bf, 0xa2b3, 0xf1a2, 0x51f1,
+    0x3351, 0x9133, 0xeb91, 0xf9eb, 0x0ef9, 0xef0e, 0x6bef, 0x316b, 0xc031, 0xd6c0, 0x1fd6, 0xb51f, 0xc7b5, 0x6ac7, 0x9d6a, 0xb89d,
+    0x54b8, 0xcc54, 0xb0cc, 0x73b0, 0x7973, 0x3279, 0x2d32, 0x7f2d, 0x047f, 0x9604, 0xfe96, 0x8afe, 0xec8a, 0xcdec, 0x5dcd, 0xde5d,
+    0x72de, 0x4372, 0x1d43, 0x181d, 0x4818, 0xf348, 0x8df3, 0x808d, 0xc380, 0x4ec3, 0x424e, 0xd742, 0x3dd7, 0x9c3d, 0xb49c, 0x97b4};
+#endif
+
 
 // Shared-memory staging of the permutation.  Entry i holds the PAIR (perm[i], perm[i+1])
 // so the two neighbouring lookups every hash level needs (perlin_noise.h:67-72) cost one
-// load, and the table is replicated once per bank (word i*32 + lane) so the 32 lanes of a
-// warp never conflict however divergent their lattice cells are.  256 x 32 x 4 B = 32 KB.
+// load; the table is replicated 2^RT_PERLIN_BANK_BITS times (word i * replicas + lane mod replicas).
 // Optionally (RT_PERLIN_GTAB) a second table holds the 16 gradient directions of perlin_noise::grad as float4 coefficient vectors (one
 // LDS.128 per corner, replicated per lane: 16 x 32 x 16 B = 8 KB), see perlin_grad.
-#define RT_PERLIN_PERM_WORDS (256 * 32)
+#ifndef RT_PERLIN_BANK_BITS
+// Replicas per entry = 2^bits (lane l reads replica l mod 2^bits).  One replica per bank (5 bits, 32 KB per CTA) makes
+// every lookup conflict-free, but the table is staged by every CTA of every launch and its shared memory comes out of
+// the L1 that holds the kernels' stack frames: measured on C1 / C3 (gpurun_out/ab_banks.log, ab_banks2.log, 128-thread
+// CTAs): 5 bits 8.92 / 4.79 ms, 4: 8.75, 3: 8.69, 2: 8.65, 1: 8.58 / 4.69, 0: 8.68 / 4.70; straight from global memory
+// through L1 (RT_PERLIN_GLOBAL): 8.52 / 4.77.  Two replicas (2 KB) it is.
+#define RT_PERLIN_BANK_BITS 1
+#endif
+#define RT_PERLIN_PERM_WORDS (256 << RT_PERLIN_BANK_BITS)
 #ifdef RT_PERLIN_GTAB // opt-in: measured 1 % SLOWER on C1 than the compare/select form (gpurun_out/ab_perlin.log)
 #define RT_PERLIN_SMEM_WORDS (RT_PERLIN_PERM_WORDS + 16 * 32 * 4)
 #else
@@ -51,13 +79,24 @@ struct PerlinTab {
     uint32_t lane;
 };
 RT_DEV void perlin_stage(uint32_t* smem, uint32_t tid, uint32_t nthreads) {
+#ifdef RT_PERLIN_GLOBAL
+    (void)smem; (void)tid; (void)nthreads;
+    return;
+#endif
+#if RT_PERLIN_BANK_BITS >= 2
     // 4 consecutive replica words hold the same pair: one 16-byte store per 4 words
     uint4* s4 = reinterpret_cast<uint4*>(smem);
     for (uint32_t w = tid; w < RT_PERLIN_PERM_WORDS / 4; w += nthreads) {
-        uint32_t i = w >> 3;
+        uint32_t i = w >> (RT_PERLIN_BANK_BITS - 2);
         uint32_t v = uint32_t(k_perlin_perm[i]) | (uint32_t(k_perlin_perm[(i + 1) & 255]) << 8);
         s4[w] = make_uint4(v, v, v, v);
     }
+#else
+    for (uint32_t w = tid; w < RT_PERLIN_PERM_WORDS; w += nthreads) {
+        uint32_t i = w >> RT_PERLIN_BANK_BITS;
+        smem[w] = uint32_t(k_perlin_perm[i]) | (uint32_t(k_perlin_perm[(i + 1) & 255]) << 8);
+    }
+#endif
 #ifdef RT_PERLIN_GTAB
     // gradient h = hash & 15 (perlin_noise.h:173-181): u = h<8 ? x : y; v = h<4 ? y : (h==12||h==14 ? x : z);
     // grad = (h&1 ? -u : u) + (h&2 ? -v : v)  ==  cx*x + cy*y + cz*z with two coefficients +-1 and one 0
@@ -73,7 +112,12 @@ RT_DEV void perlin_stage(uint32_t* smem, uint32_t tid, uint32_t nthreads) {
     }
 #endif
 }
-RT_DEV uint32_t perlin_pair(const PerlinTab& pt, uint32_t i) { return pt.s[((i & 255u) << 5) | pt.lane]; }
+RT_DEV uint32_t perlin_pair(const PerlinTab& pt, uint32_t i) {
+#ifdef RT_PERLIN_GLOBAL
+    return __ldg(&k_perlin_pairs[i & 255u]);
+#endif
+    return pt.s[((i & 255u) << RT_PERLIN_BANK_BITS) | (pt.lane & ((1u << RT_PERLIN_BANK_BITS) - 1u))];
+}
 
 // perlin_noise::grad (perlin_noise.h:173-181)
 #ifdef RT_PERLIN_GTAB

@@ -34,7 +34,9 @@ namespace rtd {
 
 enum : int { Q_NEW = 0, Q_LAMB_CONST, Q_LAMB_NOISE1, Q_LAMB_NOISE6, Q_LAMB_IMAGE, Q_METAL, Q_DIEL, Q_EMIT, NQ };
 #define Q_NONE (-1)
+#ifndef WF_THREADS
 #define WF_THREADS 256
+#endif
 // Programmatic dependent launch: iteration i+1 is launched while iteration i drains, so its CTAs are resident and
 // waiting (griddepcontrol.wait returns once the previous grid has completed and its writes are visible) instead
 // of paying the launch latency between two of the ~70 dependent launches of a frame.  WF_NO_PDL disables it.
@@ -44,6 +46,14 @@ enum : int { Q_NEW = 0, Q_LAMB_CONST, Q_LAMB_NOISE1, Q_LAMB_NOISE6, Q_LAMB_IMAGE
     asm volatile("griddepcontrol.wait;" ::: "memory")
 #else
 #define WF_PDL_PROLOGUE()
+#endif
+#ifndef WF_CTA_THREADS
+// CTA size of the CTA-chunk kernel (= its chunk size).  128 threads x 8 CTAs per SM instead of 256 x 4: the two block
+// barriers of a chunk span 4 warps instead of 8 (C1 -1.1 % at equal table size, gpurun_out/ab_t128.log; 64 x 16: +2 %)
+#define WF_CTA_THREADS 128
+#endif
+#ifndef WF_CTA_MINBLOCKS
+#define WF_CTA_MINBLOCKS (WF_THREADS * 4 / WF_CTA_THREADS) // 64 registers/thread: 32 warps per SM
 #endif
 #ifndef WF_MINBLOCKS
 #define WF_MINBLOCKS 4 // 64 registers/thread: 32 warps per SM (A/B on C1: 15.4 ms at 2, 13.5 at 3, 12.6 at 4)
@@ -314,7 +324,7 @@ RT_DEV bool wf_frame_done(const uint32_t (&n_q)[NQ], unsigned long long path_bas
 // rays of a chunk cost the same (brute-force scenes): C1 runs 11 % faster this way than with warp chunks, whose
 // four-fold atomic traffic (~1 atomic per 3.5 ns and queue counter) saturates the L2 atomic units.
 template <bool USE_BVH, bool NEE>
-__global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
+__global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     k_wf_step_cta(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
     WF_PDL_PROLOGUE();
@@ -343,7 +353,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     const int order[NQ] = {Q_LAMB_NOISE6, Q_LAMB_NOISE1, Q_LAMB_IMAGE, Q_EMIT, Q_DIEL, Q_METAL, Q_LAMB_CONST, Q_NEW};
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
-        total_chunks += (n_q[order[k]] + WF_THREADS - 1) / WF_THREADS;
+        total_chunks += (n_q[order[k]] + WF_CTA_THREADS - 1) / WF_CTA_THREADS;
         chunk_end[k] = total_chunks;
     }
 
@@ -367,7 +377,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 #pragma unroll
         for (int k = 0; k < NQ - 1; ++k) kpos += (chunk >= chunk_end[k]) ? 1 : 0;
         kind = order[kpos];
-        first = (chunk - (kpos ? chunk_end[kpos - 1] : 0u)) * WF_THREADS;
+        first = (chunk - (kpos ? chunk_end[kpos - 1] : 0u)) * WF_CTA_THREADS;
     };
     uint32_t cpar = 0;
     int kind;
@@ -831,8 +841,8 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         const unsigned need = (slots + WF_WCHUNK * (WF_THREADS / 32) - 1) / (WF_WCHUNK * (WF_THREADS / 32)) + NQ;
         grid = need < cap ? need : cap;
     } else { // two waves of CTAs, chunks by stride
-        const unsigned cap = unsigned(sm_count) * WF_CTA_WAVES * WF_MINBLOCKS;
-        const unsigned need = (slots + WF_THREADS - 1) / WF_THREADS + NQ;
+        const unsigned cap = unsigned(sm_count) * WF_CTA_WAVES * WF_CTA_MINBLOCKS;
+        const unsigned need = (slots + WF_CTA_THREADS - 1) / WF_CTA_THREADS + NQ;
         grid = need < cap ? need : cap;
     }
 
@@ -867,7 +877,7 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     auto launch = [&](auto kernel, auto... args) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(WF_THREADS);
+        cfg.blockDim = dim3(warp_grain ? WF_THREADS : WF_CTA_THREADS);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
