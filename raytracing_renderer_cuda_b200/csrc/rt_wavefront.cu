@@ -83,6 +83,13 @@ struct WavefrontState {
     cudaStream_t stream = nullptr;
 };
 
+#ifndef WF_QUEUE_CACHED // queue entries are read once and written once as well: streaming accesses (C1/C2 -0.2 %, gpurun_out/ab_qs.log)
+#define WF_QLOAD(p) __ldcs(p)
+#define WF_QSTORE(p, v) __stcs((p), (v))
+#else
+#define WF_QLOAD(p) __ldg(p)
+#define WF_QSTORE(p, v) (*(p) = (v))
+#endif
 RT_DEV uint32_t* wf_queue(const WfBuffers& b, int parity, int q) { return b.queue + (size_t(parity) * NQ + size_t(q)) * b.pool; }
 
 // Shading class of a hit: material kind x cost class of its (checker-resolved) leaf texture.
@@ -166,8 +173,14 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
                 }
             } // else: no paths left; the slot retires
         } else {
+#ifndef WF_REC_CACHED // a record is read once and written once per iteration: streaming accesses (ld/st.global.cs) keep it
+                      // from displacing the stack frames and sphere data in L1 (C1 -1.3 %, C2 -1.6 %, gpurun_out/ab_cs.log)
+            const float4 ro = __ldcs(&rec->o), rd = __ldcs(&rec->d), ra = __ldcs(&rec->a);
+            const uint4 ids = __ldcs(&rec->ids);
+#else
             const float4 ro = rec->o, rd = rec->d, ra = rec->a;
             const uint4 ids = rec->ids;
+#endif
             pixel = ids.x;
             sample = ids.y;
             bounce = ids.z;
@@ -265,10 +278,17 @@ RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers&
             A = value;
             finished = true;
         } else {
+#ifndef WF_REC_CACHED
+            __stcs(&rec->o, make_float4(ln.r.o.x, ln.r.o.y, ln.r.o.z, ln.r.time));
+            __stcs(&rec->d, make_float4(ln.r.d.x, ln.r.d.y, ln.r.d.z, h.t));
+            __stcs(&rec->a, make_float4(A.x, A.y, A.z, __uint_as_float(h.prim)));
+            __stcs(&rec->ids, make_uint4(ln.pixel, ln.sample, bounce, uint32_t(leaf)));
+#else
             rec->o = make_float4(ln.r.o.x, ln.r.o.y, ln.r.o.z, ln.r.time);
             rec->d = make_float4(ln.r.d.x, ln.r.d.y, ln.r.d.z, h.t);
             rec->a = make_float4(A.x, A.y, A.z, __uint_as_float(h.prim));
             rec->ids = make_uint4(ln.pixel, ln.sample, bounce, uint32_t(leaf));
+#endif
         }
     }
     if (finished) {
@@ -383,7 +403,7 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     int kind;
     uint32_t first;
     locate(blockIdx.x, kind, first);
-    uint32_t slot = (first + threadIdx.x < n_q[kind]) ? __ldg(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
+    uint32_t slot = (first + threadIdx.x < n_q[kind]) ? WF_QLOAD(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
     // Chunks are drawn from a ticket counter (the first gridDim.x are implicit: chunk = blockIdx.x), so a CTA that got
     // cheap chunks simply takes more of them: against handing chunks out by stride, C1 9.46 -> 9.05 ms per frame.
     // Thread 0 draws the ticket of the NEXT chunk at the top of a trip; the two barriers of the trip publish it.
@@ -417,14 +437,14 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
             s_count[cpar ^ 1u][threadIdx.x] = 0u; // the other buffer was last read before the barrier above
         }
         __syncthreads();
-        if (out_q != Q_NONE) wf_queue(wb, par_next, out_q)[s_base[cpar][out_q] + local] = slot;
+        if (out_q != Q_NONE) WF_QSTORE(wf_queue(wb, par_next, out_q) + s_base[cpar][out_q] + local, slot);
         cpar ^= 1u;
         // (requesting the next chunk's slot indices a chunk ahead, and prefetching their records, was measured: 2.6 % and
         // 1.2 % slower with 16 Mi slots — gpurun_out/ab_pipe.log, ab_misc.log)
         next_chunk = s_next_chunk[cpar ^ 1u]; // (cpar was flipped above) written before the two barriers of this trip
         if (next_chunk < total_chunks) {
             locate(next_chunk, kind, first);
-            slot = first + threadIdx.x < n_q[kind] ? __ldg(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
+            slot = first + threadIdx.x < n_q[kind] ? WF_QLOAD(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
         }
     }
 
@@ -532,7 +552,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
         for (int e = 0; e < WF_ROUNDS; ++e) {
             const uint32_t idx = first + uint32_t(e) * 32u + lane;
             const bool valid = idx < n_kind;
-            const uint32_t slot = valid ? __ldg(q_in + idx) : 0u;
+            const uint32_t slot = valid ? WF_QLOAD(q_in + idx) : 0u;
             const int out_q = wf_process_entry<USE_BVH, NEE>(sc, rp, wb, pt, kind, valid, slot, path_base + idx, npix, npaths, accum, nrays);
                 outq_pack |= uint32_t(out_q + 1) << (4 * e);
         }
@@ -562,8 +582,8 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
             const uint32_t oq1 = (outq_pack >> (4 * e)) & 15u; // queue + 1
             const uint32_t base = __shfl_sync(0xffffffffu, my_base, int(oq1 + 31u) & 31);
             if (oq1) { // the slot index is re-read from the input queue (an L1 hit) instead of living in a register
-                const uint32_t slot = __ldg(q_in + first + uint32_t(e) * 32u + lane);
-                wf_queue(wb, par_next, int(oq1) - 1)[base + rank_r[e]] = slot;
+                const uint32_t slot = WF_QLOAD(q_in + first + uint32_t(e) * 32u + lane);
+                WF_QSTORE(wf_queue(wb, par_next, int(oq1) - 1) + base + rank_r[e], slot);
             }
         }
     }
@@ -639,7 +659,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             uint32_t base = 0u;
             if (int(lane) == leader) base = atomicAdd(cnt_next + out_q, uint32_t(__popc(peers)));
             base = __shfl_sync(peers, base, leader);
-            wf_queue(wb, par_next, out_q)[base + uint32_t(__popc(peers & lt_mask))] = slot;
+            WF_QSTORE(wf_queue(wb, par_next, out_q) + base + uint32_t(__popc(peers & lt_mask)), slot);
         }
     };
 
@@ -699,7 +719,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             int out_q = Q_NONE;
             if (!tracing && rank < navail) {
                 const uint32_t idx = pos + rank;
-                const uint32_t slot = __ldg(q_in + idx);
+                const uint32_t slot = WF_QLOAD(q_in + idx);
                 if (wf_begin<NEE>(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
                     q = make_rayq(ln.r);
                     trav_begin(sc, q, t);
