@@ -83,12 +83,30 @@ struct WavefrontState {
     cudaStream_t stream = nullptr;
 };
 
-#ifndef WF_QUEUE_CACHED // queue entries are read once and written once as well: streaming accesses (C1/C2 -0.2 %, gpurun_out/ab_qs.log)
-#define WF_QLOAD(p) __ldcs(p)
-#define WF_QSTORE(p, v) __stcs((p), (v))
+// Streaming accesses to data that is read once and written once per iteration (path records, queue entries): L1
+// evict-first loads and stores (ld/st.global.cs), so they do not displace the stack frames and the sphere data
+// (C1 -1.5 %, C2 -1.9 % on the probes, C2 bench -11 %: gpurun_out/ab_cs.log, ab_qs.log; L2-only .cg accesses were
+// 3.7 % SLOWER than .cs on C1, million_ab.log).  Used by the CTA-chunk and warp-chunk kernels.  The persistent-lane
+// kernel keeps plain accesses: with streaming ones its million-sphere frame differed from the megakernel's in 0.04 %
+// of the rays, identically for .cs and .cg (so not a matter of cache coherence; the kernel sits at its register
+// limit and has shown such a codegen-dependent difference once before) — unexplained, so not shipped.
+template <bool STREAM, typename T>
+RT_DEV T wf_ld(const T* p) {
+    return STREAM ? __ldcs(p) : *p;
+}
+template <bool STREAM, typename T>
+RT_DEV void wf_st(T* p, T v) {
+    if (STREAM) __stcs(p, v);
+    else *p = v;
+}
+template <bool STREAM>
+RT_DEV uint32_t wf_qload(const uint32_t* p) {
+    return STREAM ? __ldcs(p) : __ldg(p);
+}
+#ifdef WF_NO_STREAM // A/B: plain accesses everywhere
+#define WF_STREAM false
 #else
-#define WF_QLOAD(p) __ldg(p)
-#define WF_QSTORE(p, v) (*(p) = (v))
+#define WF_STREAM true
 #endif
 RT_DEV uint32_t* wf_queue(const WfBuffers& b, int parity, int q) { return b.queue + (size_t(parity) * NQ + size_t(q)) * b.pool; }
 
@@ -140,7 +158,7 @@ struct WfLane {
 // scatter.  Returns true when a new ray (ln.r) has to be extended.  Otherwise the entry is finished here —
 // emitter, absorbed ray, depth limit, or no path left — and `out_q` says where the slot goes (Q_NEW / Q_NONE).
 // NEE = RT_RENDER_EMITTER_SAMPLING (a separate instantiation: the reference estimator's kernels do not change).
-template <bool NEE>
+template <bool NEE, bool STREAM>
 RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind, bool valid,
                      uint32_t slot, unsigned long long path, unsigned long long npix, unsigned long long npaths,
                      float4* __restrict__ accum, WfLane& ln, int& out_q) {
@@ -173,14 +191,8 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
                 }
             } // else: no paths left; the slot retires
         } else {
-#ifndef WF_REC_CACHED // a record is read once and written once per iteration: streaming accesses (ld/st.global.cs) keep it
-                      // from displacing the stack frames and sphere data in L1 (C1 -1.3 %, C2 -1.6 %, gpurun_out/ab_cs.log)
-            const float4 ro = __ldcs(&rec->o), rd = __ldcs(&rec->d), ra = __ldcs(&rec->a);
-            const uint4 ids = __ldcs(&rec->ids);
-#else
-            const float4 ro = rec->o, rd = rec->d, ra = rec->a;
-            const uint4 ids = rec->ids;
-#endif
+            const float4 ro = wf_ld<STREAM>(&rec->o), rd = wf_ld<STREAM>(&rec->d), ra = wf_ld<STREAM>(&rec->a);
+            const uint4 ids = wf_ld<STREAM>(&rec->ids);
             pixel = ids.x;
             sample = ids.y;
             bounce = ids.z;
@@ -257,7 +269,7 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
 
 // Second half: the closest hit `h` of ln.r is known.  Miss / constant emitter: the path ends (accumulate, slot to
 // Q_NEW); otherwise the record is stored and the slot goes to the shading queue of the hit.  Returns that queue.
-template <bool NEE>
+template <bool NEE, bool STREAM>
 RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, float4* __restrict__ accum, WfLane& ln,
                      const RayQ& q, Hit h) {
     WfRecord* rec = wb.rec + ln.slot;
@@ -278,17 +290,10 @@ RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers&
             A = value;
             finished = true;
         } else {
-#ifndef WF_REC_CACHED
-            __stcs(&rec->o, make_float4(ln.r.o.x, ln.r.o.y, ln.r.o.z, ln.r.time));
-            __stcs(&rec->d, make_float4(ln.r.d.x, ln.r.d.y, ln.r.d.z, h.t));
-            __stcs(&rec->a, make_float4(A.x, A.y, A.z, __uint_as_float(h.prim)));
-            __stcs(&rec->ids, make_uint4(ln.pixel, ln.sample, bounce, uint32_t(leaf)));
-#else
-            rec->o = make_float4(ln.r.o.x, ln.r.o.y, ln.r.o.z, ln.r.time);
-            rec->d = make_float4(ln.r.d.x, ln.r.d.y, ln.r.d.z, h.t);
-            rec->a = make_float4(A.x, A.y, A.z, __uint_as_float(h.prim));
-            rec->ids = make_uint4(ln.pixel, ln.sample, bounce, uint32_t(leaf));
-#endif
+            wf_st<STREAM>(&rec->o, make_float4(ln.r.o.x, ln.r.o.y, ln.r.o.z, ln.r.time));
+            wf_st<STREAM>(&rec->d, make_float4(ln.r.d.x, ln.r.d.y, ln.r.d.z, h.t));
+            wf_st<STREAM>(&rec->a, make_float4(A.x, A.y, A.z, __uint_as_float(h.prim)));
+            wf_st<STREAM>(&rec->ids, make_uint4(ln.pixel, ln.sample, bounce, uint32_t(leaf)));
         }
     }
     if (finished) {
@@ -306,7 +311,7 @@ RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfB
                             unsigned long long npaths, float4* __restrict__ accum, unsigned long long& nrays) {
     WfLane ln;
     int out_q;
-    const bool has_ray = wf_begin<NEE>(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q);
+    const bool has_ray = wf_begin<NEE, WF_STREAM>(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q);
     if (NEE) nrays += ln.shadow_rays;
     if (USE_BVH) {
         const RayQ q = make_rayq(ln.r);
@@ -318,13 +323,13 @@ RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfB
 #endif
         if (has_ray) {
             ++nrays;
-            out_q = wf_finish<NEE>(sc, rp, wb, accum, ln, q, h);
+            out_q = wf_finish<NEE, WF_STREAM>(sc, rp, wb, accum, ln, q, h);
         }
     } else if (has_ray) {
         const RayQ q = make_rayq(ln.r);
         const Hit h = closest_hit_list(sc, q, rp.tmin);
         ++nrays;
-        out_q = wf_finish<NEE>(sc, rp, wb, accum, ln, q, h);
+        out_q = wf_finish<NEE, WF_STREAM>(sc, rp, wb, accum, ln, q, h);
     }
     return out_q;
 }
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     int kind;
     uint32_t first;
     locate(blockIdx.x, kind, first);
-    uint32_t slot = (first + threadIdx.x < n_q[kind]) ? WF_QLOAD(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
+    uint32_t slot = (first + threadIdx.x < n_q[kind]) ? wf_qload<WF_STREAM>(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
     // Chunks are drawn from a ticket counter (the first gridDim.x are implicit: chunk = blockIdx.x), so a CTA that got
     // cheap chunks simply takes more of them: against handing chunks out by stride, C1 9.46 -> 9.05 ms per frame.
     // Thread 0 draws the ticket of the NEXT chunk at the top of a trip; the two barriers of the trip publish it.
@@ -437,14 +442,14 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
             s_count[cpar ^ 1u][threadIdx.x] = 0u; // the other buffer was last read before the barrier above
         }
         __syncthreads();
-        if (out_q != Q_NONE) WF_QSTORE(wf_queue(wb, par_next, out_q) + s_base[cpar][out_q] + local, slot);
+        if (out_q != Q_NONE) wf_st<WF_STREAM>(wf_queue(wb, par_next, out_q) + s_base[cpar][out_q] + local, slot);
         cpar ^= 1u;
         // (requesting the next chunk's slot indices a chunk ahead, and prefetching their records, was measured: 2.6 % and
         // 1.2 % slower with 16 Mi slots — gpurun_out/ab_pipe.log, ab_misc.log)
         next_chunk = s_next_chunk[cpar ^ 1u]; // (cpar was flipped above) written before the two barriers of this trip
         if (next_chunk < total_chunks) {
             locate(next_chunk, kind, first);
-            slot = first + threadIdx.x < n_q[kind] ? WF_QLOAD(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
+            slot = first + threadIdx.x < n_q[kind] ? wf_qload<WF_STREAM>(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
         }
     }
 
@@ -552,7 +557,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
         for (int e = 0; e < WF_ROUNDS; ++e) {
             const uint32_t idx = first + uint32_t(e) * 32u + lane;
             const bool valid = idx < n_kind;
-            const uint32_t slot = valid ? WF_QLOAD(q_in + idx) : 0u;
+            const uint32_t slot = valid ? wf_qload<WF_STREAM>(q_in + idx) : 0u;
             const int out_q = wf_process_entry<USE_BVH, NEE>(sc, rp, wb, pt, kind, valid, slot, path_base + idx, npix, npaths, accum, nrays);
                 outq_pack |= uint32_t(out_q + 1) << (4 * e);
         }
@@ -582,8 +587,8 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
             const uint32_t oq1 = (outq_pack >> (4 * e)) & 15u; // queue + 1
             const uint32_t base = __shfl_sync(0xffffffffu, my_base, int(oq1 + 31u) & 31);
             if (oq1) { // the slot index is re-read from the input queue (an L1 hit) instead of living in a register
-                const uint32_t slot = WF_QLOAD(q_in + first + uint32_t(e) * 32u + lane);
-                WF_QSTORE(wf_queue(wb, par_next, int(oq1) - 1) + base + rank_r[e], slot);
+                const uint32_t slot = wf_qload<WF_STREAM>(q_in + first + uint32_t(e) * 32u + lane);
+                wf_st<WF_STREAM>(wf_queue(wb, par_next, int(oq1) - 1) + base + rank_r[e], slot);
             }
         }
     }
@@ -659,7 +664,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             uint32_t base = 0u;
             if (int(lane) == leader) base = atomicAdd(cnt_next + out_q, uint32_t(__popc(peers)));
             base = __shfl_sync(peers, base, leader);
-            WF_QSTORE(wf_queue(wb, par_next, out_q) + base + uint32_t(__popc(peers & lt_mask)), slot);
+            *(wf_queue(wb, par_next, out_q) + base + uint32_t(__popc(peers & lt_mask))) = slot;
         }
     };
 
@@ -691,7 +696,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             int out_q = Q_NONE;
             if (tracing && t.node == RT_TRAV_DONE) {
                 ++nrays;
-                out_q = wf_finish<NEE>(sc, rp, wb, accum, ln, q, t.best);
+                out_q = wf_finish<NEE, false>(sc, rp, wb, accum, ln, q, t.best);
                 tracing = false;
             }
             push(out_q, ln.slot);
@@ -719,8 +724,8 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             int out_q = Q_NONE;
             if (!tracing && rank < navail) {
                 const uint32_t idx = pos + rank;
-                const uint32_t slot = WF_QLOAD(q_in + idx);
-                if (wf_begin<NEE>(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
+                const uint32_t slot = __ldg(q_in + idx);
+                if (wf_begin<NEE, false>(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
                     q = make_rayq(ln.r);
                     trav_begin(sc, q, t);
 #ifndef RT_PT_BINARY
