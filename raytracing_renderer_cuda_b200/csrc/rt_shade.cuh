@@ -313,7 +313,7 @@ RT_DEV Ray camera_ray(const DScene& sc, const DRenderParams& rp, uint32_t pixel,
     float time = cam.t0;
     if (cam.t1 != cam.t0) {
         U4 r1 = rng_block(rp.seed, pixel, sample, 0, 1);
-        time = cam.t0 + u01(r1.x) * (cam.t1 - cam.t0);
+        time = __fadd_rn(cam.t0, __fmul_rn(u01(r1.x), __fsub_rn(cam.t1, cam.t0))); // single roundings: the same shutter time in every kernel
     }
     Ray r;
     r.o = cam.origin + offset;
@@ -340,7 +340,10 @@ RT_DEV V3 reflect(V3 v, V3 n) { return v - 2.f * dot(v, n) * n; } // utils.h:93-
 RT_DEV bool refract(V3 v, V3 n, float mu, V3& refracted) {
     V3 i = normalize(v);
     float in = dot(i, n);
-    float delta = 1.f - mu * mu * (1 - in * in);
+    // Written with explicit single roundings: left to the compiler, `1 - in * in` was fused into an FMA in some kernels
+    // and not in others (same source, different inlining context), and the refracted rays of the persistent-lane kernel
+    // left the megakernel's by an ulp — 3.8 % of the pixels of the million-sphere frame (gpurun_out/pt_debug.log).
+    float delta = __fsub_rn(1.f, __fmul_rn(__fmul_rn(mu, mu), __fsub_rn(1.f, __fmul_rn(in, in))));
     if (delta > 0) {
         refracted = mu * (i - n * in) - n * sqrtf(delta);
         return true;
@@ -490,12 +493,12 @@ RT_DEV void scatter_dielectric(const RayQ& q, V3 p, V3 n, float ri, U4 r, Ray& o
     if (ddn > 0.f) {
         refraction_normal = -n;
         mu = ri;
-        cosine = ddn / length(q.d);
-        cosine = __fsqrt_rz(1.f - ri * ri * (1 - cosine * cosine));
+        cosine = __fdiv_rn(ddn, length(q.d));
+        cosine = __fsqrt_rz(__fsub_rn(1.f, __fmul_rn(__fmul_rn(ri, ri), __fsub_rn(1.f, __fmul_rn(cosine, cosine))))); // no contraction, as above
     } else {
         refraction_normal = n;
         mu = 1.f / ri;
-        cosine = -ddn / length(q.d);
+        cosine = __fdiv_rn(-ddn, length(q.d));
     }
     float reflect_prob;
     V3 refracted = mk(0.f, 0.f, 0.f);

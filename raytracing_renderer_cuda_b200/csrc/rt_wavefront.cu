@@ -103,6 +103,11 @@ template <bool STREAM>
 RT_DEV uint32_t wf_qload(const uint32_t* p) {
     return STREAM ? __ldcs(p) : __ldg(p);
 }
+#ifdef WF_PT_STREAM_ON // debugging aid: streaming accesses in the persistent-lane kernel too (see above)
+#define WF_PT_STREAM true
+#else
+#define WF_PT_STREAM false
+#endif
 #ifdef WF_NO_STREAM // A/B: plain accesses everywhere
 #define WF_STREAM false
 #else
@@ -664,7 +669,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             uint32_t base = 0u;
             if (int(lane) == leader) base = atomicAdd(cnt_next + out_q, uint32_t(__popc(peers)));
             base = __shfl_sync(peers, base, leader);
-            *(wf_queue(wb, par_next, out_q) + base + uint32_t(__popc(peers & lt_mask))) = slot;
+            wf_st<WF_PT_STREAM>(wf_queue(wb, par_next, out_q) + base + uint32_t(__popc(peers & lt_mask)), slot);
         }
     };
 
@@ -696,7 +701,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             int out_q = Q_NONE;
             if (tracing && t.node == RT_TRAV_DONE) {
                 ++nrays;
-                out_q = wf_finish<NEE, false>(sc, rp, wb, accum, ln, q, t.best);
+                out_q = wf_finish<NEE, WF_PT_STREAM>(sc, rp, wb, accum, ln, q, t.best);
                 tracing = false;
             }
             push(out_q, ln.slot);
@@ -724,8 +729,8 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             int out_q = Q_NONE;
             if (!tracing && rank < navail) {
                 const uint32_t idx = pos + rank;
-                const uint32_t slot = __ldg(q_in + idx);
-                if (wf_begin<NEE, false>(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
+                const uint32_t slot = wf_qload<WF_PT_STREAM>(q_in + idx);
+                if (wf_begin<NEE, WF_PT_STREAM>(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
                     q = make_rayq(ln.r);
                     trav_begin(sc, q, t);
 #ifndef RT_PT_BINARY
