@@ -348,11 +348,11 @@ RT_DEV bool wf_frame_done(const uint32_t (&n_q)[NQ], unsigned long long path_bas
     return path_base >= npaths && live == 0u;
 }
 
-// Work granularity, variant 1: a CTA takes 256 consecutive entries of ONE queue (chunks are drawn from a ticket counter)
-// and aggregates its pushes in shared memory: one global atomic per CTA chunk and target queue, two block-wide barriers
-// per chunk.  Best when all
-// rays of a chunk cost the same (brute-force scenes): C1 runs 11 % faster this way than with warp chunks, whose
-// four-fold atomic traffic (~1 atomic per 3.5 ns and queue counter) saturates the L2 atomic units.
+// Work granularity, variant 1: a CTA takes WF_CTA_THREADS consecutive entries of ONE queue (chunks are drawn from a
+// ticket counter) and aggregates its pushes in shared memory: one global atomic per CTA chunk and target queue, two
+// block-wide barriers per chunk.  Best when all rays of a chunk cost the same (brute-force scenes): C1 runs 11 % faster
+// this way than with warp chunks, whose atomic traffic (~1 atomic per 3.5 ns and queue counter) saturates the L2
+// atomic units.
 template <bool USE_BVH, bool NEE>
 __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     k_wf_step_cta(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     }
 
     // Tail iterations hold a few hundred live paths: CTAs without a chunk leave before staging anything, and
-    // the 32 KB Perlin table is staged only by CTAs that will run a noise shader (their first chunk is the
+    // the Perlin table is staged only by CTAs that will run a noise shader (their first chunk is the
     // lowest-numbered one they get, and the noise queues come first; textured emitters may need it too).
     if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
     if (blockIdx.x >= total_chunks) return;
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     }
 
     // Tail iterations hold a few hundred live paths: CTAs without a chunk leave before staging anything, and
-    // the 32 KB Perlin table is staged only by CTAs that will run a noise shader (their first chunk is the
+    // the Perlin table is staged only by CTAs that will run a noise shader (their first chunk is the
     // lowest-numbered one they get, and the noise queues come first; textured emitters may need it too).
     if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
     const uint32_t warps_per_cta = WF_THREADS / 32;
@@ -824,7 +824,7 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     if (npaths == 0) return;
     static bool attr_set = false;
     const size_t smem_full = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
-    // scenes without Perlin textures leave the 32 KB table out: 128 KB more L1 per SM for BVH nodes
+    // scenes without Perlin textures leave the table out
     const size_t smem = sc.has_noise ? smem_full : 0;
     if (!attr_set) {
         const int a = int(smem_full);
