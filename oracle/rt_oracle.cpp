@@ -20,6 +20,11 @@
 //              of the unit ball / disk (utils.h:61-91), draw order of main.cu:116-118
 //           1  the product's sampling: Philox4x32-10 keyed on (pixel, sample, bounce), direct
 //              (non-rejection) sampling of the same distributions — what csrc/rt_device.cuh does
+//
+// NOT PINNED (nothing in the reference to pin against): rt_render_params.flags & RT_RENDER_EMITTER_SAMPLING, sampler 1
+// only — the restatement of the product's shadow-ray estimator (the reference README names emitter sampling as future
+// work, README.md:27-28).  It is checked by properties (tests/test_emitter_sampling.py); with flags == 0, which is what
+// every parity test uses, none of that code runs.
 #include "rt_oracle.h"
 
 #include <atomic>

@@ -90,11 +90,7 @@ void launch_shade_probe(const DScene& sc, const DRenderParams& rp, const rt_ray*
                         rt_shade_sample* out_dev, cudaStream_t st) {
     if (n == 0) return;
     const size_t smem = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_shade_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr_set = true;
-    }
+    static_assert(RT_PERLIN_SMEM_WORDS * sizeof(uint32_t) <= 48u * 1024u, "needs cudaFuncAttributeMaxDynamicSharedMemorySize (per device)");
     k_shade_probe<<<unsigned((n + 255) / 256), 256, smem, st>>>(sc, rp, rays_dev, n, use_bvh ? 1 : 0, out_dev);
 }
 
@@ -156,11 +152,6 @@ void launch_render_mega(const DScene& sc, const DRenderParams& rp, bool use_bvh,
     unsigned long long npaths = (unsigned long long)rp.width * rp.height * (unsigned long long)rp.spp;
     if (npaths == 0) return;
     const size_t smem = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_render_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        attr_set = true;
-    }
     unsigned long long want = (npaths + 255) / 256;
     unsigned long long cap = (unsigned long long)sm_count * 32; // several waves of resident CTAs, grid-stride beyond
     unsigned blocks = unsigned(want < cap ? want : cap);

@@ -822,24 +822,10 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     *launches = 0;
     *iterations = 0;
     if (npaths == 0) return;
-    static bool attr_set = false;
-    const size_t smem_full = RT_PERLIN_SMEM_WORDS * sizeof(uint32_t);
+    // (every build option keeps the table under the 48 KB a kernel may use without a per-device opt-in attribute)
+    static_assert(RT_PERLIN_SMEM_WORDS * sizeof(uint32_t) <= 48u * 1024u, "needs cudaFuncAttributeMaxDynamicSharedMemorySize (per device)");
     // scenes without Perlin textures leave the table out
-    const size_t smem = sc.has_noise ? smem_full : 0;
-    if (!attr_set) {
-        const int a = int(smem_full);
-        cudaFuncSetAttribute(k_wf_step_cta<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        cudaFuncSetAttribute(k_wf_step_cta<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        cudaFuncSetAttribute(k_wf_step_warp<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        cudaFuncSetAttribute(k_wf_step_warp<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        cudaFuncSetAttribute(k_wf_step_pt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        cudaFuncSetAttribute(k_wf_step_cta<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        cudaFuncSetAttribute(k_wf_step_cta<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        cudaFuncSetAttribute(k_wf_step_warp<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        cudaFuncSetAttribute(k_wf_step_warp<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        cudaFuncSetAttribute(k_wf_step_pt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-        attr_set = true;
-    }
+    const size_t smem = sc.has_noise ? RT_PERLIN_SMEM_WORDS * sizeof(uint32_t) : 0;
     // emitter importance sampling: a scene without emitters renders with the reference estimator's kernels
     const bool nee = (rp.flags & RT_RENDER_EMITTER_SAMPLING) != 0u && sc.n_lights > 0u;
     // slots in use: never more than there are paths
