@@ -28,6 +28,7 @@
 #include <cstdlib>
 
 #include "rt_kernels.cuh"
+#include "rt_ring.hpp"
 #include "rt_shade.cuh"
 
 namespace rtd {
@@ -81,6 +82,7 @@ struct WavefrontState {
     uint32_t* h_counts = nullptr;           // pinned [2][3 * NQ]: queue sizes, one copy per polling parity
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
+    unsigned long long* ring_ctl = nullptr; // counters of the ring kernel (RT_WF_GRAIN=ring), allocated on first use
 };
 
 // Streaming accesses to data that is read once and written once per iteration (path records, queue entries): L1
@@ -90,28 +92,32 @@ struct WavefrontState {
 // kernel keeps plain accesses: with streaming ones its million-sphere frame differed from the megakernel's in 0.04 %
 // of the rays, identically for .cs and .cg (so not a matter of cache coherence; the kernel sits at its register
 // limit and has shown such a codegen-dependent difference once before) — unexplained, so not shipped.
-template <bool STREAM, typename T>
+// MODE: 0 plain, 1 streaming (.cs), 2 L2-only (.cg) — the ring kernel below re-reads records other SMs wrote during the
+// SAME launch, so nothing it touches may be served from a stale L1 line.
+enum : int { WF_ACC_PLAIN = 0, WF_ACC_STREAM = 1, WF_ACC_L2 = 2 };
+template <int MODE, typename T>
 RT_DEV T wf_ld(const T* p) {
-    return STREAM ? __ldcs(p) : *p;
+    return MODE == WF_ACC_L2 ? __ldcg(p) : (MODE == WF_ACC_STREAM ? __ldcs(p) : *p);
 }
-template <bool STREAM, typename T>
+template <int MODE, typename T>
 RT_DEV void wf_st(T* p, T v) {
-    if (STREAM) __stcs(p, v);
+    if (MODE == WF_ACC_L2) __stcg(p, v);
+    else if (MODE == WF_ACC_STREAM) __stcs(p, v);
     else *p = v;
 }
-template <bool STREAM>
+template <int MODE>
 RT_DEV uint32_t wf_qload(const uint32_t* p) {
-    return STREAM ? __ldcs(p) : __ldg(p);
+    return MODE == WF_ACC_L2 ? __ldcg(p) : (MODE == WF_ACC_STREAM ? __ldcs(p) : __ldg(p));
 }
 #ifdef WF_PT_STREAM_ON // debugging aid: streaming accesses in the persistent-lane kernel too (see above)
-#define WF_PT_STREAM true
+#define WF_PT_STREAM WF_ACC_STREAM
 #else
-#define WF_PT_STREAM false
+#define WF_PT_STREAM WF_ACC_PLAIN
 #endif
 #ifdef WF_NO_STREAM // A/B: plain accesses everywhere
-#define WF_STREAM false
+#define WF_STREAM WF_ACC_PLAIN
 #else
-#define WF_STREAM true
+#define WF_STREAM WF_ACC_STREAM
 #endif
 RT_DEV uint32_t* wf_queue(const WfBuffers& b, int parity, int q) { return b.queue + (size_t(parity) * NQ + size_t(q)) * b.pool; }
 
@@ -163,7 +169,7 @@ struct WfLane {
 // scatter.  Returns true when a new ray (ln.r) has to be extended.  Otherwise the entry is finished here —
 // emitter, absorbed ray, depth limit, or no path left — and `out_q` says where the slot goes (Q_NEW / Q_NONE).
 // NEE = RT_RENDER_EMITTER_SAMPLING (a separate instantiation: the reference estimator's kernels do not change).
-template <bool NEE, bool STREAM>
+template <bool NEE, int STREAM>
 RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind, bool valid,
                      uint32_t slot, unsigned long long path, unsigned long long npix, unsigned long long npaths,
                      float4* __restrict__ accum, WfLane& ln, int& out_q) {
@@ -274,7 +280,7 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
 
 // Second half: the closest hit `h` of ln.r is known.  Miss / constant emitter: the path ends (accumulate, slot to
 // Q_NEW); otherwise the record is stored and the slot goes to the shading queue of the hit.  Returns that queue.
-template <bool NEE, bool STREAM>
+template <bool NEE, int STREAM>
 RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, float4* __restrict__ accum, WfLane& ln,
                      const RayQ& q, Hit h) {
     WfRecord* rec = wb.rec + ln.slot;
@@ -310,13 +316,13 @@ RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers&
 
 // One whole queue entry (the CTA-chunk and warp-chunk kernels): begin, closest hit, finish.  Called by all 32 lanes of
 // the warp (the BVH traversal is warp-cooperative); `valid` = false for lanes past the end of the queue.
-template <bool USE_BVH, bool NEE>
+template <bool USE_BVH, bool NEE, int ACC = WF_STREAM>
 RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind,
                             bool valid, uint32_t slot, unsigned long long path, unsigned long long npix,
                             unsigned long long npaths, float4* __restrict__ accum, unsigned long long& nrays) {
     WfLane ln;
     int out_q;
-    const bool has_ray = wf_begin<NEE, WF_STREAM>(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q);
+    const bool has_ray = wf_begin<NEE, ACC>(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q);
     if (NEE) nrays += ln.shadow_rays;
     if (USE_BVH) {
         const RayQ q = make_rayq(ln.r);
@@ -328,13 +334,13 @@ RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfB
 #endif
         if (has_ray) {
             ++nrays;
-            out_q = wf_finish<NEE, WF_STREAM>(sc, rp, wb, accum, ln, q, h);
+            out_q = wf_finish<NEE, ACC>(sc, rp, wb, accum, ln, q, h);
         }
     } else if (has_ray) {
         const RayQ q = make_rayq(ln.r);
         const Hit h = closest_hit_list(sc, q, rp.tmin);
         ++nrays;
-        out_q = wf_finish<NEE, WF_STREAM>(sc, rp, wb, accum, ln, q, h);
+        out_q = wf_finish<NEE, ACC>(sc, rp, wb, accum, ln, q, h);
     }
     return out_q;
 }
@@ -770,6 +776,161 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
     if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
 }
 
+// Work granularity, variant 4 — EXPERIMENTAL, selected only by RT_WF_GRAIN=ring, never by default, and not yet run on
+// a GPU (written after the round's GPU budget was spent; tools/ring_probe.py is the check to run first: same frame
+// as the CTA-chunk kernel, then the A/B timing).  ONE persistent launch per frame and no iteration barrier: the ~60
+// thin tail iterations of a frame and the bubble between two dependent launches become the
+// latency of the longest path.
+//
+// Per shading class a ring of slot indices in the queue memory (capacity `cap`, a power of two >= 2 x slots in use)
+// and three 64-bit counters that live for the life of the WavefrontState, each in its own 128-byte line:
+//   reserve  producers: base = atomicAdd(reserve, c) hands out write positions (one atomic per CTA chunk and class)
+//   credits  a counting semaphore: producers add c right after reserving; a consumer takes n entries with
+//            atomicAdd(credits, -n) and gives them back when the old value was < n — so the sum of the successful
+//            claims never exceeds what was reserved, whatever the interleaving (no CAS loop: with ~100 claims per
+//            microsecond a compare-and-swap on the head would fail almost always)
+//   head     consumers: pos = atomicAdd(head, n) after the credits were taken, so every position below head has been
+//            reserved by a producer that is running and writes it without waiting for anybody.
+// A ring entry is slot | tag << 25 with tag = 64 | (lap & 63), lap = position / cap: a consumer polls ITS positions
+// until the tag of the current lap shows up (the producer may still be between its reserve and its store), which
+// replaces a commit counter.  Stale contents never match: the lap before carries another tag, and raw slot indices
+// written by the per-iteration kernels (< 2^24) carry tag 0.  Records are written before the entry (st.release per
+// thread) and read with L2-only loads after it (WF_ACC_L2: the address depends on the polled entry).
+// A CTA takes a chunk of up to WF_CTA_THREADS entries of the class with the most credits (full chunks while any class
+// has one — the bulk of the frame —, whatever is there in the tail), the claim of the NEXT chunk is drawn by warp 1
+// while warp 0 reserves the pushes of the current one, so a trip has the same two block barriers as k_wf_step_cta.
+// Termination: `busy` counts CTAs that hold (or are trying to take) a chunk; a CTA leaves when it finds no credits
+// and busy == 0 twice around the scan.  A CTA that pushed entries sees them itself, so work is never abandoned; a
+// wrong early exit of ANOTHER CTA only costs parallelism.  Q_NEW is ignored once every path of the frame has started
+// (its leftovers are dropped by the next frame's k_ring_commit).
+// Not proven, only practically impossible: a consumer stalled between its claim and its read for a whole lap of
+// the ring (>= slots further pushes of the same class) would find its entry overwritten and spin forever.
+using WfRing = ring::Ring;
+using ring::RingClaim;
+using ring::RC_RESERVE;
+using ring::RC_CREDITS;
+using ring::RC_HEAD;
+using RingOps = ring::Protocol<NQ, Q_NEW>; // the claim/termination protocol: rt_ring.hpp (also compiled for the host by tests/ring_sim.cpp)
+
+template <bool USE_BVH, bool NEE>
+__global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
+    k_wf_ring(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
+              const __grid_constant__ WfRing rg, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t s_count[2][NQ]; // double-buffered by chunk parity, as in k_wf_step_cta
+    __shared__ unsigned long long s_base[2][NQ];
+    __shared__ RingClaim s_claim;
+    constexpr uint32_t kClaimer = WF_CTA_THREADS >= 64 ? 32u : 0u; // lane 0 of warp 1: warp 0 does the push atomics meanwhile
+
+    const PerlinTab pt{smem, threadIdx.x & 31u};
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
+    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+
+    if (threadIdx.x == kClaimer) {
+        RingClaim c;
+        RingOps::claim_wait(rg, npaths, WF_CTA_THREADS, false, c);
+        s_claim = c;
+    }
+    if (threadIdx.x < 2 * NQ) (&s_count[0][0])[threadIdx.x] = 0u;
+    __syncthreads();
+    if (s_claim.kind < 0) return; // (uniform) a CTA that found the frame finished
+    if (sc.has_noise) perlin_stage(smem, threadIdx.x, blockDim.x); // once per CTA and frame
+    __syncthreads();
+
+    unsigned long long nrays = 0;
+    uint32_t cpar = 0;
+    for (;;) {
+        const int kind = s_claim.kind; // rewritten by the claimer only after the first barrier of this trip
+        if (kind < 0) break;
+        const uint32_t n = s_claim.n;
+        const unsigned long long pos = s_claim.pos, path_base = s_claim.path;
+        const bool valid = threadIdx.x < n;
+        uint32_t slot = 0u;
+        if (valid) { // the entry may still be on its way: poll for the tag of this lap
+            const unsigned long long p = pos + threadIdx.x;
+            const uint32_t want = ring::tag(rg, p);
+            const uint32_t* e = ring::entry(rg, kind, p);
+            uint32_t v = ring::load_entry(e);
+            while ((v >> 25) != want) v = ring::load_entry(e);
+            slot = v & 0xffffffu;
+        }
+
+        const int out_q = wf_process_entry<USE_BVH, NEE, WF_ACC_L2>(sc, rp, wb, pt, kind, valid, slot, path_base + threadIdx.x, npix,
+                                                                    npaths, accum, nrays);
+
+        // ---- push: warp ballot -> shared counters -> one reserve + one credit atomic per class ----
+        uint32_t local = 0;
+        {
+            const unsigned peers = __match_any_sync(0xffffffffu, out_q);
+            if (out_q != Q_NONE) {
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (int(lane) == leader) base = atomicAdd(&s_count[cpar][out_q], uint32_t(__popc(peers)));
+                base = __shfl_sync(peers, base, leader);
+                local = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < NQ) {
+            const uint32_t c = s_count[cpar][threadIdx.x];
+            unsigned long long base = 0ull;
+            if (c) {
+                base = ring::add(ring::ctl(rg, int(threadIdx.x), RC_RESERVE), c);
+                ring::add(ring::ctl(rg, int(threadIdx.x), RC_CREDITS), c); // consumers poll the tags
+            }
+            s_base[cpar][threadIdx.x] = base;
+            s_count[cpar ^ 1u][threadIdx.x] = 0u; // the other buffer was last read before the barrier above
+        }
+        if (threadIdx.x == kClaimer) { // the next chunk, while this CTA still counts as busy
+            RingClaim c;
+            RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c);
+            s_claim = c;
+        }
+        __syncthreads();
+        if (out_q != Q_NONE) {
+            const unsigned long long p = s_base[cpar][out_q] + local;
+            ring::publish(ring::entry(rg, out_q, p), slot | (ring::tag(rg, p) << 25)); // after this thread's record (wf_finish)
+        }
+        cpar ^= 1u;
+        if (s_claim.kind < 0) { // (uniform) nothing was claimable before this chunk's pushes: release `busy` and wait
+            __syncthreads();    // everybody has looked at s_claim
+            if (threadIdx.x == kClaimer) {
+                RingClaim c;
+                RingOps::claim_wait(rg, npaths, WF_CTA_THREADS, true, c);
+                s_claim = c;
+            }
+            __syncthreads();
+        }
+    }
+
+    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
+    if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
+}
+
+// frame start of the ring kernel (two launches, each alone on the stream): every slot in use enters Q_NEW ...
+__global__ void k_ring_fill(const __grid_constant__ WfRing rg, uint32_t n_slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const unsigned long long p = *ring::ctl(rg, Q_NEW, RC_RESERVE) + i;
+    *ring::entry(rg, Q_NEW, p) = i | (ring::tag(rg, p) << 25);
+}
+// ... and the counters: whatever an earlier frame left queued (Q_NEW entries after its last path) is dropped
+__global__ void k_ring_commit(const __grid_constant__ WfRing rg, uint32_t n_slots) {
+    const int q = int(threadIdx.x);
+    if (q < NQ) {
+        const unsigned long long r = *ring::ctl(rg, q, RC_RESERVE);
+        const unsigned long long add = q == Q_NEW ? n_slots : 0u;
+        *ring::ctl(rg, q, RC_HEAD) = r;
+        *ring::ctl(rg, q, RC_RESERVE) = r + add;
+        *ring::ctl(rg, q, RC_CREDITS) = add;
+    }
+    if (q == 0) {
+        *ring::word(rg, RingOps::RC_NEXT_PATH) = 0ull;
+        *ring::word(rg, RingOps::RC_BUSY) = 0ull;
+    }
+}
+
 // fills Q_NEW of iteration 0 with every slot and resets the path counter
 __global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -806,6 +967,7 @@ void wavefront_destroy(WavefrontState* ws) {
     if (ws->b.counts) cudaFree(ws->b.counts);
     if (ws->b.tickets) cudaFree(ws->b.tickets);
     if (ws->b.next_path) cudaFree(ws->b.next_path);
+    if (ws->ring_ctl) cudaFree(ws->ring_ctl);
     for (auto& e : ws->poll_ev)
         if (e) cudaEventDestroy(e);
     if (ws->h_status) cudaFreeHost(ws->h_status);
@@ -814,6 +976,47 @@ void wavefront_destroy(WavefrontState* ws) {
 }
 
 size_t wavefront_pool(const WavefrontState* ws) { return ws ? ws->b.pool : 0; }
+
+// RT_WF_GRAIN=ring (experimental, see k_wf_ring): fill + commit + ONE persistent launch.  Returns false when the
+// pool does not fit the entry format (slot indices of 24 bits) or the counters cannot be allocated; the caller then
+// renders with the per-iteration kernels.
+static bool wavefront_render_ring(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, bool nee, size_t smem,
+                                  uint32_t slots, float4* accum, unsigned long long* ray_counter, int sm_count, cudaStream_t st,
+                                  uint32_t* launches, uint32_t* iterations) {
+    const WfBuffers& wb = ws->b;
+    if (wb.pool > (1u << 24) || wb.pool < 64u) return false;
+    WfRing rg{};
+    rg.ring = wb.queue; // [2][NQ][pool] words, used as [NQ][cap] with cap = the largest power of two <= 2 * pool
+    rg.cap_log2 = 0;
+    while ((2ull << rg.cap_log2) <= 2ull * wb.pool) ++rg.cap_log2;
+    if (!ws->ring_ctl) { // first use: counters at zero, no word of the queue memory may look like a tagged entry
+        if (cudaMalloc(&ws->ring_ctl, size_t(RingOps::RC_COUNT) * 16u * sizeof(unsigned long long)) != cudaSuccess) {
+            ws->ring_ctl = nullptr;
+            cudaGetLastError();
+            return false;
+        }
+        cudaMemsetAsync(ws->ring_ctl, 0, size_t(RingOps::RC_COUNT) * 16u * sizeof(unsigned long long), st);
+        cudaMemsetAsync(wb.queue, 0, size_t(2) * NQ * wb.pool * sizeof(uint32_t), st);
+    }
+    rg.ctl = ws->ring_ctl;
+    const uint32_t half = 1u << (rg.cap_log2 - 1u);
+    const uint32_t n = slots < half ? slots : half; // at most half a lap of entries can ever be queued
+    k_ring_fill<<<(n + 255u) / 256u, 256, 0, st>>>(rg, n);
+    k_ring_commit<<<1, 32, 0, st>>>(rg, n);
+    const unsigned cap = unsigned(sm_count) * WF_CTA_MINBLOCKS; // resident CTAs; every one of them polls for work
+    const unsigned need = (n + WF_CTA_THREADS - 1) / WF_CTA_THREADS;
+    const unsigned grid = need < cap ? need : cap;
+    if (nee) {
+        if (use_bvh) k_wf_ring<true, true><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
+        else k_wf_ring<false, true><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
+    } else {
+        if (use_bvh) k_wf_ring<true, false><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
+        else k_wf_ring<false, false><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
+    }
+    *launches = 3;
+    *iterations = 1;
+    return true;
+}
 
 void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
                       unsigned long long* ray_counter, int sm_count, cudaStream_t st, uint32_t* launches,
@@ -831,6 +1034,9 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     // slots in use: never more than there are paths
     WfBuffers wb = ws->b;
     const uint32_t slots = uint32_t(npaths < wb.pool ? npaths : wb.pool);
+    if (const char* e = getenv("RT_WF_GRAIN"))
+        if (e[0] == 'r' && wavefront_render_ring(ws, sc, rp, use_bvh, nee, smem, slots, accum, ray_counter, sm_count, st, launches, iterations))
+            return;
     k_wf_init<<<(slots + 255) / 256 > 0 ? (slots + 255) / 256 : 1, 256, 0, st>>>(wb, slots);
     ++*launches;
 
