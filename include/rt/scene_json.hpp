@@ -62,6 +62,15 @@ public:
 private:
     const std::string& _s;
     size_t _i = 0;
+    int _depth = 0; // containers open at _i: scene documents nest 4 deep, and val() recurses once per level
+    static constexpr int kMaxDepth = 64;
+    struct nested {
+        parser& p;
+        explicit nested(parser& q) : p(q) {
+            if (++p._depth > kMaxDepth) p.fail("nesting too deep");
+        }
+        ~nested() { --p._depth; }
+    };
     [[noreturn]] void fail(const char* what) const {
         throw std::invalid_argument("JSON: " + std::string(what) + " at offset " + std::to_string(_i));
     }
@@ -82,6 +91,7 @@ private:
         const char c = _s[_i];
         value v;
         if (c == '{') {
+            const nested level(*this);
             ++_i;
             v.kind = value::OBJ;
             if (eat('}')) return v;
@@ -93,6 +103,7 @@ private:
             } while (eat(','));
             if (!eat('}')) fail("expected '}'");
         } else if (c == '[') {
+            const nested level(*this);
             ++_i;
             v.kind = value::ARR;
             if (eat(']')) return v;

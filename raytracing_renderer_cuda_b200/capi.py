@@ -21,7 +21,7 @@ LIB_PATH = Path(os.environ["RT_B200_LIB"]) if os.environ.get("RT_B200_LIB") else
 
 RT_INVALID_ID = 0xFFFFFFFF
 RT_OK = 0
-RT_ERR_INVALID_ARG = 1
+RT_ERR_INVALID_ARG, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_UNSUPPORTED, RT_ERR_NO_DEVICE, RT_ERR_IO = 1, 2, 3, 4, 5, 6
 STATUS_NAMES = {0: "RT_OK", 1: "RT_ERR_INVALID_ARG", 2: "RT_ERR_CUDA", 3: "RT_ERR_OOM", 4: "RT_ERR_UNSUPPORTED",
                 5: "RT_ERR_NO_DEVICE", 6: "RT_ERR_IO"}
 

@@ -98,8 +98,27 @@ rt_status rt_read_ppm_f32(const char* path, float** out_rgb, int32_t* width, int
         fclose(f);
         return RT_ERR_IO;
     }
+    // the header of a damaged file must not size an allocation: the pixel bytes have to be there
+    const long data_at = ftell(f);
+    uint64_t left = 0;
+    if (data_at >= 0 && fseek(f, 0, SEEK_END) == 0) {
+        const long end = ftell(f);
+        if (end >= data_at) left = uint64_t(end - data_at);
+        fseek(f, data_at, SEEK_SET);
+    }
+    const uint64_t need = uint64_t(w) * uint64_t(h) * uint64_t(ch); // < 2^64: w, h < 2^31, ch <= 3
+    if (need > left) {
+        fclose(f);
+        return RT_ERR_IO;
+    }
     size_t n = size_t(w) * size_t(h) * 3;
-    std::vector<uint8_t> bytes(size_t(w) * size_t(h) * size_t(ch));
+    std::vector<uint8_t> bytes;
+    try {
+        bytes.resize(size_t(need));
+    } catch (const std::exception&) {
+        fclose(f);
+        return RT_ERR_OOM;
+    }
     ok = fread(bytes.data(), 1, bytes.size(), f) == bytes.size();
     fclose(f);
     if (!ok) return RT_ERR_IO;
@@ -107,10 +126,8 @@ rt_status rt_read_ppm_f32(const char* path, float** out_rgb, int32_t* width, int
     if (!rgb) return RT_ERR_OOM;
     if (ch == 3) {
         for (size_t i = 0; i < n; ++i) rgb[i] = float(bytes[i]) / 255.0f;
-    } else { // grey -> RGB through the same conversion a 1-channel stbi_loadf result takes
-        std::vector<float> g(bytes.size());
-        for (size_t i = 0; i < g.size(); ++i) g[i] = float(bytes[i]) / 255.0f;
-        rt_image_to_rgb(g.data(), w, h, 1, rgb);
+    } else { // grey -> RGB: what rt_image_to_rgb does with a 1-channel stbi_loadf result
+        for (size_t i = 0; i < bytes.size(); ++i) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = float(bytes[i]) / 255.0f;
     }
     *out_rgb = rgb;
     *width = w;
@@ -267,9 +284,23 @@ rt_status rt_scene_desc_load(const char* path, rt_scene_desc** out) {
     OwnedDesc* od = nullptr;
     try {
         od = new OwnedDesc();
+        // the counts of a damaged file must not size an allocation: everything is checked against the bytes that are there
+        uint64_t left = 0;
+        if (fseek(f, 0, SEEK_END) == 0) {
+            const long end = ftell(f);
+            left = end > 0 ? uint64_t(end) : 0;
+        }
+        rewind(f);
         uint32_t hdr[7];
-        bool ok = fread(hdr, sizeof hdr, 1, f) == 1 && hdr[0] == 0x43535452u && hdr[1] == 1u;
+        bool ok = left >= sizeof hdr + sizeof(rt_camera) && fread(hdr, sizeof hdr, 1, f) == 1 && hdr[0] == 0x43535452u && hdr[1] == 1u;
         ok = ok && fread(&od->fs.cam, sizeof(rt_camera), 1, f) == 1;
+        if (ok) {
+            left -= sizeof hdr + sizeof(rt_camera);
+            const uint64_t arrays = uint64_t(hdr[2]) * sizeof(rt_sphere) + uint64_t(hdr[3]) * sizeof(rt_material) +
+                                    uint64_t(hdr[4]) * sizeof(rt_texture);
+            ok = arrays <= left && uint64_t(hdr[5]) * (2 * sizeof(int32_t)) <= left - arrays;
+            if (ok) left -= arrays;
+        }
         if (ok) {
             od->fs.spheres.resize(hdr[2]);
             od->fs.materials.resize(hdr[3]);
@@ -282,14 +313,19 @@ rt_status rt_scene_desc_load(const char* path, rt_scene_desc** out) {
         }
         for (uint32_t i = 0; ok && i < hdr[5]; ++i) {
             int32_t wh[2];
-            ok = fread(wh, sizeof wh, 1, f) == 1 && wh[0] > 0 && wh[1] > 0;
+            ok = left >= sizeof wh && fread(wh, sizeof wh, 1, f) == 1 && wh[0] > 0 && wh[1] > 0;
             if (!ok) break;
-            size_t n = size_t(wh[0]) * size_t(wh[1]) * 3;
+            left -= sizeof wh;
+            const uint64_t n = uint64_t(wh[0]) * uint64_t(wh[1]) * 3; // < 2^64: both factors are below 2^31
+            ok = n <= left / sizeof(float);
+            if (!ok) break;
+            left -= n * sizeof(float);
             od->image_data.emplace_back(n);
             ok = fread(od->image_data.back().data(), sizeof(float), n, f) == n;
             od->fs.images[i] = rt_image{nullptr, wh[0], wh[1]};
         }
         fclose(f);
+        f = nullptr;
         if (!ok) {
             delete od;
             return RT_ERR_IO;
@@ -298,9 +334,14 @@ rt_status rt_scene_desc_load(const char* path, rt_scene_desc** out) {
         *out = &od->desc;
         return RT_OK;
     } catch (const std::bad_alloc&) {
-        fclose(f);
+        if (f) fclose(f);
         delete od;
         return RT_ERR_OOM;
+    } catch (const std::exception& e) { // nothing may propagate through the C ABI
+        if (f) fclose(f);
+        delete od;
+        rtd::set_error_message(e.what());
+        return RT_ERR_IO;
     }
 }
 

@@ -221,7 +221,7 @@ struct Decoder {
             const int diff = t ? extend_receive(t) : 0;
             const int dc = c.dc_pred + diff;
             c.dc_pred = dc;
-            data[0] = int16_t(dc << succ_low);
+            data[0] = int16_t(uint32_t(dc) << succ_low); // two's-complement shift of a possibly negative value, well defined
         } else if (get_bit()) {
             data[0] = int16_t(data[0] + int16_t(1 << succ_low));
         }
@@ -254,7 +254,7 @@ struct Decoder {
                     k += r;
                     const unsigned zig = kDezigzag[k < 79 ? k : 78];
                     ++k;
-                    data[zig] = int16_t(extend_receive(s) << shift);
+                    data[zig] = int16_t(uint32_t(extend_receive(s)) << shift);
                 }
             } while (k <= spec_end);
         } else {

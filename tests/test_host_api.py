@@ -92,6 +92,39 @@ def test_scene_file_round_trip(tmp_path, earth):
         rt.SceneDesc.load(str(tmp_path / "missing.rtsc"))
 
 
+def test_damaged_scene_files_are_io_errors(tmp_path, earth):
+    """Counts and image sizes of a scene file are checked against the bytes that are there before anything is allocated:
+    a header that announces 4 G spheres, an image of 2^31 x 2^31 texels or a truncated file is RT_ERR_IO."""
+    import struct
+
+    a = rt.SceneDesc.builtin("earth_emitter", image=earth[:8, :16].copy())
+    p = tmp_path / "ok.rtsc"
+    a.save(str(p))
+    good = p.read_bytes()
+    assert rt.SceneDesc.load(str(p)).desc.n_spheres == a.desc.n_spheres
+    cam = C.sizeof(capi.rt_camera)
+    img_at = 28 + cam + a.desc.n_spheres * C.sizeof(capi.rt_sphere) + a.desc.n_materials * C.sizeof(capi.rt_material) \
+        + a.desc.n_textures * C.sizeof(capi.rt_texture)
+    assert struct.unpack_from("<ii", good, img_at) == (16, 8)
+    cases = {
+        "spheres": good[:8] + struct.pack("<I", 0xFFFFFFFF) + good[12:],
+        "materials": good[:12] + struct.pack("<I", 0xFFFFFFF0) + good[16:],
+        "images": good[:20] + struct.pack("<I", 0x7FFFFFFF) + good[24:],
+        "image_size": good[:img_at] + struct.pack("<ii", 0x7FFFFFFF, 0x7FFFFFFF) + good[img_at + 8:],
+        "truncated_arrays": good[:28 + cam + 40],
+        "truncated_image": good[:-5],
+        "header_only": good[:28],
+        "empty": b"",
+        "magic": b"XXXX" + good[4:],
+    }
+    for name, blob in cases.items():
+        q = tmp_path / f"{name}.rtsc"
+        q.write_bytes(blob)
+        with pytest.raises(capi.RtError) as e:
+            rt.SceneDesc.load(str(q))
+        assert e.value.status == capi.RT_ERR_IO, name
+
+
 def test_writer_conversion_restates_main_cu():
     rng = np.random.default_rng(0)
     rgb = rng.random((7, 5, 3), dtype=np.float32)
@@ -111,3 +144,22 @@ def test_ppm_round_trip(tmp_path):
     got = np.ctypeslib.as_array(out, (3, 4, 3)).copy()
     lib.rt_free(out)
     assert (w.value, h.value) == (4, 3) and np.array_equal(got, img.astype(np.float32) / np.float32(255))
+
+
+def test_damaged_pnm_files_are_io_errors(tmp_path):
+    """The size a PNM header announces must be backed by the file before it sizes an allocation."""
+    lib = capi.load_library()
+    out, w, h = C.POINTER(C.c_float)(), C.c_int32(), C.c_int32()
+    cases = [b"P6\n2000000000 2000000000\n255\n" + b"\0" * 64, b"P5\n65535 65535\n255\nxx", b"P6\n4 3\n255\n" + b"\0" * 35,
+             b"P6\n4 3\n65535\n" + b"\0" * 72, b"P6\n-4 3\n255\n" + b"\0" * 36, b"P6", b"", b"P3\n1 1\n255\n0 0 0\n"]
+    for i, blob in enumerate(cases):
+        p = tmp_path / f"bad{i}.ppm"
+        p.write_bytes(blob)
+        assert lib.rt_read_ppm_f32(str(p).encode(), C.byref(out), C.byref(w), C.byref(h)) == capi.RT_ERR_IO, blob[:24]
+    g = tmp_path / "grey.pgm"
+    g.write_bytes(b"P5\n# a comment\n3 2\n255\n" + bytes(range(0, 60, 10)))
+    assert lib.rt_read_ppm_f32(str(g).encode(), C.byref(out), C.byref(w), C.byref(h)) == 0
+    got = np.ctypeslib.as_array(out, (2, 3, 3)).copy()
+    lib.rt_free(out)
+    want = (np.arange(0, 60, 10, dtype=np.float32) / np.float32(255)).reshape(2, 3, 1).repeat(3, axis=2)
+    assert np.array_equal(got, want)

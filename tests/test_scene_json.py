@@ -93,6 +93,17 @@ def test_malformed_documents_are_errors(bad):
     assert e.value.status == capi.RT_ERR_INVALID_ARG and str(e.value)
 
 
+def test_deeply_nested_document_is_an_error_not_a_stack_overflow():
+    """The parser recurses once per open container: 200 000 brackets used to overflow the stack (found by fuzzing the
+    front-end under AddressSanitizer); nesting is limited to 64 levels, a scene document needs 4."""
+    for opener in ("[", "{\"a\":"):
+        with pytest.raises(capi.RtError) as e:
+            rt.SceneDesc.from_json('{"camera": ' + opener * 200_000)
+        assert e.value.status == capi.RT_ERR_INVALID_ARG and "nesting" in str(e.value)
+    ok = '{"camera": {"lookfrom": [0,0,1], "lookat": [0,0,0]}, "objects": [], "extra": ' + "[" * 60 + "]" * 60 + "}"
+    assert rt.SceneDesc.from_json(ok).desc.n_spheres == 0
+
+
 def test_cli_help_runs():
     import subprocess
 
