@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <string>
 #include <vector>
@@ -48,6 +49,17 @@ namespace {
         }                                                                                       \
     } while (0)
 
+// Every rt_status entry point is a function-try-block closed by this: nothing propagates through the C ABI
+// (SURVEY.md 8b "no exceptions across the boundary"); host containers that cannot grow are RT_ERR_OOM.
+#define RT_API_CATCH                                   \
+    catch (const std::bad_alloc&) {                    \
+        set_error("out of host memory");               \
+        return RT_ERR_OOM;                             \
+    }                                                  \
+    catch (const std::exception& e) {                  \
+        set_error("unexpected exception: %s", e.what()); \
+        return RT_ERR_INVALID_ARG;                     \
+    }
 #define ARG_CHECK(cond, msg)                  \
     do {                                      \
         if (!(cond)) {                        \
@@ -341,7 +353,7 @@ void rt_default_render_params(rt_render_params* p) {
     p->flags = 0; // the reference's estimator
 }
 
-rt_status rt_context_create(int device, rt_context** out) {
+rt_status rt_context_create(int device, rt_context** out) try {
     ARG_CHECK(out != nullptr, "out is NULL");
     *out = nullptr;
     int count = 0;
@@ -375,7 +387,7 @@ rt_status rt_context_create(int device, rt_context** out) {
     for (auto& ev : ctx->ev) CUDA_TRY(cudaEventCreate(&ev));
     *out = ctx;
     return RT_OK;
-}
+} RT_API_CATCH
 
 void rt_context_destroy(rt_context* ctx) {
     if (!ctx) return;
@@ -394,21 +406,21 @@ void rt_context_destroy(rt_context* ctx) {
     delete ctx;
 }
 
-rt_status rt_context_set_stream(rt_context* ctx, void* cuda_stream) {
+rt_status rt_context_set_stream(rt_context* ctx, void* cuda_stream) try {
     ARG_CHECK(ctx != nullptr, "ctx is NULL");
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     ctx->own_stream = false;
     return RT_OK;
-}
+} RT_API_CATCH
 
-rt_status rt_context_synchronize(rt_context* ctx) {
+rt_status rt_context_synchronize(rt_context* ctx) try {
     ARG_CHECK(ctx != nullptr, "ctx is NULL");
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return RT_OK;
-}
+} RT_API_CATCH
 
-rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out) {
+rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out) try {
     ARG_CHECK(ctx != nullptr && out != nullptr, "ctx/out is NULL");
     *out = nullptr;
     rt_status st = validate_desc(desc);
@@ -696,7 +708,7 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     guard.s = nullptr;
     *out = s;
     return RT_OK;
-}
+} RT_API_CATCH
 
 void rt_scene_destroy(rt_scene* scene) {
     if (!scene) return;
@@ -714,14 +726,14 @@ void rt_scene_destroy(rt_scene* scene) {
     delete scene;
 }
 
-rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info) {
+rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info) try {
     ARG_CHECK(scene && info, "scene/info is NULL");
     *info = scene->info;
     return RT_OK;
-}
+} RT_API_CATCH
 
 rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n, float tmin, int use_bvh,
-                           rt_hit* hits) {
+                           rt_hit* hits) try {
     ARG_CHECK(ctx && scene, "ctx/scene is NULL");
     ARG_CHECK(n == 0 || (rays && hits), "rays/hits is NULL");
     if (n == 0) return RT_OK;
@@ -745,10 +757,10 @@ rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray*
         return RT_ERR_CUDA;
     }
     return RT_OK;
-}
+} RT_API_CATCH
 
 rt_status rt_shade_probe(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n, const rt_render_params* p,
-                         int use_bvh, rt_shade_sample* out) {
+                         int use_bvh, rt_shade_sample* out) try {
     ARG_CHECK(ctx && scene && p, "ctx/scene/params is NULL");
     ARG_CHECK(n == 0 || (rays && out), "rays/out is NULL");
     ARG_CHECK(n < (size_t(1) << 32), "too many rays (the Philox key holds a 32-bit ray index)");
@@ -775,18 +787,18 @@ rt_status rt_shade_probe(rt_context* ctx, const rt_scene* scene, const rt_ray* r
         return RT_ERR_CUDA;
     }
     return RT_OK;
-}
+} RT_API_CATCH
 
 rt_status rt_render_accum_device(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, void* accum_dev,
-                                 rt_stats* stats) {
+                                 rt_stats* stats) try {
     ARG_CHECK(ctx && scene && accum_dev, "ctx/scene/accum_dev is NULL");
     rt_status st = check_params(p);
     if (st != RT_OK) return st;
     if ((st = make_current(ctx)) != RT_OK) return st;
     return render_into(ctx, scene, p, static_cast<float4*>(accum_dev), stats);
-}
+} RT_API_CATCH
 
-rt_status rt_render_accum(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, float* out_accum, rt_stats* stats) {
+rt_status rt_render_accum(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, float* out_accum, rt_stats* stats) try {
     ARG_CHECK(ctx && scene && out_accum, "ctx/scene/out_accum is NULL");
     rt_status st = check_params(p);
     if (st != RT_OK) return st;
@@ -803,10 +815,10 @@ rt_status rt_render_accum(rt_context* ctx, const rt_scene* scene, const rt_rende
     CUDA_TRY(cudaEventElapsedTime(&local.ms_d2h, ctx->ev[2], ctx->ev[3]));
     if (stats) *stats = local;
     return RT_OK;
-}
+} RT_API_CATCH
 
 rt_status rt_tonemap_device(rt_context* ctx, const void* accum_dev, int32_t width, int32_t height, void* out_rgb_dev,
-                            void* out_rgb8_dev) {
+                            void* out_rgb8_dev) try {
     ARG_CHECK(ctx && accum_dev, "ctx/accum_dev is NULL");
     ARG_CHECK(width > 0 && height > 0, "width/height must be positive");
     ARG_CHECK(out_rgb_dev || out_rgb8_dev, "no output buffer");
@@ -816,11 +828,11 @@ rt_status rt_tonemap_device(rt_context* ctx, const void* accum_dev, int32_t widt
                         static_cast<uint8_t*>(out_rgb8_dev), ctx->stream);
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
-}
+} RT_API_CATCH
 
 rt_status rt_reduce_tonemap_peers(rt_context* ctx, const void* const* peer_accum_dev, int32_t n_peers, const void* multicast_accum,
                                   int32_t width, int32_t height, int32_t row_begin, int32_t row_end, void* out_rgb_dev,
-                                  void* out_rgb8_dev, void* out_sum_dev) {
+                                  void* out_rgb8_dev, void* out_sum_dev) try {
     ARG_CHECK(ctx != nullptr, "ctx is NULL");
     ARG_CHECK(width > 0 && height > 0, "width/height must be positive");
     ARG_CHECK(row_begin >= 0 && row_begin <= row_end && row_end <= height, "bad row range");
@@ -836,9 +848,9 @@ rt_status rt_reduce_tonemap_peers(rt_context* ctx, const void* const* peer_accum
                                static_cast<float4*>(out_sum_dev), ctx->stream);
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
-}
+} RT_API_CATCH
 
-rt_status rt_render(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, float* out_rgb, rt_stats* stats) {
+rt_status rt_render(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, float* out_rgb, rt_stats* stats) try {
     ARG_CHECK(ctx && scene && out_rgb, "ctx/scene/out_rgb is NULL");
     rt_status st = check_params(p);
     if (st != RT_OK) return st;
@@ -861,7 +873,7 @@ rt_status rt_render(rt_context* ctx, const rt_scene* scene, const rt_render_para
     local.launches += 1;
     if (stats) *stats = local;
     return RT_OK;
-}
+} RT_API_CATCH
 
 size_t rt_jpeg_max_bytes(int32_t width, int32_t height) {
     if (width <= 0 || height <= 0) return 0;
@@ -869,16 +881,16 @@ size_t rt_jpeg_max_bytes(int32_t width, int32_t height) {
 }
 
 rt_status rt_jpeg_encode_device(rt_context* ctx, const void* rgb8_dev, int32_t width, int32_t height, int32_t quality,
-                                uint8_t* out_jpg, size_t cap, size_t* n_bytes, float* ms_device) {
+                                uint8_t* out_jpg, size_t cap, size_t* n_bytes, float* ms_device) try {
     ARG_CHECK(ctx && rgb8_dev && n_bytes, "ctx/rgb8_dev/n_bytes is NULL");
     ARG_CHECK(width > 0 && height > 0 && width < 65536 && height < 65536, "JPEG dimensions must be in [1, 65535]");
     rt_status st = make_current(ctx);
     if (st != RT_OK) return st;
     return jpeg_from_device(ctx, static_cast<const uint8_t*>(rgb8_dev), width, height, quality, out_jpg, cap, n_bytes, ms_device);
-}
+} RT_API_CATCH
 
 rt_status rt_jpeg_encode(rt_context* ctx, const uint8_t* rgb8, int32_t width, int32_t height, int32_t quality, uint8_t* out_jpg,
-                         size_t cap, size_t* n_bytes) {
+                         size_t cap, size_t* n_bytes) try {
     ARG_CHECK(ctx && rgb8 && n_bytes, "ctx/rgb8/n_bytes is NULL");
     ARG_CHECK(width > 0 && height > 0 && width < 65536 && height < 65536, "JPEG dimensions must be in [1, 65535]");
     rt_status st = make_current(ctx);
@@ -887,9 +899,9 @@ rt_status rt_jpeg_encode(rt_context* ctx, const uint8_t* rgb8, int32_t width, in
     if ((st = ensure_rgb8(ctx, npix)) != RT_OK) return st;
     CUDA_TRY(cudaMemcpyAsync(ctx->rgb8, rgb8, npix * 3, cudaMemcpyHostToDevice, ctx->stream));
     return jpeg_from_device(ctx, ctx->rgb8, width, height, quality, out_jpg, cap, n_bytes, nullptr);
-}
+} RT_API_CATCH
 
-rt_status rt_write_jpg(rt_context* ctx, const char* path, int32_t width, int32_t height, const uint8_t* rgb8, int32_t quality) {
+rt_status rt_write_jpg(rt_context* ctx, const char* path, int32_t width, int32_t height, const uint8_t* rgb8, int32_t quality) try {
     ARG_CHECK(path != nullptr, "path is NULL");
     const size_t cap = rt_jpeg_max_bytes(width, height);
     std::vector<uint8_t> buf(cap);
@@ -908,10 +920,10 @@ rt_status rt_write_jpg(rt_context* ctx, const char* path, int32_t width, int32_t
         return RT_ERR_IO;
     }
     return RT_OK;
-}
+} RT_API_CATCH
 
 rt_status rt_render_jpeg(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, int32_t quality, uint8_t* out_jpg,
-                         size_t cap, size_t* n_bytes, rt_stats* stats) {
+                         size_t cap, size_t* n_bytes, rt_stats* stats) try {
     ARG_CHECK(ctx && scene && out_jpg && n_bytes, "ctx/scene/out_jpg/n_bytes is NULL");
     rt_status st = check_params(p);
     if (st != RT_OK) return st;
@@ -934,10 +946,10 @@ rt_status rt_render_jpeg(rt_context* ctx, const rt_scene* scene, const rt_render
     local.launches += 8;
     if (stats) *stats = local;
     return RT_OK;
-}
+} RT_API_CATCH
 
 rt_status rt_render_progressive(rt_context* ctx, const rt_scene* scene, const rt_render_params* p, int32_t passes, float* out_rgb,
-                                rt_progress_fn on_pass, void* user, rt_stats* stats) {
+                                rt_progress_fn on_pass, void* user, rt_stats* stats) try {
     ARG_CHECK(ctx && scene && out_rgb, "ctx/scene/out_rgb is NULL");
     ARG_CHECK(passes >= 1, "passes must be >= 1");
     rt_status st = check_params(p);
@@ -968,7 +980,7 @@ rt_status rt_render_progressive(rt_context* ctx, const rt_scene* scene, const rt
     }
     if (stats) *stats = total;
     return RT_OK;
-}
+} RT_API_CATCH
 
 namespace {
 struct OwnedCoefficients { // rt_jpeg_coefficients that owns its planes; `pub` must stay the first member
@@ -977,7 +989,7 @@ struct OwnedCoefficients { // rt_jpeg_coefficients that owns its planes; `pub` m
 };
 } // namespace
 
-rt_status rt_jpeg_parse(const uint8_t* file, size_t n_bytes, rt_jpeg_coefficients** out) {
+rt_status rt_jpeg_parse(const uint8_t* file, size_t n_bytes, rt_jpeg_coefficients** out) try {
     ARG_CHECK(file && out, "file/out is NULL");
     *out = nullptr;
     OwnedCoefficients* oc = new (std::nothrow) OwnedCoefficients();
@@ -1003,14 +1015,14 @@ rt_status rt_jpeg_parse(const uint8_t* file, size_t n_bytes, rt_jpeg_coefficient
     memcpy(p.dequant, oc->img.dequant, sizeof p.dequant);
     *out = &oc->pub;
     return RT_OK;
-}
+} RT_API_CATCH
 
 void rt_jpeg_coefficients_free(rt_jpeg_coefficients* c) {
     if (c) delete reinterpret_cast<OwnedCoefficients*>(c);
 }
 
 rt_status rt_jpeg_decode(rt_context* ctx, const uint8_t* file, size_t n_bytes, float** out_pixels, int32_t* width, int32_t* height,
-                         int32_t* channels, float* ms_device) {
+                         int32_t* channels, float* ms_device) try {
     ARG_CHECK(ctx && file && out_pixels && width && height && channels, "ctx/file/out pointers are NULL");
     *out_pixels = nullptr;
     rt_status st = make_current(ctx);
@@ -1043,9 +1055,9 @@ rt_status rt_jpeg_decode(rt_context* ctx, const uint8_t* file, size_t n_bytes, f
     *height = img.height;
     *channels = ch;
     return RT_OK;
-}
+} RT_API_CATCH
 
-rt_status rt_image_load(rt_context* ctx, const char* path, float** out_rgb, int32_t* width, int32_t* height) {
+rt_status rt_image_load(rt_context* ctx, const char* path, float** out_rgb, int32_t* width, int32_t* height) try {
     ARG_CHECK(path && out_rgb && width && height, "path/out pointers are NULL");
     *out_rgb = nullptr;
     FILE* f = fopen(path, "rb");
@@ -1081,6 +1093,6 @@ rt_status rt_image_load(rt_context* ctx, const char* path, float** out_rgb, int3
     }
     *out_rgb = rgb;
     return RT_OK;
-}
+} RT_API_CATCH
 
 } // extern "C"

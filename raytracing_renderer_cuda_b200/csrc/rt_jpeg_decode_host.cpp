@@ -7,6 +7,7 @@
 #include "rt_jpeg_decode_host.hpp"
 
 #include <cstring>
+#include <exception>
 
 namespace rtj {
 
@@ -439,6 +440,9 @@ struct Decoder {
         if (c != 3 && c != 1 && c != 4) return fail("bad component count");
         if (c == 4) return fail("4-component (CMYK/YCCK) JPEG is not supported");
         img.n_comp = c;
+        // stb:3223 (stbi__mad3sizes_valid): width * height * components must fit an int — also what keeps a damaged
+        // header from sizing the coefficient arrays below
+        if (uint64_t(img.width) * uint64_t(img.height) * uint64_t(c) > 0x7fffffffull) return fail("too large");
         if (Lf != 8 + 3 * c) return fail("bad SOF len");
         rgb_ids = 0;
         for (int i = 0; i < c; ++i) {
@@ -558,8 +562,13 @@ bool decode_coefficients(const uint8_t* data, size_t n_bytes, CoefficientImage& 
         out.error = "not a JPEG file";
         return false;
     }
-    Decoder d(data, n_bytes, out);
-    return d.run();
+    try { // the coefficient arrays of a (legitimately) huge frame may not fit: an error, never an exception for the C ABI above
+        Decoder d(data, n_bytes, out);
+        return d.run();
+    } catch (const std::exception&) {
+        out.error = "out of memory";
+        return false;
+    }
 }
 
 } // namespace rtj

@@ -72,6 +72,24 @@ def test_truncated_file_does_not_crash(golden):
             pass
 
 
+def test_frame_size_that_overflows_an_int_is_rejected_like_stb(golden):
+    """stb_image.h:3223 rejects width * height * components > INT_MAX ("too large"); the same check keeps a damaged
+    frame header (65535 x 65535 on a 1 x 1 file) from sizing 25 GB of coefficient arrays — that used to end in a
+    std::bad_alloc thrown through the C ABI."""
+    import struct
+
+    data = bytearray(golden["file000"].tobytes())
+    sof = max(data.find(b"\xff\xc0"), data.find(b"\xff\xc2"))
+    assert sof > 0
+    data[sof + 5:sof + 9] = struct.pack(">HH", 65535, 65535)
+    with pytest.raises(capi.RtError) as e:
+        capi.jpeg_parse(bytes(data))
+    assert e.value.status == capi.RT_ERR_INVALID_ARG and "too large" in str(e.value)
+    if oa.REFSTB_SO.exists():
+        with pytest.raises(Exception):
+            oa.ref_stb_load_jpeg(bytes(data))
+
+
 @pytest.mark.skipif(not oa.REFSTB_SO.exists(), reason="oracle/_ref/libref_stb.so is built from /root/reference only")
 def test_pinned_live_against_stb_in_every_mode():
     from PIL import Image
