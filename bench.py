@@ -345,6 +345,10 @@ def run_ours(args) -> None:
         paths_total = float(W) * H * spp * world
         value = paths_total / ms_step / 1e3
         n_step_launches = max(1, launches_step - 2)  # k_wf_step launches (excl. k_wf_init, tonemap)
+        kernel_name = ("k_wf_step_pt" if int(info.n_spheres) >= 4096 else "k_wf_step_warp") if int(info.n_nodes) else "k_wf_step_cta"
+        grain = os.environ.get("RT_WF_GRAIN", "")
+        if grain.startswith("r") and iters == 1:  # experimental single-launch kernel: k_ring_fill + k_ring_commit + k_wf_ring
+            kernel_name, n_step_launches = "k_wf_ring", 1
         fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s at the measured max SM clock
         flop_launch = rays_rank / n_step_launches * FLOP_PER_RAY[args.config]
         dur_launch_s = ms_kernel_span / 1e3 / n_step_launches
@@ -364,11 +368,11 @@ def run_ours(args) -> None:
             "rays_per_path": rays_total / paths_total,
             "config": {"workload": cfg["name"], "scene": cfg["scene"], "width": W, "height": H, "spp_per_gpu": spp,
                        "spp_total": spp * world, "max_depth": 50, "n_spheres": int(info.n_spheres), "bvh_nodes": int(info.n_nodes),
-                       "bvh_mode": int(info.bvh_mode), "pipeline": "wavefront", "parallelism": f"samples x{world}", "collective": collective,
+                       "bvh_mode": int(info.bvh_mode), "pipeline": "wavefront" + (f" (RT_WF_GRAIN={os.environ['RT_WF_GRAIN']})" if os.environ.get("RT_WF_GRAIN") else ""), "parallelism": f"samples x{world}", "collective": collective,
                        "l2": "flushed between timed steps (256 MiB fill, outside the timed spans)",
                        "timing": "sum of per-step CUDA-event spans on the launching stream, max over ranks"},
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": traffic, "ncu": ncu_static, "kernel": ("k_wf_step_pt" if int(info.n_spheres) >= 4096 else "k_wf_step_warp") if int(info.n_nodes) else "k_wf_step_cta", "launches_per_step": n_step_launches,
+                         "traffic": traffic, "ncu": ncu_static, "kernel": kernel_name, "launches_per_step": n_step_launches,
                          "avg_launch_ms": dur_launch_s * 1e3, "flop_per_ray": FLOP_PER_RAY[args.config],
                          "peak_source": f"148 SM x 128 lanes x 2 flop x {peaks['sm_max_mhz']:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peaks['source']})",
                          "note": "no dense contraction and L2-resident state: the bounding roofline is FP32 issue (SURVEY.md 8d), not hbm/tensor",
