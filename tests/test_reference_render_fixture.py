@@ -54,7 +54,7 @@ def test_cuda_frame_reproduces_the_reference_render(earth, pipeline):
     """The reference's frame itself — 1200x600, 100 spp, depth 50 (config C1) — through rt_render, then the writer
     conversion and the fixture's box filter."""
     fix = _fixture()
-    ctx = rt.Context(0)
+    ctx = rt.Context(0)  # (as the module-scoped fixtures of the other GPU tests: released with the object)
     scene = rt.Scene(ctx, rt.SceneDesc.builtin("earth_emitter", earth))
     img, st = scene.render(rt.default_params(width=1200, height=600, spp=100, pipeline=pipeline))
     assert st.paths == 1200 * 600 * 100
@@ -63,4 +63,3 @@ def test_cuda_frame_reproduces_the_reference_render(earth, pipeline):
     # and the library's own writer conversion is the one restated above
     assert np.array_equal(capi.quantize_rgb8(img).astype(np.float64) / 255.0, _written_bytes(img))
     scene.close()
-    ctx.close()
