@@ -29,8 +29,8 @@ def frame(scene, grain, **kw):
 
 
 cases = [("earth_emitter", dict(width=96, height=48, spp=8)), ("earth_emitter", dict(width=400, height=200, spp=16)),
-         ("perlin_motion", dict(width=320, height=160, spp=16)), ("book1_final", dict(width=320, height=180, spp=16)),
-         ("earth_emitter", dict(width=1200, height=600, spp=100)), ("book1_final", dict(width=1920, height=1080, spp=64))]
+         ("earth_emitter", dict(width=1200, height=600, spp=100)), ("perlin_motion", dict(width=320, height=160, spp=16)),
+         ("book1_final", dict(width=320, height=180, spp=16)), ("book1_final", dict(width=1920, height=1080, spp=64))]
 for name, kw in cases:
     sc = rt.Scene(ctx, rt.SceneDesc.builtin(name, load_earth() if name == "earth_emitter" else None))
     ref, sr, _ = frame(sc, None, **kw)
