@@ -43,7 +43,11 @@ RT_RING_FN uint32_t load_entry(const uint32_t* p) {
 }
 // release store: the thread's earlier writes (its path record) are visible before the entry is (MEMBAR.ALL.GPU + ST in
 // SASS; fence.acq_rel / __threadfence() would also invalidate the SM's L1 — CCTL.IVALL — on every push)
+#ifndef WF_RING_RELAXED_PUBLISH
 RT_RING_FN void publish(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+#else // A/B ONLY (what does the fence cost?): without the release the consumer may read a record that is not there yet
+RT_RING_FN void publish(uint32_t* p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+#endif
 RT_RING_FN unsigned long long add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 RT_RING_FN void pause(unsigned ns) { __nanosleep(ns); }
 #else

@@ -776,11 +776,11 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
     if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
 }
 
-// Work granularity, variant 4 — EXPERIMENTAL, selected only by RT_WF_GRAIN=ring, never by default, and not yet run on
-// a GPU (written after the round's GPU budget was spent; tools/ring_probe.py is the check to run first: same frame
-// as the CTA-chunk kernel, then the A/B timing).  ONE persistent launch per frame and no iteration barrier: the ~60
-// thin tail iterations of a frame and the bubble between two dependent launches become the
-// latency of the longest path.
+// Work granularity, variant 4 — EXPERIMENTAL, selected only by RT_WF_GRAIN=ring, never by default.  ONE persistent
+// launch per frame and no iteration barrier: the ~60 thin tail iterations of a frame and the bubble between two
+// dependent launches become the latency of the longest path.  Measured (profiles/r01_ring.md):
+// identical frames; 24-39 % faster than the per-iteration kernels on frames of <= 1.3 M paths, 19-21 % slower on C1/C2
+// (the bulk costs more per entry: three atomics per push, L2-only record accesses, a release fence per entry = 5 %).
 //
 // Per shading class a ring of slot indices in the queue memory (capacity `cap`, a power of two >= 2 x slots in use)
 // and three 64-bit counters that live for the life of the WavefrontState, each in its own 128-byte line:
@@ -810,6 +810,11 @@ using ring::RingClaim;
 using ring::RC_RESERVE;
 using ring::RC_CREDITS;
 using ring::RC_HEAD;
+#ifdef WF_RING_ACC_STREAM // A/B ONLY (what do the L2-only accesses cost?): .cs loads may hit a stale L1 line in the tail
+#define WF_RING_ACC WF_ACC_STREAM
+#else
+#define WF_RING_ACC WF_ACC_L2
+#endif
 using RingOps = ring::Protocol<NQ, Q_NEW>; // the claim/termination protocol: rt_ring.hpp (also compiled for the host by tests/ring_sim.cpp)
 
 template <bool USE_BVH, bool NEE>
@@ -820,6 +825,9 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     __shared__ uint32_t s_count[2][NQ]; // double-buffered by chunk parity, as in k_wf_step_cta
     __shared__ unsigned long long s_base[2][NQ];
     __shared__ RingClaim s_claim;
+#ifdef WF_RING_EARLY_CLAIM
+    __shared__ RingClaim s_early[2]; // the next chunk, claimed at the TOP of a trip (hidden behind the shading), by chunk parity
+#endif
     constexpr uint32_t kClaimer = WF_CTA_THREADS >= 64 ? 32u : 0u; // lane 0 of warp 1: warp 0 does the push atomics meanwhile
 
     const PerlinTab pt{smem, threadIdx.x & 31u};
@@ -855,8 +863,15 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
             while ((v >> 25) != want) v = ring::load_entry(e);
             slot = v & 0xffffffu;
         }
+#ifdef WF_RING_EARLY_CLAIM
+        if (threadIdx.x == kClaimer) { // this CTA counts as busy; a failed attempt is repeated between the barriers below
+            RingClaim c;
+            RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c);
+            s_early[cpar] = c;
+        }
+#endif
 
-        const int out_q = wf_process_entry<USE_BVH, NEE, WF_ACC_L2>(sc, rp, wb, pt, kind, valid, slot, path_base + threadIdx.x, npix,
+        const int out_q = wf_process_entry<USE_BVH, NEE, WF_RING_ACC>(sc, rp, wb, pt, kind, valid, slot, path_base + threadIdx.x, npix,
                                                                     npaths, accum, nrays);
 
         // ---- push: warp ballot -> shared counters -> one reserve + one credit atomic per class ----
@@ -884,7 +899,11 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
         }
         if (threadIdx.x == kClaimer) { // the next chunk, while this CTA still counts as busy
             RingClaim c;
-            RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c);
+#ifdef WF_RING_EARLY_CLAIM
+            c = s_early[cpar];
+            if (c.kind < 0)
+#endif
+                RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c);
             s_claim = c;
         }
         __syncthreads();

@@ -1,6 +1,7 @@
 #!/bin/bash
-# First GPU job of the round after round 1 (run through gpurun, ~6 GPU-minutes): does the experimental barrier-free
-# kernel (RT_WF_GRAIN=ring, never run on a GPU so far) render the default kernels' frame, and what does it cost?
+# GPU job for the experimental barrier-free kernel (RT_WF_GRAIN=ring; run through gpurun, ~6 GPU-minutes): the probe
+# (same frame as the default kernels, A/B frame times — passed in round 1, profiles/r01_ring.md), then the GPU parity
+# tests under it, the C1 bench with and without it, and the ncu capture that round 1 had no budget for.
 # Every step has its own timeout: a protocol bug would show as a hang, which must not cost a gpurun strike.
 set -x
 cd "$(dirname "$0")/.."
