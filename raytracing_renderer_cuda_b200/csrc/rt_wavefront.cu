@@ -83,6 +83,8 @@ struct WavefrontState {
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
     unsigned long long* ring_ctl = nullptr; // counters of the ring kernel (RT_WF_GRAIN=ring), allocated on first use
+    uint32_t* tail_ring = nullptr;          // RT_WF_TAIL: a small ring of its own ([NQ][1 << kTailCapLog2]) + its counters
+    unsigned long long* tail_ctl = nullptr;
 };
 
 // Streaming accesses to data that is read once and written once per iteration (path records, queue entries): L1
@@ -950,6 +952,41 @@ __global__ void k_ring_commit(const __grid_constant__ WfRing rg, uint32_t n_slot
     }
 }
 
+// RT_WF_TAIL (experimental, off by default, NOT yet run on a GPU): the per-iteration kernels render the bulk of a frame,
+// and once every path has started and few are alive the queues of the current iteration are moved into a small ring
+// and ONE k_wf_ring launch finishes the frame — the thin tail iterations (0.7 of C1's 8.5 ms) are where the
+// barrier-free form wins (frames of <= 1.3 M paths: -24...-39 %, profiles/r01_ring.md), the bulk is where it loses.
+// k_ring_import: entry i of every shading queue of iteration `it` -> ring position reserve + i (Q_NEW is not
+// imported: no path is left to start).  k_ring_commit_tail: the counters; next_path = npaths makes the ring kernel
+// ignore Q_NEW.  Each runs alone on the stream.
+__global__ void k_ring_import(const __grid_constant__ WfBuffers wb, const __grid_constant__ WfRing rg, int it) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t* cnt = wb.counts + (it % 3) * NQ;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        if (q == Q_NEW) continue;
+        if (i < cnt[q]) {
+            const unsigned long long p = *ring::ctl(rg, q, RC_RESERVE) + i;
+            *ring::entry(rg, q, p) = wf_queue(wb, it & 1, q)[i] | (ring::tag(rg, p) << 25);
+        }
+    }
+}
+__global__ void k_ring_commit_tail(const __grid_constant__ WfBuffers wb, const __grid_constant__ WfRing rg, int it,
+                                   unsigned long long npaths) {
+    const int q = int(threadIdx.x);
+    if (q < NQ) {
+        const unsigned long long r = *ring::ctl(rg, q, RC_RESERVE);
+        const unsigned long long add = q == Q_NEW ? 0u : wb.counts[(it % 3) * NQ + q];
+        *ring::ctl(rg, q, RC_HEAD) = r;
+        *ring::ctl(rg, q, RC_RESERVE) = r + add;
+        *ring::ctl(rg, q, RC_CREDITS) = add;
+    }
+    if (q == 0) {
+        *ring::word(rg, RingOps::RC_NEXT_PATH) = npaths;
+        *ring::word(rg, RingOps::RC_BUSY) = 0ull;
+    }
+}
+
 // fills Q_NEW of iteration 0 with every slot and resets the path counter
 __global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -987,6 +1024,8 @@ void wavefront_destroy(WavefrontState* ws) {
     if (ws->b.tickets) cudaFree(ws->b.tickets);
     if (ws->b.next_path) cudaFree(ws->b.next_path);
     if (ws->ring_ctl) cudaFree(ws->ring_ctl);
+    if (ws->tail_ring) cudaFree(ws->tail_ring);
+    if (ws->tail_ctl) cudaFree(ws->tail_ctl);
     for (auto& e : ws->poll_ev)
         if (e) cudaEventDestroy(e);
     if (ws->h_status) cudaFreeHost(ws->h_status);
@@ -1034,6 +1073,46 @@ static bool wavefront_render_ring(WavefrontState* ws, const DScene& sc, const DR
     }
     *launches = 3;
     *iterations = 1;
+    return true;
+}
+
+// RT_WF_TAIL: finishes a frame whose paths have all started with one ring launch (see k_ring_import).  `live_max` bounds
+// the live paths (they only get fewer once no path is left to start).  False: not possible, keep iterating.
+constexpr uint32_t kTailCapLog2 = 21; // 2 Mi entries per class: room for 1 Mi live paths (half a lap)
+static bool wavefront_finish_with_ring(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, bool nee, size_t smem,
+                                       uint32_t it, uint32_t live_max, unsigned long long npaths, float4* accum,
+                                       unsigned long long* ray_counter, int sm_count, cudaStream_t st) {
+    const WfBuffers& wb = ws->b;
+    if (wb.pool > (1u << 24) || live_max == 0u || live_max > (1u << (kTailCapLog2 - 1u))) return false;
+    if (!ws->tail_ring) {
+        const size_t ring_bytes = (size_t(NQ) << kTailCapLog2) * sizeof(uint32_t);
+        const size_t ctl_bytes = size_t(RingOps::RC_COUNT) * 16u * sizeof(unsigned long long);
+        if (cudaMalloc(&ws->tail_ring, ring_bytes) != cudaSuccess || cudaMalloc(&ws->tail_ctl, ctl_bytes) != cudaSuccess) {
+            if (ws->tail_ring) cudaFree(ws->tail_ring);
+            ws->tail_ring = nullptr;
+            ws->tail_ctl = nullptr;
+            cudaGetLastError();
+            return false;
+        }
+        cudaMemsetAsync(ws->tail_ring, 0, ring_bytes, st);
+        cudaMemsetAsync(ws->tail_ctl, 0, ctl_bytes, st);
+    }
+    WfRing rg{};
+    rg.ring = ws->tail_ring;
+    rg.ctl = ws->tail_ctl;
+    rg.cap_log2 = kTailCapLog2;
+    k_ring_import<<<(live_max + 255u) / 256u, 256, 0, st>>>(wb, rg, int(it));
+    k_ring_commit_tail<<<1, 32, 0, st>>>(wb, rg, int(it), npaths);
+    const unsigned cap = unsigned(sm_count) * WF_CTA_MINBLOCKS;
+    const unsigned need = (live_max + WF_CTA_THREADS - 1) / WF_CTA_THREADS;
+    const unsigned grid = need < cap ? need : cap;
+    if (nee) {
+        if (use_bvh) k_wf_ring<true, true><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
+        else k_wf_ring<false, true><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
+    } else {
+        if (use_bvh) k_wf_ring<true, false><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
+        else k_wf_ring<false, false><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
+    }
     return true;
 }
 
@@ -1171,6 +1250,12 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         cudaEventRecord(ws->poll_ev[par], st);
         polled[par].it_after = it;
     };
+    // RT_WF_TAIL=<live paths>: hand the tail of the frame to one ring launch (experimental, off unless set)
+    uint32_t tail_live = 0;
+    if (const char* e = getenv("RT_WF_TAIL")) {
+        const long v = atol(e);
+        if (v > 0) tail_live = uint32_t(v < (1l << (kTailCapLog2 - 1)) ? v : (1l << (kTailCapLog2 - 1)));
+    }
     const uint32_t generations = uint32_t((npaths + slots - 1) / slots);
     const uint32_t max_iters = 4u * (uint32_t(rp.max_depth) + 2u) + 64u * generations;
     enqueue(2u * generations + 4u); // a path lives ~2 iterations: enough to start most of the frame
@@ -1186,6 +1271,11 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
             if (k != Q_NEW) live += c[k];
         const unsigned long long started = ws->h_status[par];
         if (live == 0 && (started >= npaths || c[Q_NEW] == 0)) break;
+        if (tail_live && started >= npaths && live <= tail_live &&
+            wavefront_finish_with_ring(ws, sc, rp, use_bvh, nee, smem, it, uint32_t(live), npaths, accum, ray_counter, sm_count, st)) {
+            *launches += 3; // k_ring_import, k_ring_commit_tail, k_wf_ring
+            break;
+        }
         if (it >= max_iters) break; // safety net; cannot trigger for max_depth-bounded paths
         par ^= 1;
     }

@@ -42,6 +42,17 @@ for name, kw in cases:
               "max px diff", float(d.max()), flush=True)
         if not ok:
             sys.exit(1)
+    # RT_WF_TAIL (never run on a GPU when this was written): per-iteration kernels for the bulk, one ring launch for the tail
+    for tail in ("65536", "1000000"):
+        os.environ["RT_WF_TAIL"] = tail
+        got, st, _ = frame(sc, None, **kw)
+        os.environ.pop("RT_WF_TAIL")
+        d = np.abs(got[..., :3] - ref[..., :3]).max(axis=2) / kw["spp"]
+        ok = np.array_equal(got[..., 3], ref[..., 3]) and st.rays == sr.rays and float(d.max()) < 1e-4
+        print(name, kw, "RT_WF_TAIL", tail, "OK" if ok else "MISMATCH", "launches", st.launches, "iterations", st.iterations,
+              "(default:", sr.launches, sr.iterations, ") ms", round(st.ms_total, 3), "default ms", round(sr.ms_total, 3), flush=True)
+        if not ok:
+            sys.exit(1)
     t = {}
     for grain in (None, "ring", None, "ring"):
         ms = []
@@ -49,6 +60,13 @@ for name, kw in cases:
             _, st, _ = frame(sc, grain, **kw)
             ms.append(st.ms_total)
         t.setdefault(grain or "default", []).append(float(np.median(ms)))
+    os.environ["RT_WF_TAIL"] = "262144"
+    ms = []
+    for _ in range(5):
+        _, st, _ = frame(sc, None, **kw)
+        ms.append(st.ms_total)
+    os.environ.pop("RT_WF_TAIL")
+    t["default + RT_WF_TAIL=262144"] = [float(np.median(ms))]
     print(name, kw, "ms per frame (median of 5, twice):", t, flush=True)
     sc.close()
 os.environ.pop("RT_WF_GRAIN", None)
