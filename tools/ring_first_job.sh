@@ -7,6 +7,7 @@ set -x
 cd "$(dirname "$0")/.."
 timeout 300 python tools/ring_probe.py > gpurun_out/ring_probe.log 2>&1; echo "ring_probe rc=$?"; tail -n 12 gpurun_out/ring_probe.log
 if grep -q "ring probe ok" gpurun_out/ring_probe.log; then
+    RT_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental_ring.py -m gpu -x -q > gpurun_out/pytest_ring_modes.log 2>&1; tail -n 3 gpurun_out/pytest_ring_modes.log
     RT_WF_GRAIN=ring timeout 300 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/pytest_ring.log 2>&1; tail -n 3 gpurun_out/pytest_ring.log
     RT_WF_GRAIN=ring timeout 120 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/bench_c1_ring.json 2> gpurun_out/bench_c1_ring.err
     timeout 120 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/bench_c1_default.json 2> gpurun_out/bench_c1_default.err
