@@ -106,19 +106,27 @@ struct Protocol {
         out.path = q == QNEW ? add(word(rg, RC_NEXT_PATH), (unsigned long long)n) : 0ull;
         return true;
     }
+    // How many entries a claim asks for when a class holds c credits: a chunk (or what is there), and `batch` chunks at
+    // once while the class holds plenty (>= 64 batches) — fewer claims on the counters of the fullest class, which every
+    // CTA picks at the same time; never in the tail, where a batch would serialise entries other CTAs could take.
+    static RT_RING_FN uint32_t claim_size(long long c, uint32_t chunk, uint32_t batch) {
+        if (batch > 1u && c >= 64ll * (long long)(batch * chunk)) return batch * chunk;
+        return uint32_t(c < (long long)chunk ? c : (long long)chunk);
+    }
     // the caller holds `busy`: one or two attempts, no waiting
-    static RT_RING_FN void claim_try(const Ring& rg, unsigned long long npaths, uint32_t chunk, RingClaim& out) {
+    static RT_RING_FN void claim_try(const Ring& rg, unsigned long long npaths, uint32_t chunk, RingClaim& out, uint32_t batch = 1u) {
         out.kind = -1;
         for (int attempt = 0; attempt < 2; ++attempt) {
             long long c;
             const int q = scan(rg, npaths, c);
             if (q < 0) return;
-            if (take(rg, q, uint32_t(c < (long long)chunk ? c : (long long)chunk), out)) return;
+            if (take(rg, q, claim_size(c, chunk, batch), out)) return;
         }
     }
     // waits for work or for the end of the frame; `holding`: the caller still holds `busy` for the chunk it just finished.
     // On success the caller holds `busy` (one count per CTA) until it calls claim_wait(holding = true) again.
-    static RT_RING_FN void claim_wait(const Ring& rg, unsigned long long npaths, uint32_t chunk, bool holding, RingClaim& out) {
+    static RT_RING_FN void claim_wait(const Ring& rg, unsigned long long npaths, uint32_t chunk, bool holding, RingClaim& out,
+                                      uint32_t batch = 1u) {
         unsigned long long* busy = word(rg, RC_BUSY);
         if (holding) add(busy, ~0ull);
         unsigned backoff = 64u;
@@ -129,7 +137,7 @@ struct Protocol {
             const int q = scan(rg, npaths, c);
             if (q >= 0) {
                 add(busy, 1ull); // before the credits move: a scanner sees either the credits or a busy CTA
-                if (take(rg, q, uint32_t(c < (long long)chunk ? c : (long long)chunk), out)) return;
+                if (take(rg, q, claim_size(c, chunk, batch), out)) return;
                 add(busy, ~0ull);
             } else if (b0 == 0ull && peek(busy) == 0ull) {
                 return; // nothing queued, nobody who could queue anything

@@ -817,6 +817,9 @@ using ring::RC_HEAD;
 #else
 #define WF_RING_ACC WF_ACC_L2
 #endif
+#ifndef WF_RING_BATCH
+#define WF_RING_BATCH 1u // chunks per claim while a class holds plenty (A/B: 4 — untested hypothesis: the fullest class's counters are hot)
+#endif
 using RingOps = ring::Protocol<NQ, Q_NEW>; // the claim/termination protocol: rt_ring.hpp (also compiled for the host by tests/ring_sim.cpp)
 
 template <bool USE_BVH, bool NEE>
@@ -839,7 +842,7 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
 
     if (threadIdx.x == kClaimer) {
         RingClaim c;
-        RingOps::claim_wait(rg, npaths, WF_CTA_THREADS, false, c);
+        RingOps::claim_wait(rg, npaths, WF_CTA_THREADS, false, c, WF_RING_BATCH);
         s_claim = c;
     }
     if (threadIdx.x < 2 * NQ) (&s_count[0][0])[threadIdx.x] = 0u;
@@ -853,7 +856,7 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     for (;;) {
         const int kind = s_claim.kind; // rewritten by the claimer only after the first barrier of this trip
         if (kind < 0) break;
-        const uint32_t n = s_claim.n;
+        const uint32_t n = s_claim.n < WF_CTA_THREADS ? s_claim.n : WF_CTA_THREADS; // (a batch claim is worked off a chunk per trip)
         const unsigned long long pos = s_claim.pos, path_base = s_claim.path;
         const bool valid = threadIdx.x < n;
         uint32_t slot = 0u;
@@ -868,7 +871,8 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
 #ifdef WF_RING_EARLY_CLAIM
         if (threadIdx.x == kClaimer) { // this CTA counts as busy; a failed attempt is repeated between the barriers below
             RingClaim c;
-            RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c);
+            c.kind = -1;
+            if (!(WF_RING_BATCH > 1u && s_claim.n > WF_CTA_THREADS)) RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c, WF_RING_BATCH);
             s_early[cpar] = c;
         }
 #endif
@@ -901,11 +905,18 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
         }
         if (threadIdx.x == kClaimer) { // the next chunk, while this CTA still counts as busy
             RingClaim c;
+            if (WF_RING_BATCH > 1u && s_claim.n > WF_CTA_THREADS) { // the rest of a batch claim
+                c = s_claim;
+                c.n -= WF_CTA_THREADS;
+                c.pos += WF_CTA_THREADS;
+                if (c.kind == Q_NEW) c.path += WF_CTA_THREADS;
+            } else {
 #ifdef WF_RING_EARLY_CLAIM
-            c = s_early[cpar];
-            if (c.kind < 0)
+                c = s_early[cpar];
+                if (c.kind < 0)
 #endif
-                RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c);
+                    RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c, WF_RING_BATCH);
+            }
             s_claim = c;
         }
         __syncthreads();
@@ -918,7 +929,7 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
             __syncthreads();    // everybody has looked at s_claim
             if (threadIdx.x == kClaimer) {
                 RingClaim c;
-                RingOps::claim_wait(rg, npaths, WF_CTA_THREADS, true, c);
+                RingOps::claim_wait(rg, npaths, WF_CTA_THREADS, true, c, WF_RING_BATCH);
                 s_claim = c;
             }
             __syncthreads();

@@ -12,7 +12,7 @@
 // trips of every slot; NOT true for preempted host threads).  So: small rings, whose lap tags wrap many times, are run
 // with ONE thread; many threads get a ring so large that a lap outlasts any preemption.
 //
-//   ring_sim <threads> <slots> <cap_log2> <chunk> <paths per frame> <frames> <seed>   -> prints "ok ..." / exits non-zero
+//   ring_sim <threads> <slots> <cap_log2> <chunk> <paths per frame> <frames> <seed> [batch]   -> prints "ok ..." / exits non-zero
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -57,7 +57,7 @@ struct Sim {
     std::vector<std::atomic<int>> started, ended;
     std::atomic<unsigned long long> processed{0};
     std::atomic<int> failed{0};
-    uint32_t chunk = 8;
+    uint32_t chunk = 8, batch = 1; // batch: chunks per claim while a class holds plenty (WF_RING_BATCH)
     unsigned long long npaths = 0;
     uint64_t seed = 1;
 
@@ -82,12 +82,13 @@ struct Sim {
     // one CTA (k_wf_ring): `chunk` lanes are played one after the other
     void cta() {
         RingClaim cl;
-        Ops::claim_wait(rg, npaths, chunk, false, cl);
+        Ops::claim_wait(rg, npaths, chunk, false, cl, batch);
         std::vector<uint32_t> slot(chunk);
         std::vector<int> out(chunk);
         while (cl.kind >= 0 && !failed.load(std::memory_order_relaxed)) {
             uint32_t count[NQ] = {0};
-            for (uint32_t i = 0; i < cl.n; ++i) { // every lane polls its position right after the claim, as in the kernel
+            const uint32_t n_here = cl.n < chunk ? cl.n : chunk; // a batch claim is worked off a chunk per trip
+            for (uint32_t i = 0; i < n_here; ++i) { // every lane polls its position right after the claim, as in the kernel
                 const unsigned long long p = cl.pos + i;
                 const uint32_t want = rtd::ring::tag(rg, p);
                 const uint32_t* e = rtd::ring::entry(rg, cl.kind, p);
@@ -99,7 +100,7 @@ struct Sim {
                 }
                 slot[i] = v & 0xffffffu;
             }
-            for (uint32_t i = 0; i < cl.n; ++i) {
+            for (uint32_t i = 0; i < n_here; ++i) {
                 const uint32_t s = slot[i];
                 out[i] = -1;
                 if (s >= rec.size()) {
@@ -142,15 +143,22 @@ struct Sim {
                 }
             }
             RingClaim next;
-            Ops::claim_try(rg, npaths, chunk, next);
-            for (uint32_t i = 0; i < cl.n; ++i) {
+            if (batch > 1 && cl.n > chunk) { // the rest of a batch claim
+                next = cl;
+                next.n -= chunk;
+                next.pos += chunk;
+                if (cl.kind == QNEW) next.path += chunk;
+            } else {
+                Ops::claim_try(rg, npaths, chunk, next, batch);
+            }
+            for (uint32_t i = 0; i < n_here; ++i) {
                 if (out[i] < 0) continue;
                 const unsigned long long p = base[out[i]]++;
                 held[slot[i]].store(0);
                 rtd::ring::publish(rtd::ring::entry(rg, out[i], p), slot[i] | (rtd::ring::tag(rg, p) << 25));
             }
             cl = next;
-            if (cl.kind < 0) Ops::claim_wait(rg, npaths, chunk, true, cl);
+            if (cl.kind < 0) Ops::claim_wait(rg, npaths, chunk, true, cl, batch);
         }
     }
 };
@@ -169,6 +177,7 @@ int main(int argc, char** argv) {
     sim.npaths = strtoull(argv[5], nullptr, 10);
     const int frames = atoi(argv[6]);
     const uint64_t seed0 = strtoull(argv[7], nullptr, 10);
+    if (argc > 8) sim.batch = uint32_t(atoi(argv[8]));
     if (slots * 2u > (1u << cap_log2)) {
         fprintf(stderr, "ring_sim: the ring must hold two laps of the slots in use\n");
         return 64;
@@ -232,7 +241,7 @@ int main(int argc, char** argv) {
     done.store(true);
     watchdog.join();
     if (sim.failed.load()) return 1;
-    printf("ok threads=%d slots=%u cap=2^%u chunk=%u paths=%llu frames=%d entries=%llu laps=%llu\n", threads, slots, cap_log2, sim.chunk,
-           sim.npaths, frames, total, laps_max);
+    printf("ok threads=%d slots=%u cap=2^%u chunk=%u batch=%u paths=%llu frames=%d entries=%llu laps=%llu\n", threads, slots, cap_log2,
+           sim.chunk, sim.batch, sim.npaths, frames, total, laps_max);
     return 0;
 }

@@ -51,6 +51,17 @@ def test_concurrent_consumers(ring_sim, cfg):
     _run(ring_sim, threads, *cfg[1:])
 
 
+@pytest.mark.parametrize("cfg", [
+    (8, 65536, 20, 4, 400000, 2, 7, 4),  # batch claims (WF_RING_BATCH): 4 chunks at once while a class holds >= 64 batches
+    (1, 8192, 14, 2, 100000, 3, 3, 4),   # ... single consumer, ring laps
+    (6, 16384, 20, 1, 200000, 2, 9, 8),
+])
+def test_batch_claims(ring_sim, cfg):
+    threads = min(cfg[0], max(1, os.cpu_count() or 2))
+    got = _run(ring_sim, threads, *cfg[1:])
+    assert got["batch"] == str(cfg[7])
+
+
 def test_rejects_ring_smaller_than_two_laps(ring_sim):
     out = subprocess.run([ring_sim, "1", "64", "6", "8", "100", "1", "1"], capture_output=True, text=True)
     assert out.returncode == 64

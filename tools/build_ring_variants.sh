@@ -1,7 +1,8 @@
 #!/bin/bash
-# Builds gpurun_variants/librt_ring_{e,r,s,all}.so for tools/ring_ab.py: only rt_wavefront.cu differs, the other objects
+# Builds gpurun_variants/librt_ring_{e,r,s,b4,all}.so for tools/ring_ab.py: only rt_wavefront.cu differs, the other objects
 # come from build/ (run `make lib` first).  Flags: WF_RING_EARLY_CLAIM, WF_RING_RELAXED_PUBLISH (unsafe, A/B only),
-# WF_RING_ACC_STREAM (unsafe, A/B only) — see profiles/r01_ring.md.
+# WF_RING_ACC_STREAM (unsafe, A/B only) — see profiles/r01_ring.md; WF_RING_BATCH=4 (batch claims: untested hypothesis
+# that the counters of the fullest class are the bulk's bottleneck).
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_variants
@@ -17,6 +18,7 @@ build_v() {
 build_v ring_e -DWF_RING_EARLY_CLAIM &
 build_v ring_r -DWF_RING_RELAXED_PUBLISH &
 build_v ring_s -DWF_RING_ACC_STREAM &
+build_v ring_b4 -DWF_RING_BATCH=4u &
 build_v ring_all -DWF_RING_EARLY_CLAIM -DWF_RING_RELAXED_PUBLISH -DWF_RING_ACC_STREAM &
 wait
 ls -la gpurun_variants/

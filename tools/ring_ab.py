@@ -1,5 +1,5 @@
 """A/B of k_wf_ring build variants on C1 (tools/ring_first_job.sh / by hand): one process per library, RT_WF_GRAIN=ring,
-1 warm-up + 5 frames, median.  `python tools/ring_ab.py ring_all ring_e ring_r ring_s default`"""
+1 warm-up + 5 frames, median.  `python tools/ring_ab.py ring_b4 ring_e ring_r ring_s ring_all default`"""
 import os, subprocess, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
