@@ -206,7 +206,18 @@ typedef struct rt_hit {
     uint32_t id;  /* rt_sphere.id of the closest object, RT_INVALID_ID on miss */
     float p[3];
     float n[3];   /* outward normal (sphere.h:123) */
-    float u, v;   /* get_sphere_uv (sphere.h:61-83); computed for every sphere kind */
+    float u, v;   /* get_sphere_uv (sphere.h:61-83), computed for every sphere kind.
+                   * DELIBERATE DEVIATION from the reference: moving_sphere::hit (sphere.h:157-190) never writes
+                   * u and v, so the reference shades a moving sphere with whatever the shared temp_rec of its
+                   * traversal loop last held (hitable_list.h:69-76, bvh.h:130-150) — the (u, v) of the last
+                   * static sphere whose hit() succeeded on that ray in ITS traversal order, or uninitialised
+                   * stack memory when there was none.  That value depends on the reference's BVH topology
+                   * (random split axes, bvh.h:84-92) and, in the second case, on nothing at all, so it cannot be
+                   * reproduced by another acceleration structure; this library computes the moving sphere's own
+                   * (u, v) at the ray's time.  Only an IMAGE texture on a MOVING sphere can tell the difference
+                   * (none of the reference's scenes has one); the oracle (oracle/rt_oracle.cpp) restates the
+                   * reference's list-order behaviour and the parity tests mask moving spheres out of the (u, v)
+                   * comparison (tests/test_gpu_parity.py). */
 } rt_hit;
 
 /* One integrator step at the closest hit of a caller-supplied ray (second parity hook): the terms of
@@ -251,7 +262,9 @@ void rt_scene_destroy(rt_scene* scene); /* replaces free_scene<<<1,1>>> (main.cu
 rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info);
 
 /* Parity hook: closest hit of scene.hit(r, tmin, FLT_MAX) (hitable_list.h:60-79)
- * for n caller-supplied rays. use_bvh=0 forces the brute-force list path. */
+ * for n caller-supplied rays.  use_bvh = 0 forces the brute-force list path, 1 walks the binary BVH
+ * (bvh_node::dfs, bvh.h:121-155), 2 the 4-wide form of the same tree that the large-scene render kernel
+ * traverses (RT_ERR_INVALID_ARG when the scene has none: it is built from 4096 primitives on). */
 rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n,
                            float tmin, int use_bvh, rt_hit* hits);
 

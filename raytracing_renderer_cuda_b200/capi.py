@@ -336,7 +336,7 @@ class Scene:
         _check(self.lib, self.lib.rt_scene_get_info(self._h, C.byref(i)))
         return i
 
-    def trace_primary(self, rays: np.ndarray, tmin: float = 1e-5, use_bvh: bool = True) -> np.ndarray:
+    def trace_primary(self, rays: np.ndarray, tmin: float = 1e-5, use_bvh: bool | int = True) -> np.ndarray:
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
         _check(self.lib, self.lib.rt_trace_primary(self.ctx._h, self._h, rays.ctypes.data, rays.shape[0], tmin,

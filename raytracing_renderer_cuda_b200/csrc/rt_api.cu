@@ -74,7 +74,8 @@ struct rt_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
-    int sm_count = 148;
+    int sm_count = 0;             // multiProcessorCount of the device (launch sizing)
+    cudaMemPool_t pool = nullptr; // scene allocations (stream-ordered, private to the context)
     unsigned long long* d_ray_counter = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float4* accum = nullptr; // scratch for rt_render / rt_render_accum
@@ -115,7 +116,7 @@ rt_status dev_alloc(rt_scene* s, T** out, size_t count) {
     *out = nullptr;
     if (count == 0) return RT_OK;
     void* p = nullptr;
-    CUDA_TRY(cudaMallocAsync(&p, count * sizeof(T), s->ctx->stream)); // stream-ordered pool: no map/unmap per scene
+    CUDA_TRY(cudaMallocFromPoolAsync(&p, count * sizeof(T), s->ctx->pool, s->ctx->stream)); // stream-ordered pool: no map/unmap per scene
     s->allocs.push_back(p);
     s->info.device_bytes += count * sizeof(T);
     *out = static_cast<T*>(p);
@@ -189,12 +190,14 @@ rt_status check_params(const rt_render_params* p) {
     ARG_CHECK(p->max_depth >= 0 && p->max_depth < (1 << 23), "max_depth out of range");
     ARG_CHECK(p->pipeline <= RT_PIPE_MEGAKERNEL, "bad pipeline");
     ARG_CHECK((p->flags & ~RT_RENDER_EMITTER_SAMPLING) == 0u, "unknown render flags");
-    ARG_CHECK(uint64_t(p->width) * uint64_t(p->height) < (1ull << 32), "frame has more than 2^32 pixels");
+    ARG_CHECK(uint64_t(p->width) * uint64_t(p->height) < (1ull << 31), "frame has more than 2^31 pixels");
     return RT_OK;
 }
 
 rtd::DRenderParams to_device_params(const rt_render_params& p) {
     rtd::DRenderParams d;
+    d.div_width = rtd::make_fastdiv(uint32_t(p.width));
+    d.div_npix = rtd::make_fastdiv(uint32_t(uint64_t(p.width) * uint64_t(p.height))); // < 2^32: check_params
     d.width = p.width;
     d.height = p.height;
     d.spp = p.spp;
@@ -308,8 +311,12 @@ rt_status render_into(rt_context* ctx, const rt_scene* scene, const rt_render_pa
                 return RT_ERR_OOM;
             }
         }
-        rtd::wavefront_render(ctx->wf, scene->d, rp, use_bvh, accum, ctx->d_ray_counter, ctx->sm_count, ctx->stream,
-                              &launches, &iterations);
+        if (!rtd::wavefront_render(ctx->wf, scene->d, rp, use_bvh, accum, ctx->d_ray_counter, ctx->sm_count, ctx->stream, &launches,
+                                   &iterations)) {
+            const cudaError_t e = cudaGetLastError();
+            set_error("wavefront_render: frame unfinished after %u iterations (%s)", iterations, cudaGetErrorString(e));
+            return RT_ERR_CUDA;
+        }
     }
     CUDA_TRY(cudaGetLastError());
     if (stats) {
@@ -374,17 +381,29 @@ rt_status rt_context_create(int device, rt_context** out) try {
     if (!ctx) return RT_ERR_OOM;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    {
-        // keep freed scene memory in the device's stream-ordered pool instead of returning it to the driver
-        cudaMemPool_t pool = nullptr;
-        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    // everything created below is released by rt_context_destroy when a later step fails
+    const rt_status st = [&]() -> rt_status {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        // A memory pool of the context's own for scene data: freed scene memory stays in it (release threshold = max)
+        // instead of going back to the driver, without touching the device's DEFAULT pool, which torch and every other
+        // user of cudaMallocAsync in the process share.
+        cudaMemPoolProps pp{};
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        CUDA_TRY(cudaMemPoolCreate(&ctx->pool, &pp));
         unsigned long long keep = ~0ull;
-        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        CUDA_TRY(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        CUDA_TRY(cudaMalloc(&ctx->d_ray_counter, sizeof(unsigned long long)));
+        for (auto& ev : ctx->ev) CUDA_TRY(cudaEventCreate(&ev));
+        return RT_OK;
+    }();
+    if (st != RT_OK) {
+        rt_context_destroy(ctx);
+        return st;
     }
-    CUDA_TRY(cudaMalloc(&ctx->d_ray_counter, sizeof(unsigned long long)));
-    for (auto& ev : ctx->ev) CUDA_TRY(cudaEventCreate(&ev));
     *out = ctx;
     return RT_OK;
 } RT_API_CATCH
@@ -402,6 +421,7 @@ void rt_context_destroy(rt_context* ctx) {
     for (auto& c : ctx->array_cache) cudaFreeArray(c.arr);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -681,6 +701,17 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     s->d.root = bvh_root;
     s->d.mats = dmats;
     s->d.texs = dtexs;
+    s->d.n_list = 0;
+#ifndef RT_NO_LIST_CONST // (A/B switch: the global-memory list loop)
+    if (mode == RT_BVH_NONE && n != 0 && n <= RT_LIST_MAX) { // the list in the constant bank (DScene::lst_*)
+        s->d.n_list = n;
+        for (uint32_t k = 0; k < n; ++k) {
+            s->d.lst_a[k] = ha[k];
+            s->d.lst_b[k] = hb[k];
+            memcpy(&s->d.lst_dt[k], &hc[k].x, 4);
+        }
+    }
+#endif
     s->d.has_noise = 0;
     for (const auto& t : ht)
         if (t.kind == RT_TEX_NOISE_PERLIN || t.kind == RT_TEX_NOISE_TURBULANCE || t.kind == RT_TEX_NOISE_MARBLE || t.kind == RT_TEX_WOOD) s->d.has_noise = 1;
@@ -736,6 +767,8 @@ rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray*
                            rt_hit* hits) try {
     ARG_CHECK(ctx && scene, "ctx/scene is NULL");
     ARG_CHECK(n == 0 || (rays && hits), "rays/hits is NULL");
+    ARG_CHECK(use_bvh >= 0 && use_bvh <= 2, "use_bvh must be 0 (list), 1 (BVH) or 2 (4-wide BVH)");
+    ARG_CHECK(use_bvh != 2 || scene->d.nodes4 != nullptr, "use_bvh = 2: the scene has no 4-wide nodes (built from 4096 primitives on)");
     if (n == 0) return RT_OK;
     rt_status st = make_current(ctx);
     if (st != RT_OK) return st;
@@ -745,7 +778,7 @@ rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray*
     cudaError_t e = cudaMallocAsync(&d_hits, n * sizeof(rt_hit), ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
-        rtd::launch_trace_primary(scene->d, d_rays, n, tmin, use_bvh != 0, d_hits, ctx->stream);
+        rtd::launch_trace_primary(scene->d, d_rays, n, tmin, use_bvh, d_hits, ctx->stream);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_hits, n * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream);

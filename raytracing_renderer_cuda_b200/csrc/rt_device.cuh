@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "../../include/rt_api.h"
+#include "rt_fastdiv.hpp"
 
 namespace rtd {
 
@@ -88,6 +89,7 @@ struct BvhNode4 {
 #define RT_BVH4_EMPTY 0x7fffffff
 
 #define RT_MAX_IMAGES 8
+#define RT_LIST_MAX 12 // scenes of up to this many spheres travel inside the kernel parameters (constant bank), see DScene::lst_*
 #define RT_BVH_STACK_DEPTH 64 // per-thread traversal stack entries (rt_intersect.cuh)
 
 struct DScene {
@@ -110,9 +112,19 @@ struct DScene {
     DCamera cam;
     uint32_t n_lights;              // emitter spheres (RT_RENDER_EMITTER_SAMPLING), at most RT_MAX_LIGHTS
     uint32_t lights[RT_MAX_LIGHTS]; // their primitive indices, in the caller's list order
+    // Brute-force list scenes (n_spheres <= RT_LIST_MAX, no BVH — C1's 8 spheres, the hdr scene's 3): a copy of sph_a /
+    // sph_b / dt inside the kernel parameters.  The list loop's index is warp-uniform, so the sphere data are read from
+    // the constant bank through the uniform datapath (LDCU) instead of one LDG.128 + 64-bit address arithmetic per
+    // sphere and ray (ncu, C1: those and the loop control were 5 % of the kernel's instructions).  n_list = 0: not filled.
+    uint32_t n_list;
+    float4 lst_a[RT_LIST_MAX]; // (c0.xyz, r)
+    float4 lst_b[RT_LIST_MAX]; // (rz(c1 - c0).xyz, t0)
+    float lst_dt[RT_LIST_MAX]; // t1 - t0
 };
 
 struct DRenderParams {
+    FastDiv div_width; // pixel -> (column, row)
+    FastDiv div_npix;  // path -> (sample, pixel), see PathMap
     int32_t width, height;
     int32_t spp, sample_offset;
     int32_t max_depth;

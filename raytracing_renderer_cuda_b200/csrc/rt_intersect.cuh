@@ -101,8 +101,28 @@ RT_DEV void test_prim(const DScene& sc, const RayQ& q, uint32_t prim, float tmin
 RT_DEV Hit closest_hit_list(const DScene& sc, const RayQ& q, float tmin) {
     Hit best{FLT_MAX, RT_INVALID_ID};
     float t;
-    // two spheres per trip: the second sphere's load is in flight while the first is tested (C1: -1.6 % per frame,
-    // gpurun_out/ab_unroll.log; four per trip gives the gain back to register pressure)
+    if (sc.n_list != 0u) { // small scene: sphere data from the kernel parameters (constant bank, uniform loads)
+#ifdef RT_LIST_ROLLED
+#pragma unroll 1
+        for (uint32_t i = 0; i < sc.n_static; ++i) {
+            if (sphere_root_static(q, sc.lst_a[i], tmin, t)) consider(sc, i, t, best);
+        }
+#else
+        // unrolled over the compile-time index: the sphere's centre and radius are immediate constant-bank operands of
+        // the FADD/FFMA instructions — no load, no address, no loop counter
+#pragma unroll
+        for (uint32_t i = 0; i < RT_LIST_MAX; ++i) {
+            if (i >= sc.n_static) break;
+            if (sphere_root_static(q, sc.lst_a[i], tmin, t)) consider(sc, i, t, best);
+        }
+#endif
+#pragma unroll 1
+        for (uint32_t i = sc.n_static; i < sc.n_spheres; ++i) {
+            if (sphere_root_moving(q, sc.lst_a[i], sc.lst_b[i], sc.lst_dt[i], tmin, t)) consider(sc, i, t, best);
+        }
+        return best;
+    }
+    // two spheres per trip: the second sphere's load is in flight while the first is tested
 #pragma unroll 2
     for (uint32_t i = 0; i < sc.n_static; ++i) {
         float4 a = __ldg(&sc.sph_a[i]);
@@ -267,6 +287,22 @@ RT_DEV Hit closest_hit_bvh(const DScene& sc, const RayQ& q, float tmin) {
     // lane stopping for a sphere test in the middle of the others' descent.
     while (true) {
         while (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner(sc, q, tmin, t, stack);
+        if (t.node == RT_TRAV_DONE) break;
+        trav_leaf(sc, q, tmin, t, stack);
+    }
+    return t.best;
+}
+
+// The same walk over the 4-wide nodes (the tree k_wf_step_pt traverses; built from RT_PT_MIN_SPHERES primitives on):
+// per-lane loop, used by the parity hook (rt_trace_primary, use_bvh = 2) so that the wide traversal is compared
+// with the reference kernel ray by ray.
+RT_DEV Hit closest_hit_bvh4(const DScene& sc, const RayQ& q, float tmin) {
+    int stack[RT_BVH_STACK];
+    Trav t;
+    trav_begin(sc, q, t);
+    t.node = int(sc.root4);
+    while (true) {
+        while (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner<true>(sc, q, tmin, t, stack);
         if (t.node == RT_TRAV_DONE) break;
         trav_leaf(sc, q, tmin, t, stack);
     }

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) k_trace_primary(const __grid_constant__ D
     r.d = mk(in.direction[0], in.direction[1], in.direction[2]);
     r.time = in.time;
     RayQ q = make_rayq(r);
-    Hit h = closest_hit(sc, q, tmin, use_bvh != 0);
+    Hit h = (use_bvh == 2 && sc.nodes4) ? closest_hit_bvh4(sc, q, tmin) : closest_hit(sc, q, tmin, use_bvh != 0);
     rt_hit out;
     if (h.prim == RT_INVALID_ID) {
         out.t = FLT_MAX;
@@ -36,11 +36,11 @@ __global__ void __launch_bounds__(256) k_trace_primary(const __grid_constant__ D
     hits[i] = out;
 }
 
-void launch_trace_primary(const DScene& sc, const rt_ray* rays_dev, size_t n, float tmin, bool use_bvh,
+void launch_trace_primary(const DScene& sc, const rt_ray* rays_dev, size_t n, float tmin, int use_bvh,
                           rt_hit* hits_dev, cudaStream_t st) {
     if (n == 0) return;
     unsigned blocks = unsigned((n + 255) / 256);
-    k_trace_primary<<<blocks, 256, 0, st>>>(sc, rays_dev, n, tmin, use_bvh ? 1 : 0, hits_dev);
+    k_trace_primary<<<blocks, 256, 0, st>>>(sc, rays_dev, n, tmin, use_bvh, hits_dev);
 }
 
 // --------------------------------------------------------------- shade_probe ----

@@ -8,7 +8,7 @@
 namespace rtd {
 
 // parity hook: closest hit for caller-supplied rays
-void launch_trace_primary(const DScene& sc, const rt_ray* rays_dev, size_t n, float tmin, bool use_bvh,
+void launch_trace_primary(const DScene& sc, const rt_ray* rays_dev, size_t n, float tmin, int use_bvh, // 0 list, 1 BVH, 2 4-wide BVH
                           rt_hit* hits_dev, cudaStream_t st);
 
 // parity hook: closest hit + one shading step (terms of main.cu:45-55) per caller-supplied ray
@@ -34,8 +34,9 @@ struct WavefrontState;
 WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st);
 void wavefront_destroy(WavefrontState* ws);
 size_t wavefront_pool(const WavefrontState* ws);
-// renders rp.spp samples of every pixel into accum (+=); returns launches/iterations
-void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
+// renders rp.spp samples of every pixel into accum (+=); returns launches/iterations.  false: the frame did not
+// finish within the iteration bound (a defect or a CUDA error — never a silently short frame)
+bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
                       unsigned long long* ray_counter, int sm_count, cudaStream_t st, uint32_t* launches,
                       uint32_t* iterations);
 

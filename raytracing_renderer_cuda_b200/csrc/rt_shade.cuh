@@ -8,9 +8,22 @@
 namespace rtd {
 
 // ------------------------------------------------------------------ Perlin ----
-// perlin_noise() is one out-of-line function and the octave loop is not unrolled: the shade kernel drops from
-// 9 000 to 3 900 SASS instructions (144 KB -> 62 KB), which removes the instruction-cache stalls ncu showed
-// (profiles/r01_wavefront_ncu.md) and lets ptxas fit 4 CTAs of 256 threads per SM (64 registers).
+// perlin_noise() / perlin_turbulence() are out-of-line functions and the octave loop is not unrolled: the shade kernels
+// stay at ~3 800 SASS instructions (62 KB instead of 144 KB), which removed the instruction-cache stalls of the first
+// version and lets ptxas fit 32 warps per SM (64 registers).
+//
+// Round 2 rewrote the lattice walk and the gradient for instruction count (ncu, C1: Perlin was 36 % of all executed
+// warp instructions at 194 per octave, 108 of them the eight gradient selections, and the ALU pipe — selects, compares,
+// logic — was the busiest pipe of the kernel; profiles/r02_c1_instruction_diet.md):
+//  * ONE shared-memory table of 512 slots (the reference's doubled p[512], perlin_noise.h:43, so no index is ever
+//    masked after the first).  Slot i = (p[i] * 8) | code(p[i]) << 16 | code(p[i + 1]) << 24: the low half is the BYTE
+//    OFFSET of slot p[i] (slots are 8 bytes apart: two replicas, lane parity picks one), so the next level's address is
+//    one add — `LDS.U16 [slot]` and `LDS.U16 [slot + 8]` fetch p[i] and p[i + 1] without any shift or mask —, and the two
+//    high bytes are the gradient codes of the lattice points z and z + 1 in the form R2P turns into five predicates
+//    with one instruction (bit 0: u = y, 1: v = y, 2: v = x, 3: negate u, 4: negate v; perlin_noise::grad,
+//    perlin_noise.h:173-181).  A gradient is then R2P + 5 FSEL + FADD = 7 instructions instead of 13-14.
+//  * per octave: 10 LDS + 7 address adds instead of 7 LDS + 33 shifts/masks/adds; 124 instead of 194 instructions.
+// The arithmetic (operands, order, roundings) is unchanged: every value is bit-identical to the round-1 code.
 #ifndef RT_PERLIN_INLINE
 #define RT_PERLIN_FN static __device__ __noinline__
 #define RT_PERLIN_UNROLL _Pragma("unroll 1")
@@ -33,189 +46,88 @@ __device__ const uint8_t k_perlin_perm[256] = {
     242, 193, 238, 210, 144, 12,  191, 179, 162, 241, 81,  51,  145, 235, 249, 14,  239, 107, 49,  192, 214, 31,
     181, 199, 106, 157, 184, 84,  204, 176, 115, 121, 50,  45,  127, 4,   150, 254, 138, 236, 205, 93,  222, 114,
     67,  29,  24,  72,  243, 141, 128, 195, 78,  66,  215, 61,  156, 180};
-#ifdef RT_PERLIN_GLOBAL
-// A/B: the pair table (perm[i] | perm[i + 1] << 8) read straight from global memory through L1 (1 KB), no staging
-__device__ const uint32_t k_perlin_pairs[256] = {
-    0xa097, 0x89a0, 0x5b89, 0x5a5b, 0x0f5a, 0x830f, 0x0d83, 0xc90d, 0x5fc9, 0x605f, 0x3560, 0xc235, 0xe9c2, 0x07e9, 0xe107, 0x8ce1,
-    0x248c, 0x6724, 0x1e67, 0x451e, 0x8e45, 0x088e, 0x6308, 0x2563, 0xf025, 0x15f0, 0x0a15, 0x170a, 0xbe17, 0x06be, 0x9406, 0xf794,
-    0x78f7, 0xea78, 0x4bea, 0x004b, 0x1a00, 0xc51a, 0x3ec5, 0x5e3e, 0xfc5e, 0xdbfc, 0xcbdb, 0x75cb, 0x2375, 0x0b23, 0x200b, 0x3920,
-    0xb139, 0x21b1, 0x5821, 0xed58, 0x95ed, 0x3895, 0x5738, 0xae57, 0x14ae, 0x7d14, 0x887d, 0xab88, 0xa8ab, 0x44a8, 0xaf44, 0x4aaf,
-    0xa54a, 0x47a5, 0x8647, 0x8b86, 0x308b, 0x1b30, 0xa61b, 0x4da6, 0x924d, 0x9e92, 0xe79e, 0x53e7, 0x6f53, 0xe56f, 0x7ae5, 0x3c7a,
-    0xd33c, 0x85d3, 0xe685, 0xdce6, 0x69dc, 0x5c69, 0x295c, 0x3729, 0x2e37, 0xf52e, 0x28f5, 0xf428, 0x66f4, 0x8f66, 0x368f, 0x4136,
-    0x1941, 0x3f19, 0xa13f, 0x01a1, 0xd801, 0x50d8, 0x4950, 0xd149, 0x4cd1, 0x844c, 0xbb84, 0xd0bb, 0x59d0, 0x1259, 0xa912, 0xc8a9,
-    0xc4c8, 0x87c4, 0x8287, 0x7482, 0xbc74, 0x9fbc, 0x569f, 0xa456, 0x64a4, 0x6d64, 0xc66d, 0xadc6, 0xbaad, 0x03ba, 0x4003, 0x3440,
-    0xd934, 0xe2d9, 0xfae2, 0x7cfa, 0x7b7c, 0x057b, 0xca05, 0x26ca, 0x9326, 0x7693, 0x7e76, 0xff7e, 0x52ff, 0x5552, 0xd455, 0xcfd4,
-    0xcecf, 0x3bce, 0xe33b, 0x2fe3, 0x102f, 0x3a10, 0x113a, 0xb611, 0xbdb6, 0x1cbd, 0x2a1c, 0xdf2a, 0xb7df, 0xaab7, 0xd5aa, 0x77d5,
-    0xf877, 0x98f8, 0x0298, 0x2c02, 0x9a2c, 0xa39a, 0x46a3, 0xdd46, 0x99dd, 0x6599, 0x9b65, 0xa79b, 0x2ba7, 0xac2b, 0x09ac, 0x8109,
-    0x1681, 0x2716, 0xfd27, 0x13fd, 0x6213, 0x6c62, 0x6e6c, 0x4f6e, 0x714f, 0xe071, 0xe8e0, 0xb2e8, 0xb9b2, 0x70b9, 0x6870, 0xda68,
-    0xf6da, 0x61f6, 0xe461, 0xfbe4, 0x22fb, 0xf222, 0xc1f2, 0xeec1, 0xd2ee, 0x90d2, 0x0c90, 0xbf0c, 0xb3bf, 0xa2b3, 0xf1a2, 0x51f1,
-    0x3351, 0x9133, 0xeb91, 0xf9eb, 0x0ef9, 0xef0e, 0x6bef, 0x316b, 0xc031, 0xd6c0, 0x1fd6, 0xb51f, 0xc7b5, 0x6ac7, 0x9d6a, 0xb89d,
-    0x54b8, 0xcc54, 0xb0cc, 0x73b0, 0x7973, 0x3279, 0x2d32, 0x7f2d, 0x047f, 0x9604, 0xfe96, 0x8afe, 0xec8a, 0xcdec, 0x5dcd, 0xde5d,
-    0x72de, 0x4372, 0x1d43, 0x181d, 0x4818, 0xf348, 0x8df3, 0x808d, 0xc380, 0x4ec3, 0x424e, 0xd742, 0x3dd7, 0x9c3d, 0xb49c, 0x97b4};
-#endif
 
-
-// Shared-memory staging of the permutation.  Entry i holds the PAIR (perm[i], perm[i+1])
-// so the two neighbouring lookups every hash level needs (perlin_noise.h:67-72) cost one
-// load; the table is replicated 2^RT_PERLIN_BANK_BITS times (word i * replicas + lane mod replicas).
-// Optionally (RT_PERLIN_GTAB) a second table holds the 16 gradient directions of perlin_noise::grad as float4 coefficient vectors (one
-// LDS.128 per corner, replicated per lane: 16 x 32 x 16 B = 8 KB), see perlin_grad.
-#ifndef RT_PERLIN_BANK_BITS
-// Replicas per entry = 2^bits (lane l reads replica l mod 2^bits).  One replica per bank (5 bits, 32 KB per CTA) makes
-// every lookup conflict-free, but the table is staged by every CTA of every launch and its shared memory comes out of
-// the L1 that holds the kernels' stack frames: measured on C1 / C3 (gpurun_out/ab_banks.log, ab_banks2.log, 128-thread
-// CTAs): 5 bits 8.92 / 4.79 ms, 4: 8.75, 3: 8.69, 2: 8.65, 1: 8.58 / 4.69, 0: 8.68 / 4.70; straight from global memory
-// through L1 (RT_PERLIN_GLOBAL): 8.52 / 4.77.  Two replicas (2 KB) it is.
-#define RT_PERLIN_BANK_BITS 1
-#endif
-#define RT_PERLIN_PERM_WORDS (256 << RT_PERLIN_BANK_BITS)
-#ifdef RT_PERLIN_GTAB // opt-in: measured 1 % SLOWER on C1 than the compare/select form (gpurun_out/ab_perlin.log)
-#define RT_PERLIN_SMEM_WORDS (RT_PERLIN_PERM_WORDS + 16 * 32 * 4)
-#else
-#define RT_PERLIN_SMEM_WORDS RT_PERLIN_PERM_WORDS
-#endif
+#define RT_PERLIN_SLOTS 512u
+#define RT_PERLIN_SMEM_WORDS (RT_PERLIN_SLOTS * 2u) // two replicas per slot: 4 KB per CTA
 struct PerlinTab {
     const uint32_t* s; // shared memory, RT_PERLIN_SMEM_WORDS words
     uint32_t lane;
 };
+// gradient code of hash h (perlin_noise::grad, perlin_noise.h:173-181): u = h < 8 ? x : y;
+// v = h < 4 ? y : (h == 12 || h == 14 ? x : z); result = (h & 1 ? -u : u) + (h & 2 ? -v : v)
+RT_DEV uint32_t perlin_code(uint32_t hash) {
+    const uint32_t h = hash & 15u;
+    return (h >= 8u ? 1u : 0u) | (h < 4u ? 2u : 0u) | ((h == 12u || h == 14u) ? 4u : 0u) | ((h & 1u) << 3) | ((h & 2u) << 3);
+}
 RT_DEV void perlin_stage(uint32_t* smem, uint32_t tid, uint32_t nthreads) {
-#ifdef RT_PERLIN_GLOBAL
-    (void)smem; (void)tid; (void)nthreads;
-    return;
-#endif
-#if RT_PERLIN_BANK_BITS >= 2
-    // 4 consecutive replica words hold the same pair: one 16-byte store per 4 words
-    uint4* s4 = reinterpret_cast<uint4*>(smem);
-    for (uint32_t w = tid; w < RT_PERLIN_PERM_WORDS / 4; w += nthreads) {
-        uint32_t i = w >> (RT_PERLIN_BANK_BITS - 2);
-        uint32_t v = uint32_t(k_perlin_perm[i]) | (uint32_t(k_perlin_perm[(i + 1) & 255]) << 8);
-        s4[w] = make_uint4(v, v, v, v);
+    for (uint32_t w = tid; w < RT_PERLIN_SMEM_WORDS; w += nthreads) {
+        const uint32_t i = w >> 1;
+        const uint32_t p0 = k_perlin_perm[i & 255u], p1 = k_perlin_perm[(i + 1u) & 255u];
+        smem[w] = (p0 * 8u) | (perlin_code(p0) << 16) | (perlin_code(p1) << 24);
     }
-#else
-    for (uint32_t w = tid; w < RT_PERLIN_PERM_WORDS; w += nthreads) {
-        uint32_t i = w >> RT_PERLIN_BANK_BITS;
-        smem[w] = uint32_t(k_perlin_perm[i]) | (uint32_t(k_perlin_perm[(i + 1) & 255]) << 8);
-    }
-#endif
-#ifdef RT_PERLIN_GTAB
-    // gradient h = hash & 15 (perlin_noise.h:173-181): u = h<8 ? x : y; v = h<4 ? y : (h==12||h==14 ? x : z);
-    // grad = (h&1 ? -u : u) + (h&2 ? -v : v)  ==  cx*x + cy*y + cz*z with two coefficients +-1 and one 0
-    float4* g4 = reinterpret_cast<float4*>(smem + RT_PERLIN_PERM_WORDS);
-    for (uint32_t e = tid; e < 16u * 32u; e += nthreads) {
-        const uint32_t h = e >> 5;
-        float c[3] = {0.f, 0.f, 0.f};
-        const int ua = h < 8u ? 0 : 1;
-        const int va = h < 4u ? 1 : ((h == 12u || h == 14u) ? 0 : 2);
-        c[ua] = (h & 1u) ? -1.f : 1.f;
-        c[va] = (h & 2u) ? -1.f : 1.f;
-        g4[e] = make_float4(c[0], c[1], c[2], 0.f);
-    }
-#endif
 }
-RT_DEV uint32_t perlin_pair(const PerlinTab& pt, uint32_t i) {
-#ifdef RT_PERLIN_GLOBAL
-    return __ldg(&k_perlin_pairs[i & 255u]);
-#endif
-    return pt.s[((i & 255u) << RT_PERLIN_BANK_BITS) | (pt.lane & ((1u << RT_PERLIN_BANK_BITS) - 1u))];
-}
+// byte address of slot 0 of this lane's replica
+RT_DEV const char* perlin_base(const PerlinTab& pt) { return reinterpret_cast<const char*>(pt.s) + ((pt.lane & 1u) << 2); }
+// (p[i] * 8, p[i + 1] * 8) of the slot at byte address `slot`
+RT_DEV uint32_t perlin_next(const char* slot) { return *reinterpret_cast<const uint16_t*>(slot); }
+RT_DEV uint32_t perlin_next1(const char* slot) { return *reinterpret_cast<const uint16_t*>(slot + 8); }
 
-// perlin_noise::grad (perlin_noise.h:173-181)
-#ifdef RT_PERLIN_GTAB
-// Table form: exact — the zero coefficient adds nothing and the two unit coefficients give the same single rounding
-// as +-u +-v — and 3 FP instructions + one LDS.128 instead of ~13 compare/select/logic instructions per corner.
-RT_DEV float perlin_grad(const PerlinTab& pt, uint32_t hash, float x, float y, float z) {
-    const float4 c = reinterpret_cast<const float4*>(pt.s + RT_PERLIN_PERM_WORDS)[((hash & 15u) << 5) | pt.lane];
-    return __fmaf_rn(c.z, z, __fmaf_rn(c.y, y, c.x * x));
+// perlin_noise::grad (perlin_noise.h:173-181) from the code byte BYTE (2: lattice point z, 3: z + 1) of a slot word
+template <int BYTE>
+RT_DEV float perlin_grad(uint32_t w, float x, float y, float z) {
+    constexpr int SH = 8 * BYTE;
+    const bool uy = (w >> SH) & 1u, vy = (w >> (SH + 1)) & 1u, vx = (w >> (SH + 2)) & 1u, nu = (w >> (SH + 3)) & 1u, nv = (w >> (SH + 4)) & 1u;
+    float u = uy ? y : x;
+    float v = vx ? x : z;
+    v = vy ? y : v;
+    u = nu ? -u : u;
+    v = nv ? -v : v;
+    return u + v;
 }
-#else
-RT_DEV float perlin_grad(const PerlinTab&, uint32_t hash, float x, float y, float z) {
-    uint32_t h = hash & 15u;
-    float u = h < 8u ? x : y;
-    float v = h < 4u ? y : ((h == 12u || h == 14u) ? x : z);
-    return ((h & 1u) == 0u ? u : -u) + ((h & 2u) == 0u ? v : -v);
-}
-#endif
 RT_DEV float perlin_ease(float t) { return t * t * t * (t * (t * 6.f - 15.f) + 10.f); } // :156-165
 RT_DEV float perlin_lerp(float t, float a, float b) { return a + t * (b - a); }         // :167-171
 
-// perlin_noise::noise (perlin_noise.h:46-105)
-RT_DEV float perlin_noise_body(const PerlinTab& pt, V3 p) {
+// perlin_noise::noise (perlin_noise.h:46-105); `base` = perlin_base(pt)
+RT_DEV float perlin_noise_body(const char* base, V3 p) {
     float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
     uint32_t xi = uint32_t(int(fx)) & 255u, yi = uint32_t(int(fy)) & 255u, zi = uint32_t(int(fz)) & 255u;
     float xf = p.x - fx, yf = p.y - fy, zf = p.z - fz;
     float u = perlin_ease(xf), v = perlin_ease(yf), w = perlin_ease(zf);
-    uint32_t px = perlin_pair(pt, xi);        // (p[xi], p[xi+1])
-    uint32_t A = (px & 255u) + yi;            // p[xi] + yi
-    uint32_t B = ((px >> 8) & 255u) + yi;     // p[xi+1] + yi
-    uint32_t pa = perlin_pair(pt, A);         // (p[A], p[A+1])
-    uint32_t pb = perlin_pair(pt, B);         // (p[B], p[B+1])
-    uint32_t AA = (pa & 255u) + zi, AB = ((pa >> 8) & 255u) + zi;
-    uint32_t BA = (pb & 255u) + zi, BB = ((pb >> 8) & 255u) + zi;
-    uint32_t gaa = perlin_pair(pt, AA), gba = perlin_pair(pt, BA); // (p[AA], p[AA+1]) ...
-    uint32_t gab = perlin_pair(pt, AB), gbb = perlin_pair(pt, BB);
+    const char* sx = base + xi * 8u;                    // slot xi
+    const char* by = base + yi * 8u;                    // slot p[.] + yi  =  by + p[.] * 8
+    const char* bz = base + zi * 8u;
+    const char* sA = by + perlin_next(sx);              // slot A  = p[xi] + yi          (:67)
+    const char* sB = by + perlin_next1(sx);             // slot B  = p[xi + 1] + yi      (:70)
+    const uint32_t gaa = *reinterpret_cast<const uint32_t*>(bz + perlin_next(sA));  // slot AA = p[A] + zi: codes of p[AA], p[AA + 1]
+    const uint32_t gab = *reinterpret_cast<const uint32_t*>(bz + perlin_next1(sA)); // slot AB = p[A + 1] + zi
+    const uint32_t gba = *reinterpret_cast<const uint32_t*>(bz + perlin_next(sB));  // slot BA = p[B] + zi
+    const uint32_t gbb = *reinterpret_cast<const uint32_t*>(bz + perlin_next1(sB)); // slot BB = p[B + 1] + zi
     float x1 = xf - 1.f, y1 = yf - 1.f, z1 = zf - 1.f;
     float res = perlin_lerp(
         w,
-        perlin_lerp(v, perlin_lerp(u, perlin_grad(pt, gaa, xf, yf, zf), perlin_grad(pt, gba, x1, yf, zf)),
-                    perlin_lerp(u, perlin_grad(pt, gab, xf, y1, zf), perlin_grad(pt, gbb, x1, y1, zf))),
-        perlin_lerp(v, perlin_lerp(u, perlin_grad(pt, gaa >> 8, xf, yf, z1), perlin_grad(pt, gba >> 8, x1, yf, z1)),
-                    perlin_lerp(u, perlin_grad(pt, gab >> 8, xf, y1, z1), perlin_grad(pt, gbb >> 8, x1, y1, z1))));
+        perlin_lerp(v, perlin_lerp(u, perlin_grad<2>(gaa, xf, yf, zf), perlin_grad<2>(gba, x1, yf, zf)),
+                    perlin_lerp(u, perlin_grad<2>(gab, xf, y1, zf), perlin_grad<2>(gbb, x1, y1, zf))),
+        perlin_lerp(v, perlin_lerp(u, perlin_grad<3>(gaa, xf, yf, z1), perlin_grad<3>(gba, x1, yf, z1)),
+                    perlin_lerp(u, perlin_grad<3>(gab, xf, y1, z1), perlin_grad<3>(gbb, x1, y1, z1))));
     return (res + 1.0f) / 2.0f;
 }
-RT_PERLIN_FN float perlin_noise(const PerlinTab& pt, V3 p) { return perlin_noise_body(pt, p); }
+RT_PERLIN_FN float perlin_noise(const PerlinTab& pt, V3 p) { return perlin_noise_body(perlin_base(pt), p); }
 
 // perlin_noise::turbulance_noise, implementation 3 (perlin_noise.h:142-153), defaults
-// lacunacity 2, gain .5, 6 octaves (perlin_noise.h:13-17)
-#ifdef RT_PERLIN_PAIR
-// two octaves per call: the two lattice walks (floor -> three dependent table levels -> eight gradients -> seven
-// lerps) are independent, so their fixed-latency chains interleave; the sum is still taken octave by octave
-struct F2 {
-    float a, b;
-};
-RT_PERLIN_FN F2 perlin_noise2(const PerlinTab& pt, V3 p, float f0, float f1) {
-    return F2{perlin_noise_body(pt, p * f0), perlin_noise_body(pt, p * f1)};
-}
-RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
+// lacunacity 2, gain .5, 6 octaves (perlin_noise.h:13-17).  ONE out-of-line call per 6-octave evaluation with the
+// noise body inlined in its loop.
+RT_PERLIN_FN float perlin_turbulence(const PerlinTab& pt, V3 p) {
+    const char* base = perlin_base(pt);
     float frequency = 1.f, sum = 0.f, amplitude = 1.f;
     RT_PERLIN_UNROLL
-    for (int i = 0; i < 3; ++i) {
-        const F2 r = perlin_noise2(pt, p, frequency, frequency * 2.f);
-        sum += fabsf(r.a * 2.f - 1.f) * amplitude;
-        sum += fabsf(r.b * 2.f - 1.f) * (amplitude * 0.5f);
-        frequency *= 4.f;
-        amplitude *= 0.25f;
-    }
-    return sum;
-}
-#else
-#if !defined(RT_PERLIN_INLINE) && !defined(RT_PERLIN_TURB_CALLS)
-// ONE out-of-line call per 6-octave evaluation with the noise body inlined in its loop (six calls of perlin_noise cost
-// 1-2 % more on C1/C3: gpurun_out/ab_turbfn.log)
-static __device__ __noinline__ float perlin_turbulence(const PerlinTab& pt, V3 p) {
-    float frequency = 1.f, sum = 0.f, amplitude = 1.f;
-#pragma unroll 1
     for (int i = 0; i < 6; ++i) {
-        float r = perlin_noise_body(pt, p * frequency);
+        float r = perlin_noise_body(base, p * frequency);
         sum += fabsf(r * 2.f - 1.f) * amplitude;
         frequency *= 2.f;
         amplitude *= 0.5f;
     }
     return sum;
 }
-#else
-RT_DEV float perlin_turbulence(const PerlinTab& pt, V3 p) {
-    float frequency = 1.f, sum = 0.f, amplitude = 1.f;
-    RT_PERLIN_UNROLL
-    for (int i = 0; i < 6; ++i) {
-        float r = perlin_noise(pt, p * frequency);
-        sum += fabsf(r * 2.f - 1.f) * amplitude;
-        frequency *= 2.f;
-        amplitude *= 0.5f;
-    }
-    return sum;
-}
-#endif
-#endif
 
 // ------------------------------------------------------------------ textures ----
 RT_DEV DTexture load_tex(const DScene& sc, int32_t ix) {
@@ -302,7 +214,7 @@ RT_DEV V3 texture_value(const DScene& sc, const PerlinTab& pt, int32_t ix, V3 n,
 // Draw order of the reference: jitter x, jitter y, lens disk, shutter time.
 RT_DEV Ray camera_ray(const DScene& sc, const DRenderParams& rp, uint32_t pixel, uint32_t sample) {
     const DCamera& cam = sc.cam;
-    uint32_t i = pixel % uint32_t(rp.width), j = pixel / uint32_t(rp.width);
+    const uint32_t j = fastdiv(pixel, rp.div_width), i = pixel - j * uint32_t(rp.width);
     U4 r0 = rng_block(rp.seed, pixel, sample, 0, 0);
     float s = float(i + u01(r0.x)) / float(rp.width);
     float t = float(j + u01(r0.y)) / float(rp.height);

@@ -28,7 +28,6 @@
 #include <cstdlib>
 
 #include "rt_kernels.cuh"
-#include "rt_ring.hpp"
 #include "rt_shade.cuh"
 
 namespace rtd {
@@ -73,8 +72,28 @@ struct WfBuffers {
     uint32_t* counts;            // [3][NQ] queue sizes, rotating: cur / next / being-zeroed
     uint32_t* tickets;           // [3] chunk ticket counters, same rotation
     unsigned long long* next_path; // [2], rotating: [it & 1] = paths started before iteration `it`
+    uint2* next_ps;                // [2], same rotation: (next_path % pixels, next_path / pixels), kept by the kernels so that
+                                   // no thread divides a 64-bit path number (PathMap)
     uint32_t pool;
 };
+
+// Where the new paths of an iteration start: entry idx of Q_NEW is path next_path + idx, i.e. pixel
+// (pix_base + idx) % npix of sample smp_base + (pix_base + idx) / npix — one 32-bit division by an invariant
+// (FastDiv; pix_base < npix < 2^31 and idx < pool <= 2^28 cannot overflow).  n_valid: entries that still get a path.
+struct PathMap {
+    uint32_t pix_base, smp_base, n_valid;
+};
+RT_DEV PathMap make_pathmap(const WfBuffers& wb, int it, unsigned long long path_base, uint32_t n_new, unsigned long long npaths) {
+    const uint2 ps = wb.next_ps[it & 1];
+    const unsigned long long left = npaths > path_base ? npaths - path_base : 0ull;
+    return PathMap{ps.x, ps.y, left < n_new ? uint32_t(left) : n_new};
+}
+// block 0 / thread 0 of every step kernel: the counters of the next iteration
+RT_DEV void wf_advance_paths(const WfBuffers& wb, int it, unsigned long long path_base, uint32_t n_new, unsigned long long npix) {
+    const unsigned long long next = path_base + n_new;
+    wb.next_path[(it + 1) & 1] = next;
+    wb.next_ps[(it + 1) & 1] = make_uint2(uint32_t(next % npix), uint32_t(next / npix));
+}
 
 struct WavefrontState {
     WfBuffers b{};
@@ -82,9 +101,7 @@ struct WavefrontState {
     uint32_t* h_counts = nullptr;           // pinned [2][3 * NQ]: queue sizes, one copy per polling parity
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
-    unsigned long long* ring_ctl = nullptr; // counters of the ring kernel (RT_WF_GRAIN=ring), allocated on first use
-    uint32_t* tail_ring = nullptr;          // RT_WF_TAIL: a small ring of its own ([NQ][1 << kTailCapLog2]) + its counters
-    unsigned long long* tail_ctl = nullptr;
+    int persist_max = -1, window_max = 0; // L2 persistence limits of this state's device, queried on first use
 };
 
 // Streaming accesses to data that is read once and written once per iteration (path records, queue entries): L1
@@ -173,8 +190,7 @@ struct WfLane {
 // NEE = RT_RENDER_EMITTER_SAMPLING (a separate instantiation: the reference estimator's kernels do not change).
 template <bool NEE, int STREAM>
 RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind, bool valid,
-                     uint32_t slot, unsigned long long path, unsigned long long npix, unsigned long long npaths,
-                     float4* __restrict__ accum, WfLane& ln, int& out_q) {
+                     uint32_t slot, uint32_t idx, const PathMap& pm, float4* __restrict__ accum, WfLane& ln, int& out_q) {
     const V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
     const WfRecord* rec = wb.rec + slot;
     bool has_ray = false;   // a ray to extend
@@ -190,9 +206,10 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
 
     if (valid) {
         if (kind == Q_NEW) {
-            if (path < npaths) {
-                pixel = uint32_t(path % npix);
-                sample = uint32_t(path / npix) + uint32_t(rp.sample_offset);
+            if (idx < pm.n_valid) {
+                const uint32_t x = pm.pix_base + idx, q = fastdiv(x, rp.div_npix);
+                pixel = x - q * rp.div_npix.d;
+                sample = pm.smp_base + q + uint32_t(rp.sample_offset);
                 A = mk(rp.world_r, rp.world_g, rp.world_b);
                 if (rp.max_depth > 0) {
                     r = camera_ray(sc, rp, pixel, sample);
@@ -320,11 +337,11 @@ RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers&
 // the warp (the BVH traversal is warp-cooperative); `valid` = false for lanes past the end of the queue.
 template <bool USE_BVH, bool NEE, int ACC = WF_STREAM>
 RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind,
-                            bool valid, uint32_t slot, unsigned long long path, unsigned long long npix,
-                            unsigned long long npaths, float4* __restrict__ accum, unsigned long long& nrays) {
+                            bool valid, uint32_t slot, uint32_t idx, const PathMap& pm, float4* __restrict__ accum,
+                            unsigned long long& nrays) {
     WfLane ln;
     int out_q;
-    const bool has_ray = wf_begin<NEE, ACC>(sc, rp, wb, pt, kind, valid, slot, path, npix, npaths, accum, ln, out_q);
+    const bool has_ray = wf_begin<NEE, ACC>(sc, rp, wb, pt, kind, valid, slot, idx, pm, accum, ln, out_q);
     if (NEE) nrays += ln.shadow_rays;
     if (USE_BVH) {
         const RayQ q = make_rayq(ln.r);
@@ -369,6 +386,15 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t s_count[2][NQ]; // double-buffered by chunk parity: two barriers per chunk instead of four
     __shared__ uint32_t s_base[2][NQ];
+    // The chunk a CTA works on next, located by ONE thread (round 1 had all 128 threads redo the search through the
+    // per-queue chunk table after every chunk: 5 % of the kernel's instructions, profiles/r02_c1_instruction_diet.md)
+    struct __align__(16) Chunk {
+        int kind;               // shading queue, -1: no chunk left
+        uint32_t first, n_kind; // first entry of the chunk, entries in the queue
+        uint32_t pad;
+        const uint32_t* q_in;   // the queue
+    };
+    __shared__ Chunk s_chunk[2];
 
     const PerlinTab pt{smem, threadIdx.x & 31u};
     const uint32_t lane = threadIdx.x & 31u;
@@ -383,11 +409,9 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     uint32_t n_q[NQ], chunk_end[NQ];
     uint32_t total_chunks = 0;
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-        // most expensive classes first so the long chunks start early
-        n_q[k] = __ldg(cnt_cur + k);
-    }
-    // chunk order: NOISE6, NOISE1, IMAGE, EMIT, DIEL, METAL, LAMB_CONST, NEW
+    for (int k = 0; k < NQ; ++k) n_q[k] = __ldg(cnt_cur + k);
+    // chunk order, most expensive classes first so the long chunks start early:
+    // NOISE6, NOISE1, IMAGE, EMIT, DIEL, METAL, LAMB_CONST, NEW
     const int order[NQ] = {Q_LAMB_NOISE6, Q_LAMB_NOISE1, Q_LAMB_IMAGE, Q_EMIT, Q_DIEL, Q_METAL, Q_LAMB_CONST, Q_NEW};
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
@@ -398,43 +422,51 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     // Tail iterations hold a few hundred live paths: CTAs without a chunk leave before staging anything, and
     // the Perlin table is staged only by CTAs that will run a noise shader (their first chunk is the
     // lowest-numbered one they get, and the noise queues come first; textured emitters may need it too).
-    if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
-    if (blockIdx.x >= total_chunks) return;
     const unsigned long long npix = (unsigned long long)rp.width * rp.height;
     const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) wf_advance_paths(wb, it, path_base, n_q[Q_NEW], npix);
+    if (blockIdx.x >= total_chunks) return;
     if (wf_frame_done(n_q, path_base, npaths)) return;
+    const PathMap pm = make_pathmap(wb, it, path_base, n_q[Q_NEW], npaths);
     if (sc.has_noise && (blockIdx.x < chunk_end[1] || n_q[Q_EMIT] != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     if (threadIdx.x < 2 * NQ) (&s_count[0][0])[threadIdx.x] = 0u;
+
+    // chunk number -> s_chunk[par] (thread 0 only)
+    auto locate = [&](uint32_t chunk, uint32_t par) {
+        Chunk c;
+        c.kind = -1;
+        c.first = c.n_kind = c.pad = 0u;
+        c.q_in = nullptr;
+        if (chunk < total_chunks) {
+            int kpos = 0;
+#pragma unroll
+            for (int k = 0; k < NQ - 1; ++k) kpos += (chunk >= chunk_end[k]) ? 1 : 0;
+            c.kind = order[kpos];
+            c.first = (chunk - (kpos ? chunk_end[kpos - 1] : 0u)) * WF_CTA_THREADS;
+            c.n_kind = n_q[c.kind];
+            c.q_in = wf_queue(wb, par_cur, c.kind);
+        }
+        s_chunk[par] = c;
+    };
+    if (threadIdx.x == 0) locate(blockIdx.x, 0u); // the first gridDim.x chunks are implicit: chunk = blockIdx.x
     __syncthreads();
 
     unsigned long long nrays = 0;
-
-    // chunk -> (queue kind, first entry)
-    auto locate = [&](uint32_t chunk, int& kind, uint32_t& first) {
-        int kpos = 0;
-#pragma unroll
-        for (int k = 0; k < NQ - 1; ++k) kpos += (chunk >= chunk_end[k]) ? 1 : 0;
-        kind = order[kpos];
-        first = (chunk - (kpos ? chunk_end[kpos - 1] : 0u)) * WF_CTA_THREADS;
-    };
     uint32_t cpar = 0;
-    int kind;
-    uint32_t first;
-    locate(blockIdx.x, kind, first);
-    uint32_t slot = (first + threadIdx.x < n_q[kind]) ? wf_qload<WF_STREAM>(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
-    // Chunks are drawn from a ticket counter (the first gridDim.x are implicit: chunk = blockIdx.x), so a CTA that got
-    // cheap chunks simply takes more of them: against handing chunks out by stride, C1 9.46 -> 9.05 ms per frame.
-    // Thread 0 draws the ticket of the NEXT chunk at the top of a trip; the two barriers of the trip publish it.
-    __shared__ uint32_t s_next_chunk[2];
+    // Chunks are drawn from a ticket counter, so a CTA that got cheap chunks simply takes more of them (against handing
+    // chunks out by stride: C1 9.46 -> 9.05 ms per frame).  Thread 0 draws the ticket of the NEXT chunk at the top of a
+    // trip and turns it into a chunk record at the bottom — the atomic's latency hides behind the chunk's shading —;
+    // the two barriers of the trip publish the record.
     uint32_t* ticket = wb.tickets + (it % 3);
-    uint32_t next_chunk = 0u;
-    for (uint32_t chunk = blockIdx.x; chunk < total_chunks; chunk = next_chunk) {
-        if (threadIdx.x == 0) s_next_chunk[cpar] = gridDim.x + atomicAdd(ticket, 1u);
-        const uint32_t idx = first + threadIdx.x;
-        const bool valid = idx < n_q[kind];
-        const int kind_now = kind;
+    Chunk ck = s_chunk[0];
+    uint32_t slot = (ck.first + threadIdx.x < ck.n_kind) ? wf_qload<WF_STREAM>(ck.q_in + ck.first + threadIdx.x) : 0u;
+    while (ck.kind >= 0) {
+        uint32_t drawn = 0u;
+        if (threadIdx.x == 0) drawn = atomicAdd(ticket, 1u);
+        const uint32_t idx = ck.first + threadIdx.x;
+        const bool valid = idx < ck.n_kind;
 
-        const int out_q = wf_process_entry<USE_BVH, NEE>(sc, rp, wb, pt, kind_now, valid, slot, path_base + idx, npix, npaths, accum, nrays);
+        const int out_q = wf_process_entry<USE_BVH, NEE>(sc, rp, wb, pt, ck.kind, valid, slot, idx, pm, accum, nrays);
 
         // ---- queue push: warp ballot -> shared counters -> one global atomic per queue ----
         uint32_t local = 0;
@@ -448,6 +480,7 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
                 local = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
             }
         }
+        if (threadIdx.x == 0) locate(gridDim.x + drawn, cpar ^ 1u);
         __syncthreads();
         if (threadIdx.x < NQ) {
             uint32_t c = s_count[cpar][threadIdx.x];
@@ -457,13 +490,10 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
         __syncthreads();
         if (out_q != Q_NONE) wf_st<WF_STREAM>(wf_queue(wb, par_next, out_q) + s_base[cpar][out_q] + local, slot);
         cpar ^= 1u;
-        // (requesting the next chunk's slot indices a chunk ahead, and prefetching their records, was measured: 2.6 % and
-        // 1.2 % slower with 16 Mi slots — gpurun_out/ab_pipe.log, ab_misc.log)
-        next_chunk = s_next_chunk[cpar ^ 1u]; // (cpar was flipped above) written before the two barriers of this trip
-        if (next_chunk < total_chunks) {
-            locate(next_chunk, kind, first);
-            slot = first + threadIdx.x < n_q[kind] ? wf_qload<WF_STREAM>(wf_queue(wb, par_cur, kind) + first + threadIdx.x) : 0u;
-        }
+        // (requesting the next chunk's slot indices a chunk ahead, and prefetching their records, was measured in
+        // round 1: 2.6 % and 1.2 % slower with 16 Mi slots)
+        ck = s_chunk[cpar]; // written before the two barriers of this trip; rewritten after the first barrier of the next
+        if (ck.kind >= 0) slot = ck.first + threadIdx.x < ck.n_kind ? wf_qload<WF_STREAM>(ck.q_in + ck.first + threadIdx.x) : 0u;
     }
 
     for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
@@ -533,12 +563,13 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     // Tail iterations hold a few hundred live paths: CTAs without a chunk leave before staging anything, and
     // the Perlin table is staged only by CTAs that will run a noise shader (their first chunk is the
     // lowest-numbered one they get, and the noise queues come first; textured emitters may need it too).
-    if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_q[Q_NEW];
-    const uint32_t warps_per_cta = WF_THREADS / 32;
-    if (blockIdx.x * warps_per_cta >= total_chunks) return;
     const unsigned long long npix = (unsigned long long)rp.width * rp.height;
     const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) wf_advance_paths(wb, it, path_base, n_q[Q_NEW], npix);
+    const uint32_t warps_per_cta = WF_THREADS / 32;
+    if (blockIdx.x * warps_per_cta >= total_chunks) return;
     if (wf_frame_done(n_q, path_base, npaths)) return;
+    const PathMap pm = make_pathmap(wb, it, path_base, n_q[Q_NEW], npaths);
     if (sc.has_noise && (chunk_end[1] != 0u || n_q[Q_EMIT] != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     __syncthreads(); // the only block-wide barrier of the kernel
 
@@ -571,7 +602,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
             const uint32_t idx = first + uint32_t(e) * 32u + lane;
             const bool valid = idx < n_kind;
             const uint32_t slot = valid ? wf_qload<WF_STREAM>(q_in + idx) : 0u;
-            const int out_q = wf_process_entry<USE_BVH, NEE>(sc, rp, wb, pt, kind, valid, slot, path_base + idx, npix, npaths, accum, nrays);
+            const int out_q = wf_process_entry<USE_BVH, NEE>(sc, rp, wb, pt, kind, valid, slot, idx, pm, accum, nrays);
                 outq_pack |= uint32_t(out_q + 1) << (4 * e);
         }
 
@@ -655,13 +686,14 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
         if (order[k] == Q_EMIT) n_emit = n;
         if (order[k] == Q_NEW) n_new = n;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) wb.next_path[(it + 1) & 1] = path_base + n_new;
+    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
+    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
+    if (blockIdx.x == 0 && threadIdx.x == 0) wf_advance_paths(wb, it, path_base, n_new, npix);
     if (blockIdx.x * (WF_THREADS / 32) >= total_chunks) return;
+    const PathMap pm = make_pathmap(wb, it, path_base, n_new, npaths);
     if (sc.has_noise && (noise_chunks != 0u || n_emit != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     __syncthreads(); // the only block-wide barrier of the kernel
 
-    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
-    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
     unsigned long long nrays = 0;
 
     auto draw = [&]() -> uint32_t {
@@ -738,7 +770,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
             if (!tracing && rank < navail) {
                 const uint32_t idx = pos + rank;
                 const uint32_t slot = wf_qload<WF_PT_STREAM>(q_in + idx);
-                if (wf_begin<NEE, WF_PT_STREAM>(sc, rp, wb, pt, kind, true, slot, path_base + idx, npix, npaths, accum, ln, out_q)) {
+                if (wf_begin<NEE, WF_PT_STREAM>(sc, rp, wb, pt, kind, true, slot, idx, pm, accum, ln, out_q)) {
                     q = make_rayq(ln.r);
                     trav_begin(sc, q, t);
 #ifndef RT_PT_BINARY
@@ -778,233 +810,16 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
     if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
 }
 
-// Work granularity, variant 4 — EXPERIMENTAL, selected only by RT_WF_GRAIN=ring, never by default.  ONE persistent
-// launch per frame and no iteration barrier: the ~60 thin tail iterations of a frame and the bubble between two
-// dependent launches become the latency of the longest path.  Measured (profiles/r01_ring.md):
-// identical frames; 24-39 % faster than the per-iteration kernels on frames of <= 1.3 M paths, 19-21 % slower on C1/C2
-// (the bulk costs more per entry: three atomics per push, L2-only record accesses, a release fence per entry = 5 %).
-//
-// Per shading class a ring of slot indices in the queue memory (capacity `cap`, a power of two >= 2 x slots in use)
-// and three 64-bit counters that live for the life of the WavefrontState, each in its own 128-byte line:
-//   reserve  producers: base = atomicAdd(reserve, c) hands out write positions (one atomic per CTA chunk and class)
-//   credits  a counting semaphore: producers add c right after reserving; a consumer takes n entries with
-//            atomicAdd(credits, -n) and gives them back when the old value was < n — so the sum of the successful
-//            claims never exceeds what was reserved, whatever the interleaving (no CAS loop: with ~100 claims per
-//            microsecond a compare-and-swap on the head would fail almost always)
-//   head     consumers: pos = atomicAdd(head, n) after the credits were taken, so every position below head has been
-//            reserved by a producer that is running and writes it without waiting for anybody.
-// A ring entry is slot | tag << 25 with tag = 64 | (lap & 63), lap = position / cap: a consumer polls ITS positions
-// until the tag of the current lap shows up (the producer may still be between its reserve and its store), which
-// replaces a commit counter.  Stale contents never match: the lap before carries another tag, and raw slot indices
-// written by the per-iteration kernels (< 2^24) carry tag 0.  Records are written before the entry (st.release per
-// thread) and read with L2-only loads after it (WF_ACC_L2: the address depends on the polled entry).
-// A CTA takes a chunk of up to WF_CTA_THREADS entries of the class with the most credits (full chunks while any class
-// has one — the bulk of the frame —, whatever is there in the tail), the claim of the NEXT chunk is drawn by warp 1
-// while warp 0 reserves the pushes of the current one, so a trip has the same two block barriers as k_wf_step_cta.
-// Termination: `busy` counts CTAs that hold (or are trying to take) a chunk; a CTA leaves when it finds no credits
-// and busy == 0 twice around the scan.  A CTA that pushed entries sees them itself, so work is never abandoned; a
-// wrong early exit of ANOTHER CTA only costs parallelism.  Q_NEW is ignored once every path of the frame has started
-// (its leftovers are dropped by the next frame's k_ring_commit).
-// Not proven, only practically impossible: a consumer stalled between its claim and its read for a whole lap of
-// the ring (>= slots further pushes of the same class) would find its entry overwritten and spin forever.
-using WfRing = ring::Ring;
-using ring::RingClaim;
-using ring::RC_RESERVE;
-using ring::RC_CREDITS;
-using ring::RC_HEAD;
-#ifdef WF_RING_ACC_STREAM // A/B ONLY (what do the L2-only accesses cost?): .cs loads may hit a stale L1 line in the tail
-#define WF_RING_ACC WF_ACC_STREAM
-#else
-#define WF_RING_ACC WF_ACC_L2
-#endif
-#ifndef WF_RING_BATCH
-#define WF_RING_BATCH 1u // chunks per claim while a class holds plenty (A/B: 4 — untested hypothesis: the fullest class's counters are hot)
-#endif
-using RingOps = ring::Protocol<NQ, Q_NEW>; // the claim/termination protocol: rt_ring.hpp (also compiled for the host by tests/ring_sim.cpp)
-
-template <bool USE_BVH, bool NEE>
-__global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
-    k_wf_ring(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
-              const __grid_constant__ WfRing rg, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint32_t s_count[2][NQ]; // double-buffered by chunk parity, as in k_wf_step_cta
-    __shared__ unsigned long long s_base[2][NQ];
-    __shared__ RingClaim s_claim;
-#ifdef WF_RING_EARLY_CLAIM
-    __shared__ RingClaim s_early[2]; // the next chunk, claimed at the TOP of a trip (hidden behind the shading), by chunk parity
-#endif
-    constexpr uint32_t kClaimer = WF_CTA_THREADS >= 64 ? 32u : 0u; // lane 0 of warp 1: warp 0 does the push atomics meanwhile
-
-    const PerlinTab pt{smem, threadIdx.x & 31u};
-    const uint32_t lane = threadIdx.x & 31u;
-    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
-    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
-
-    if (threadIdx.x == kClaimer) {
-        RingClaim c;
-        RingOps::claim_wait(rg, npaths, WF_CTA_THREADS, false, c, WF_RING_BATCH);
-        s_claim = c;
-    }
-    if (threadIdx.x < 2 * NQ) (&s_count[0][0])[threadIdx.x] = 0u;
-    __syncthreads();
-    if (s_claim.kind < 0) return; // (uniform) a CTA that found the frame finished
-    if (sc.has_noise) perlin_stage(smem, threadIdx.x, blockDim.x); // once per CTA and frame
-    __syncthreads();
-
-    unsigned long long nrays = 0;
-    uint32_t cpar = 0;
-    for (;;) {
-        const int kind = s_claim.kind; // rewritten by the claimer only after the first barrier of this trip
-        if (kind < 0) break;
-        const uint32_t n = s_claim.n < WF_CTA_THREADS ? s_claim.n : WF_CTA_THREADS; // (a batch claim is worked off a chunk per trip)
-        const unsigned long long pos = s_claim.pos, path_base = s_claim.path;
-        const bool valid = threadIdx.x < n;
-        uint32_t slot = 0u;
-        if (valid) { // the entry may still be on its way: poll for the tag of this lap
-            const unsigned long long p = pos + threadIdx.x;
-            const uint32_t want = ring::tag(rg, p);
-            const uint32_t* e = ring::entry(rg, kind, p);
-            uint32_t v = ring::load_entry(e);
-            while ((v >> 25) != want) v = ring::load_entry(e);
-            slot = v & 0xffffffu;
-        }
-#ifdef WF_RING_EARLY_CLAIM
-        if (threadIdx.x == kClaimer) { // this CTA counts as busy; a failed attempt is repeated between the barriers below
-            RingClaim c;
-            c.kind = -1;
-            if (!(WF_RING_BATCH > 1u && s_claim.n > WF_CTA_THREADS)) RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c, WF_RING_BATCH);
-            s_early[cpar] = c;
-        }
-#endif
-
-        const int out_q = wf_process_entry<USE_BVH, NEE, WF_RING_ACC>(sc, rp, wb, pt, kind, valid, slot, path_base + threadIdx.x, npix,
-                                                                    npaths, accum, nrays);
-
-        // ---- push: warp ballot -> shared counters -> one reserve + one credit atomic per class ----
-        uint32_t local = 0;
-        {
-            const unsigned peers = __match_any_sync(0xffffffffu, out_q);
-            if (out_q != Q_NONE) {
-                const int leader = __ffs(peers) - 1;
-                uint32_t base = 0;
-                if (int(lane) == leader) base = atomicAdd(&s_count[cpar][out_q], uint32_t(__popc(peers)));
-                base = __shfl_sync(peers, base, leader);
-                local = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < NQ) {
-            const uint32_t c = s_count[cpar][threadIdx.x];
-            unsigned long long base = 0ull;
-            if (c) {
-                base = ring::add(ring::ctl(rg, int(threadIdx.x), RC_RESERVE), c);
-                ring::add(ring::ctl(rg, int(threadIdx.x), RC_CREDITS), c); // consumers poll the tags
-            }
-            s_base[cpar][threadIdx.x] = base;
-            s_count[cpar ^ 1u][threadIdx.x] = 0u; // the other buffer was last read before the barrier above
-        }
-        if (threadIdx.x == kClaimer) { // the next chunk, while this CTA still counts as busy
-            RingClaim c;
-            if (WF_RING_BATCH > 1u && s_claim.n > WF_CTA_THREADS) { // the rest of a batch claim
-                c = s_claim;
-                c.n -= WF_CTA_THREADS;
-                c.pos += WF_CTA_THREADS;
-                if (c.kind == Q_NEW) c.path += WF_CTA_THREADS;
-            } else {
-#ifdef WF_RING_EARLY_CLAIM
-                c = s_early[cpar];
-                if (c.kind < 0)
-#endif
-                    RingOps::claim_try(rg, npaths, WF_CTA_THREADS, c, WF_RING_BATCH);
-            }
-            s_claim = c;
-        }
-        __syncthreads();
-        if (out_q != Q_NONE) {
-            const unsigned long long p = s_base[cpar][out_q] + local;
-            ring::publish(ring::entry(rg, out_q, p), slot | (ring::tag(rg, p) << 25)); // after this thread's record (wf_finish)
-        }
-        cpar ^= 1u;
-        if (s_claim.kind < 0) { // (uniform) nothing was claimable before this chunk's pushes: release `busy` and wait
-            __syncthreads();    // everybody has looked at s_claim
-            if (threadIdx.x == kClaimer) {
-                RingClaim c;
-                RingOps::claim_wait(rg, npaths, WF_CTA_THREADS, true, c, WF_RING_BATCH);
-                s_claim = c;
-            }
-            __syncthreads();
-        }
-    }
-
-    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
-    if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
-}
-
-// frame start of the ring kernel (two launches, each alone on the stream): every slot in use enters Q_NEW ...
-__global__ void k_ring_fill(const __grid_constant__ WfRing rg, uint32_t n_slots) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots) return;
-    const unsigned long long p = *ring::ctl(rg, Q_NEW, RC_RESERVE) + i;
-    *ring::entry(rg, Q_NEW, p) = i | (ring::tag(rg, p) << 25);
-}
-// ... and the counters: whatever an earlier frame left queued (Q_NEW entries after its last path) is dropped
-__global__ void k_ring_commit(const __grid_constant__ WfRing rg, uint32_t n_slots) {
-    const int q = int(threadIdx.x);
-    if (q < NQ) {
-        const unsigned long long r = *ring::ctl(rg, q, RC_RESERVE);
-        const unsigned long long add = q == Q_NEW ? n_slots : 0u;
-        *ring::ctl(rg, q, RC_HEAD) = r;
-        *ring::ctl(rg, q, RC_RESERVE) = r + add;
-        *ring::ctl(rg, q, RC_CREDITS) = add;
-    }
-    if (q == 0) {
-        *ring::word(rg, RingOps::RC_NEXT_PATH) = 0ull;
-        *ring::word(rg, RingOps::RC_BUSY) = 0ull;
-    }
-}
-
-// RT_WF_TAIL (experimental, off by default, NOT yet run on a GPU): the per-iteration kernels render the bulk of a frame,
-// and once every path has started and few are alive the queues of the current iteration are moved into a small ring
-// and ONE k_wf_ring launch finishes the frame — the thin tail iterations (0.7 of C1's 8.5 ms) are where the
-// barrier-free form wins (frames of <= 1.3 M paths: -24...-39 %, profiles/r01_ring.md), the bulk is where it loses.
-// k_ring_import: entry i of every shading queue of iteration `it` -> ring position reserve + i (Q_NEW is not
-// imported: no path is left to start).  k_ring_commit_tail: the counters; next_path = npaths makes the ring kernel
-// ignore Q_NEW.  Each runs alone on the stream.
-__global__ void k_ring_import(const __grid_constant__ WfBuffers wb, const __grid_constant__ WfRing rg, int it) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t* cnt = wb.counts + (it % 3) * NQ;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        if (q == Q_NEW) continue;
-        if (i < cnt[q]) {
-            const unsigned long long p = *ring::ctl(rg, q, RC_RESERVE) + i;
-            *ring::entry(rg, q, p) = wf_queue(wb, it & 1, q)[i] | (ring::tag(rg, p) << 25);
-        }
-    }
-}
-__global__ void k_ring_commit_tail(const __grid_constant__ WfBuffers wb, const __grid_constant__ WfRing rg, int it,
-                                   unsigned long long npaths) {
-    const int q = int(threadIdx.x);
-    if (q < NQ) {
-        const unsigned long long r = *ring::ctl(rg, q, RC_RESERVE);
-        const unsigned long long add = q == Q_NEW ? 0u : wb.counts[(it % 3) * NQ + q];
-        *ring::ctl(rg, q, RC_HEAD) = r;
-        *ring::ctl(rg, q, RC_RESERVE) = r + add;
-        *ring::ctl(rg, q, RC_CREDITS) = add;
-    }
-    if (q == 0) {
-        *ring::word(rg, RingOps::RC_NEXT_PATH) = npaths;
-        *ring::word(rg, RingOps::RC_BUSY) = 0ull;
-    }
-}
-
 // fills Q_NEW of iteration 0 with every slot and resets the path counter
 __global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_slots) wf_queue(wb, 0, Q_NEW)[i] = i;
     if (i < 3 * NQ) wb.counts[i] = (i == Q_NEW) ? n_slots : 0u;
     if (i < 3) wb.tickets[i] = 0u;
-    if (i == 0) wb.next_path[0] = wb.next_path[1] = 0ull;
+    if (i == 0) {
+        wb.next_path[0] = wb.next_path[1] = 0ull;
+        wb.next_ps[0] = wb.next_ps[1] = make_uint2(0u, 0u);
+    }
 }
 
 WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st) {
@@ -1016,6 +831,7 @@ WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st) {
     ok = ok && cudaMalloc(&ws->b.counts, 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.tickets, 3 * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.next_path, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ws->b.next_ps, 2 * sizeof(uint2)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ws->h_status, 2 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ws->h_counts, 2 * 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ws->poll_ev[0], cudaEventDisableTiming) == cudaSuccess;
@@ -1034,9 +850,7 @@ void wavefront_destroy(WavefrontState* ws) {
     if (ws->b.counts) cudaFree(ws->b.counts);
     if (ws->b.tickets) cudaFree(ws->b.tickets);
     if (ws->b.next_path) cudaFree(ws->b.next_path);
-    if (ws->ring_ctl) cudaFree(ws->ring_ctl);
-    if (ws->tail_ring) cudaFree(ws->tail_ring);
-    if (ws->tail_ctl) cudaFree(ws->tail_ctl);
+    if (ws->b.next_ps) cudaFree(ws->b.next_ps);
     for (auto& e : ws->poll_ev)
         if (e) cudaEventDestroy(e);
     if (ws->h_status) cudaFreeHost(ws->h_status);
@@ -1046,94 +860,13 @@ void wavefront_destroy(WavefrontState* ws) {
 
 size_t wavefront_pool(const WavefrontState* ws) { return ws ? ws->b.pool : 0; }
 
-// RT_WF_GRAIN=ring (experimental, see k_wf_ring): fill + commit + ONE persistent launch.  Returns false when the
-// pool does not fit the entry format (slot indices of 24 bits) or the counters cannot be allocated; the caller then
-// renders with the per-iteration kernels.
-static bool wavefront_render_ring(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, bool nee, size_t smem,
-                                  uint32_t slots, float4* accum, unsigned long long* ray_counter, int sm_count, cudaStream_t st,
-                                  uint32_t* launches, uint32_t* iterations) {
-    const WfBuffers& wb = ws->b;
-    if (wb.pool > (1u << 24) || wb.pool < 64u) return false;
-    WfRing rg{};
-    rg.ring = wb.queue; // [2][NQ][pool] words, used as [NQ][cap] with cap = the largest power of two <= 2 * pool
-    rg.cap_log2 = 0;
-    while ((2ull << rg.cap_log2) <= 2ull * wb.pool) ++rg.cap_log2;
-    if (!ws->ring_ctl) { // first use: counters at zero, no word of the queue memory may look like a tagged entry
-        if (cudaMalloc(&ws->ring_ctl, size_t(RingOps::RC_COUNT) * 16u * sizeof(unsigned long long)) != cudaSuccess) {
-            ws->ring_ctl = nullptr;
-            cudaGetLastError();
-            return false;
-        }
-        cudaMemsetAsync(ws->ring_ctl, 0, size_t(RingOps::RC_COUNT) * 16u * sizeof(unsigned long long), st);
-        cudaMemsetAsync(wb.queue, 0, size_t(2) * NQ * wb.pool * sizeof(uint32_t), st);
-    }
-    rg.ctl = ws->ring_ctl;
-    const uint32_t half = 1u << (rg.cap_log2 - 1u);
-    const uint32_t n = slots < half ? slots : half; // at most half a lap of entries can ever be queued
-    k_ring_fill<<<(n + 255u) / 256u, 256, 0, st>>>(rg, n);
-    k_ring_commit<<<1, 32, 0, st>>>(rg, n);
-    const unsigned cap = unsigned(sm_count) * WF_CTA_MINBLOCKS; // resident CTAs; every one of them polls for work
-    const unsigned need = (n + WF_CTA_THREADS - 1) / WF_CTA_THREADS;
-    const unsigned grid = need < cap ? need : cap;
-    if (nee) {
-        if (use_bvh) k_wf_ring<true, true><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
-        else k_wf_ring<false, true><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
-    } else {
-        if (use_bvh) k_wf_ring<true, false><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
-        else k_wf_ring<false, false><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
-    }
-    *launches = 3;
-    *iterations = 1;
-    return true;
-}
-
-// RT_WF_TAIL: finishes a frame whose paths have all started with one ring launch (see k_ring_import).  `live_max` bounds
-// the live paths (they only get fewer once no path is left to start).  False: not possible, keep iterating.
-constexpr uint32_t kTailCapLog2 = 21; // 2 Mi entries per class: room for 1 Mi live paths (half a lap)
-static bool wavefront_finish_with_ring(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, bool nee, size_t smem,
-                                       uint32_t it, uint32_t live_max, unsigned long long npaths, float4* accum,
-                                       unsigned long long* ray_counter, int sm_count, cudaStream_t st) {
-    const WfBuffers& wb = ws->b;
-    if (wb.pool > (1u << 24) || live_max == 0u || live_max > (1u << (kTailCapLog2 - 1u))) return false;
-    if (!ws->tail_ring) {
-        const size_t ring_bytes = (size_t(NQ) << kTailCapLog2) * sizeof(uint32_t);
-        const size_t ctl_bytes = size_t(RingOps::RC_COUNT) * 16u * sizeof(unsigned long long);
-        if (cudaMalloc(&ws->tail_ring, ring_bytes) != cudaSuccess || cudaMalloc(&ws->tail_ctl, ctl_bytes) != cudaSuccess) {
-            if (ws->tail_ring) cudaFree(ws->tail_ring);
-            ws->tail_ring = nullptr;
-            ws->tail_ctl = nullptr;
-            cudaGetLastError();
-            return false;
-        }
-        cudaMemsetAsync(ws->tail_ring, 0, ring_bytes, st);
-        cudaMemsetAsync(ws->tail_ctl, 0, ctl_bytes, st);
-    }
-    WfRing rg{};
-    rg.ring = ws->tail_ring;
-    rg.ctl = ws->tail_ctl;
-    rg.cap_log2 = kTailCapLog2;
-    k_ring_import<<<(live_max + 255u) / 256u, 256, 0, st>>>(wb, rg, int(it));
-    k_ring_commit_tail<<<1, 32, 0, st>>>(wb, rg, int(it), npaths);
-    const unsigned cap = unsigned(sm_count) * WF_CTA_MINBLOCKS;
-    const unsigned need = (live_max + WF_CTA_THREADS - 1) / WF_CTA_THREADS;
-    const unsigned grid = need < cap ? need : cap;
-    if (nee) {
-        if (use_bvh) k_wf_ring<true, true><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
-        else k_wf_ring<false, true><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
-    } else {
-        if (use_bvh) k_wf_ring<true, false><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
-        else k_wf_ring<false, false><<<grid, WF_CTA_THREADS, smem, st>>>(sc, rp, wb, rg, accum, ray_counter);
-    }
-    return true;
-}
-
-void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
+bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
                       unsigned long long* ray_counter, int sm_count, cudaStream_t st, uint32_t* launches,
                       uint32_t* iterations) {
     const unsigned long long npaths = (unsigned long long)rp.width * rp.height * (unsigned long long)rp.spp;
     *launches = 0;
     *iterations = 0;
-    if (npaths == 0) return;
+    if (npaths == 0) return true;
     // (every build option keeps the table under the 48 KB a kernel may use without a per-device opt-in attribute)
     static_assert(RT_PERLIN_SMEM_WORDS * sizeof(uint32_t) <= 48u * 1024u, "needs cudaFuncAttributeMaxDynamicSharedMemorySize (per device)");
     // scenes without Perlin textures leave the table out
@@ -1143,9 +876,6 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     // slots in use: never more than there are paths
     WfBuffers wb = ws->b;
     const uint32_t slots = uint32_t(npaths < wb.pool ? npaths : wb.pool);
-    if (const char* e = getenv("RT_WF_GRAIN"))
-        if (e[0] == 'r' && wavefront_render_ring(ws, sc, rp, use_bvh, nee, smem, slots, accum, ray_counter, sm_count, st, launches, iterations))
-            return;
     k_wf_init<<<(slots + 255) / 256 > 0 ? (slots + 255) / 256 : 1, 256, 0, st>>>(wb, slots);
     ++*launches;
 
@@ -1181,7 +911,8 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     // the node array, which every ray re-reads along its walk; an access-policy window marks the nodes persisting.
     bool l2_window = false;
     if (use_bvh && sc.nodes && sc.n_nodes >= RT_PT_MIN_SPHERES && !getenv("RT_NO_L2_PERSIST")) {
-        static int persist_max = -1, window_max = 0;
+        int& persist_max = ws->persist_max; // per state, i.e. per context and device (not per process)
+        int& window_max = ws->window_max;
         if (persist_max < 0) {
             int dev = 0;
             cudaGetDevice(&dev);
@@ -1261,15 +992,13 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         cudaEventRecord(ws->poll_ev[par], st);
         polled[par].it_after = it;
     };
-    // RT_WF_TAIL=<live paths>: hand the tail of the frame to one ring launch (experimental, off unless set)
-    uint32_t tail_live = 0;
-    if (const char* e = getenv("RT_WF_TAIL")) {
-        const long v = atol(e);
-        if (v > 0) tail_live = uint32_t(v < (1l << (kTailCapLog2 - 1)) ? v : (1l << (kTailCapLog2 - 1)));
-    }
-    const uint32_t generations = uint32_t((npaths + slots - 1) / slots);
-    const uint32_t max_iters = 4u * (uint32_t(rp.max_depth) + 2u) + 64u * generations;
-    enqueue(2u * generations + 4u); // a path lives ~2 iterations: enough to start most of the frame
+    // Upper bound of the iteration count: a path advances one bounce per iteration and lives at most max_depth + 2
+    // of them (ray-gen, max_depth traces, the shading step that finds the depth exhausted); while unstarted paths
+    // remain every slot is busy, so the last path starts before iteration npaths * (max_depth + 2) / slots.
+    const unsigned long long generations = (npaths + slots - 1) / slots;
+    const unsigned long long max_iters = (generations + 1ull) * ((unsigned long long)rp.max_depth + 2ull) + 64ull;
+    bool complete = false;
+    enqueue(uint32_t(2ull * generations + 4ull < max_iters ? 2ull * generations + 4ull : max_iters)); // a path lives ~2 iterations
     snapshot(0);
     int par = 0;
     while (true) {
@@ -1281,13 +1010,11 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         for (int k = 0; k < NQ; ++k)
             if (k != Q_NEW) live += c[k];
         const unsigned long long started = ws->h_status[par];
-        if (live == 0 && (started >= npaths || c[Q_NEW] == 0)) break;
-        if (tail_live && started >= npaths && live <= tail_live &&
-            wavefront_finish_with_ring(ws, sc, rp, use_bvh, nee, smem, it, uint32_t(live), npaths, accum, ray_counter, sm_count, st)) {
-            *launches += 3; // k_ring_import, k_ring_commit_tail, k_wf_ring
+        if (live == 0 && (started >= npaths || c[Q_NEW] == 0)) {
+            complete = true;
             break;
         }
-        if (it >= max_iters) break; // safety net; cannot trigger for max_depth-bounded paths
+        if (it >= max_iters) break; // a bug, not a long frame (see the bound above): reported, never a silently short frame
         par ^= 1;
     }
     *iterations = it;
@@ -1296,6 +1023,7 @@ void wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         av.accessPolicyWindow.num_bytes = 0;
         cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
     }
+    return complete;
 }
 
 } // namespace rtd

@@ -68,6 +68,21 @@ def cpu_golden():
 SCENES = ("earth_emitter", "book1_final", "perlin_motion")
 
 
+def record_parity(test: str, **values) -> None:
+    """Appends the MEASURED value behind a parity gate (PSNR dB, differing-pixel fractions, mismatch counts) to
+    gpurun_out/parity.jsonl (or $RT_PARITY_LOG), so that the numbers the assertions only bound are kept:
+    tools/parity_report.py turns the file into profiles/rNN_parity.md."""
+    import json
+
+    path = Path(os.environ.get("RT_PARITY_LOG", ROOT / "gpurun_out" / "parity.jsonl"))
+    try:
+        path.parent.mkdir(parents=True, exist_ok=True)
+        with open(path, "a") as f:
+            f.write(json.dumps({"test": test, **{k: (float(v) if hasattr(v, "__float__") else v) for k, v in values.items()}}) + "\n")
+    except OSError:
+        pass
+
+
 def make_env_image(w: int = 250, h: int = 130):
     """Procedural environment image for the reference's second scene (populate_scene_hdr, main.cu:136-182; its
     textures/hdr.jpg is not shipped).  Deliberately NOT the render size and not a multiple of 8: the reference's

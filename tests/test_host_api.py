@@ -163,3 +163,14 @@ def test_damaged_pnm_files_are_io_errors(tmp_path):
     lib.rt_free(out)
     want = (np.arange(0, 60, 10, dtype=np.float32) / np.float32(255)).reshape(2, 3, 1).repeat(3, axis=2)
     assert np.array_equal(got, want)
+
+
+def test_fastdiv_is_exact(tmp_path):
+    """rtd::FastDiv (csrc/rt_fastdiv.hpp) turns the per-path `path % pixels`, `pixel / width` of the kernels into five
+    integer instructions; the quotient must be exact for every 32-bit operand (edge values + 8.6 M random pairs)."""
+    import subprocess
+
+    exe = tmp_path / "fastdiv_check"
+    subprocess.check_call(["g++", "-std=c++17", "-O2", str(ROOT / "tests" / "fastdiv_check.cpp"), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout[-300:]
