@@ -173,7 +173,18 @@ inline float num(const json::value& o, const char* key, double dflt, bool requir
         return float(dflt);
     }
     if (v->kind != json::value::NUM) throw std::invalid_argument(std::string("scene JSON: \"") + key + "\" is not a number");
+    if (!std::isfinite(v->num) || std::fabs(v->num) > 3.0e38) throw std::invalid_argument(std::string("scene JSON: \"") + key + "\" is not a finite float");
     return float(v->num);
+}
+// integer fields (seed, object ids, frame size, sample counts): taken from the document's double — exact up to 2^53 —
+// with a range check, never through float (which rounds above 2^24) and never by casting an out-of-range value
+inline long long integer(const json::value& o, const char* key, long long dflt, long long lo, long long hi) {
+    const json::value* v = o.find(key);
+    if (!v) return dflt;
+    if (v->kind != json::value::NUM || !(v->num >= double(lo) && v->num <= double(hi)) || v->num != std::floor(v->num))
+        throw std::invalid_argument(std::string("scene JSON: \"") + key + "\" must be an integer in [" + std::to_string(lo) + ", " +
+                                    std::to_string(hi) + "]");
+    return (long long)v->num;
 }
 inline vec3 vec(const json::value& o, const char* key, vec3 dflt, bool required = false) {
     const json::value* v = o.find(key);
@@ -283,7 +294,7 @@ inline void scene_from_json(const std::string& doc_text, const std::string& base
         } else {
             throw std::invalid_argument("scene JSON: unknown object type " + type);
         }
-        made->set_id(uint32_t(num(o, "id", double(b.objects.size()))));
+        made->set_id(uint32_t(integer(o, "id", (long long)b.objects.size(), 0, 0xffffffffll)));
         b.objects.push_back(made);
     }
     const uint32_t n = uint32_t(b.objects.size());
@@ -310,11 +321,11 @@ inline void scene_from_json(const std::string& doc_text, const std::string& base
 
     if (render) {
         if (const json::value* r = doc.find("render")) {
-            render->width = int32_t(num(*r, "width", render->width));
-            render->height = int32_t(num(*r, "height", render->height));
-            render->spp = int32_t(num(*r, "spp", render->spp));
-            render->max_depth = int32_t(num(*r, "max_depth", render->max_depth));
-            render->seed = uint32_t(num(*r, "seed", render->seed));
+            render->width = int32_t(integer(*r, "width", render->width, 1, 0x7fffffffll));
+            render->height = int32_t(integer(*r, "height", render->height, 1, 0x7fffffffll));
+            render->spp = int32_t(integer(*r, "spp", render->spp, 0, 0x7fffffffll));
+            render->max_depth = int32_t(integer(*r, "max_depth", render->max_depth, 0, (1 << 23) - 1));
+            render->seed = uint32_t(integer(*r, "seed", render->seed, 0, 0xffffffffll));
             render->tmin = num(*r, "tmin", render->tmin);
             render->bloom = num(*r, "bloom", render->bloom);
             vec(*r, "world", vec3(render->world[0], render->world[1], render->world[2])).store(render->world);

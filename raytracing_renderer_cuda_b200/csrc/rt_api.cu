@@ -35,6 +35,13 @@ void set_error(const char* fmt, ...) {
 
 } // namespace
 namespace rtd {
+namespace {
+thread_local cudaMemPool_t g_thread_pool = nullptr;
+}
+void set_thread_mempool(cudaMemPool_t pool) { g_thread_pool = pool; }
+cudaError_t malloc_async_bytes(void** p, size_t bytes, cudaStream_t st) {
+    return g_thread_pool ? cudaMallocFromPoolAsync(p, bytes, g_thread_pool, st) : cudaMallocAsync(p, bytes, st);
+}
 // message hook for the host-only translation unit (rt_host.cpp), which has no CUDA error paths of its own
 void set_error_message(const char* msg) { g_last_error = msg ? msg : ""; }
 } // namespace rtd
@@ -108,6 +115,7 @@ namespace {
 
 rt_status make_current(const rt_context* ctx) {
     CUDA_TRY(cudaSetDevice(ctx->device));
+    rtd::set_thread_mempool(ctx->pool);
     return RT_OK;
 }
 
@@ -116,7 +124,7 @@ rt_status dev_alloc(rt_scene* s, T** out, size_t count) {
     *out = nullptr;
     if (count == 0) return RT_OK;
     void* p = nullptr;
-    CUDA_TRY(cudaMallocFromPoolAsync(&p, count * sizeof(T), s->ctx->pool, s->ctx->stream)); // stream-ordered pool: no map/unmap per scene
+    CUDA_TRY(cudaMallocFromPoolAsync(&p, count * sizeof(T), s->ctx->pool, s->ctx->stream)); // the context's pool: no map/unmap per scene
     s->allocs.push_back(p);
     s->info.device_bytes += count * sizeof(T);
     *out = static_cast<T*>(p);
@@ -179,7 +187,19 @@ rt_status validate_desc(const rt_scene_desc* d) {
         if (m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_EMITTER)
             ARG_CHECK(m.texture >= 0 && uint32_t(m.texture) < d->n_textures, "material texture out of range");
     }
-    for (uint32_t i = 0; i < d->n_spheres; ++i) ARG_CHECK(d->spheres[i].material < d->n_materials, "sphere material out of range");
+    // non-finite geometry would reach the builders' bin arithmetic (undefined for NaN / infinity) and the slab tests
+    auto finite3 = [](const float* v) { return std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]); };
+    for (uint32_t i = 0; i < d->n_spheres; ++i) {
+        const rt_sphere& sp = d->spheres[i];
+        ARG_CHECK(sp.material < d->n_materials, "sphere material out of range");
+        ARG_CHECK(finite3(sp.center0) && finite3(sp.center1) && std::isfinite(sp.radius) && std::isfinite(sp.time0) &&
+                      std::isfinite(sp.time1),
+                  "sphere centre / radius / time is not finite");
+    }
+    const rt_camera& c = d->camera;
+    ARG_CHECK(finite3(c.lookfrom) && finite3(c.lookat) && finite3(c.up) && std::isfinite(c.vfov) && std::isfinite(c.aspect) &&
+                  std::isfinite(c.aperture) && std::isfinite(c.focus_dist) && std::isfinite(c.time0) && std::isfinite(c.time1),
+              "camera parameter is not finite");
     return RT_OK;
 }
 
@@ -190,6 +210,9 @@ rt_status check_params(const rt_render_params* p) {
     ARG_CHECK(p->max_depth >= 0 && p->max_depth < (1 << 23), "max_depth out of range");
     ARG_CHECK(p->pipeline <= RT_PIPE_MEGAKERNEL, "bad pipeline");
     ARG_CHECK((p->flags & ~RT_RENDER_EMITTER_SAMPLING) == 0u, "unknown render flags");
+    ARG_CHECK(std::isfinite(p->tmin) && std::isfinite(p->bloom) && std::isfinite(p->world[0]) && std::isfinite(p->world[1]) &&
+                  std::isfinite(p->world[2]),
+              "tmin / bloom / world colour is not finite");
     ARG_CHECK(uint64_t(p->width) * uint64_t(p->height) < (1ull << 31), "frame has more than 2^31 pixels");
     return RT_OK;
 }
@@ -555,7 +578,7 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
         const uint32_t m = big.empty() ? n : uint32_t(normal.size());
         uint32_t* d_ids = nullptr;
         if (!big.empty()) {
-            CUDA_TRY(cudaMallocAsync(&d_ids, m * sizeof(uint32_t), stream));
+            CUDA_TRY(rtd::malloc_async(&d_ids, m * sizeof(uint32_t), stream));
             CUDA_TRY(cudaMemcpyAsync(d_ids, normal.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         }
         float rb[6];
@@ -598,7 +621,7 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     if (dnodes && n_nodes) { // the 4-wide form the persistent-lane kernel walks (half the dependent node fetches per ray)
         if ((st = dev_alloc(s, &dnodes4, n_nodes / 2 + 64)) != RT_OK) return st;
         rtd::BvhNode4* scratch = nullptr; // worst case (a degenerate chain) every binary node survives
-        CUDA_TRY(cudaMallocAsync(&scratch, size_t(n_nodes) * sizeof(rtd::BvhNode4), stream));
+        CUDA_TRY(rtd::malloc_async(&scratch, size_t(n_nodes) * sizeof(rtd::BvhNode4), stream));
         cudaError_t e = rtd::bvh_collapse4(dnodes, n_nodes, bvh_root, bstats.depth, scratch, &n_nodes4, &root4, stream);
         if (e == cudaSuccess && n_nodes4 <= n_nodes / 2 + 64) {
             e = cudaMemcpyAsync(dnodes4, scratch, size_t(n_nodes4) * sizeof(rtd::BvhNode4), cudaMemcpyDeviceToDevice, stream);
@@ -640,8 +663,8 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
         const size_t texels = size_t(im.width) * size_t(im.height);
         float* d_rgb = nullptr;
         float4* d_rgba = nullptr;
-        CUDA_TRY(cudaMallocAsync(&d_rgb, texels * 3 * sizeof(float), stream));
-        cudaError_t e = cudaMallocAsync(&d_rgba, texels * sizeof(float4), stream);
+        CUDA_TRY(rtd::malloc_async(&d_rgb, texels * 3 * sizeof(float), stream));
+        cudaError_t e = rtd::malloc_async(&d_rgba, texels * sizeof(float4), stream);
         if (e != cudaSuccess) {
             cudaFreeAsync(d_rgb, stream);
             set_error("cudaMallocAsync(image staging) failed: %s", cudaGetErrorString(e));
@@ -657,7 +680,7 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
         cudaChannelFormatDesc cd = cudaCreateChannelDesc<float4>();
         e = cudaMemcpyAsync(d_rgb, im.rgb, texels * 3 * sizeof(float), cudaMemcpyHostToDevice, stream);
         if (e == cudaSuccess) {
-            rtd::launch_rgb_to_rgba(d_rgb, d_rgba, texels, stream);
+            rtd::launch_rgb_to_rgba(d_rgb, d_rgba, texels, ctx->sm_count, stream);
             if (!arr) e = cudaMallocArray(&arr, &cd, size_t(im.width), size_t(im.height));
         }
         if (e == cudaSuccess) {
@@ -774,8 +797,8 @@ rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray*
     if (st != RT_OK) return st;
     rt_ray* d_rays = nullptr;
     rt_hit* d_hits = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_rays, n * sizeof(rt_ray), ctx->stream));
-    cudaError_t e = cudaMallocAsync(&d_hits, n * sizeof(rt_hit), ctx->stream);
+    CUDA_TRY(rtd::malloc_async(&d_rays, n * sizeof(rt_ray), ctx->stream));
+    cudaError_t e = rtd::malloc_async(&d_hits, n * sizeof(rt_hit), ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         rtd::launch_trace_primary(scene->d, d_rays, n, tmin, use_bvh, d_hits, ctx->stream);
@@ -802,8 +825,8 @@ rt_status rt_shade_probe(rt_context* ctx, const rt_scene* scene, const rt_ray* r
     if (st != RT_OK) return st;
     rt_ray* d_rays = nullptr;
     rt_shade_sample* d_out = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_rays, n * sizeof(rt_ray), ctx->stream));
-    cudaError_t e = cudaMallocAsync(&d_out, n * sizeof(rt_shade_sample), ctx->stream);
+    CUDA_TRY(rtd::malloc_async(&d_rays, n * sizeof(rt_ray), ctx->stream));
+    cudaError_t e = rtd::malloc_async(&d_out, n * sizeof(rt_shade_sample), ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         rtd::DRenderParams rp = to_device_params(*p);
@@ -858,7 +881,7 @@ rt_status rt_tonemap_device(rt_context* ctx, const void* accum_dev, int32_t widt
     rt_status st = make_current(ctx);
     if (st != RT_OK) return st;
     rtd::launch_tonemap(static_cast<const float4*>(accum_dev), width, height, static_cast<float*>(out_rgb_dev),
-                        static_cast<uint8_t*>(out_rgb8_dev), ctx->stream);
+                        static_cast<uint8_t*>(out_rgb8_dev), ctx->sm_count, ctx->stream);
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
 } RT_API_CATCH
@@ -878,7 +901,7 @@ rt_status rt_reduce_tonemap_peers(rt_context* ctx, const void* const* peer_accum
     if (st != RT_OK) return st;
     rtd::launch_reduce_tonemap(peer_accum_dev, n_peers, multicast_accum, width, height, row_begin, row_end,
                                static_cast<float*>(out_rgb_dev), static_cast<uint8_t*>(out_rgb8_dev),
-                               static_cast<float4*>(out_sum_dev), ctx->stream);
+                               static_cast<float4*>(out_sum_dev), ctx->sm_count, ctx->stream);
     CUDA_TRY(cudaGetLastError());
     return RT_OK;
 } RT_API_CATCH
@@ -895,7 +918,7 @@ rt_status rt_render(rt_context* ctx, const rt_scene* scene, const rt_render_para
     rt_stats local;
     if ((st = render_into(ctx, scene, p, ctx->accum, &local)) != RT_OK) return st;
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rtd::launch_tonemap(ctx->accum, p->width, p->height, ctx->out_rgb, nullptr, ctx->stream);
+    rtd::launch_tonemap(ctx->accum, p->width, p->height, ctx->out_rgb, nullptr, ctx->sm_count, ctx->stream);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(out_rgb, ctx->out_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -969,7 +992,7 @@ rt_status rt_render_jpeg(rt_context* ctx, const rt_scene* scene, const rt_render
     rt_stats local;
     if ((st = render_into(ctx, scene, p, ctx->accum, &local)) != RT_OK) return st;
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rtd::launch_tonemap(ctx->accum, p->width, p->height, nullptr, ctx->rgb8, ctx->stream);
+    rtd::launch_tonemap(ctx->accum, p->width, p->height, nullptr, ctx->rgb8, ctx->sm_count, ctx->stream);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
     float ms_jpg = 0.f;
@@ -1000,7 +1023,7 @@ rt_status rt_render_progressive(rt_context* ctx, const rt_scene* scene, const rt
         rt_stats local;
         if ((st = render_into(ctx, scene, &pk, ctx->accum, &local)) != RT_OK) return st;
         // the accumulator carries the sample count per pixel, so the same finalisation works after every pass
-        rtd::launch_tonemap(ctx->accum, p->width, p->height, ctx->out_rgb, nullptr, ctx->stream);
+        rtd::launch_tonemap(ctx->accum, p->width, p->height, ctx->out_rgb, nullptr, ctx->sm_count, ctx->stream);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(out_rgb, ctx->out_rgb, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1068,7 +1091,7 @@ rt_status rt_jpeg_decode(rt_context* ctx, const uint8_t* file, size_t n_bytes, f
     const int ch = img.n_comp == 1 ? 1 : 3;
     const size_t n = size_t(img.width) * size_t(img.height) * size_t(ch);
     float* d_out = nullptr;
-    CUDA_TRY(cudaMallocAsync(&d_out, n * sizeof(float), ctx->stream));
+    CUDA_TRY(rtd::malloc_async(&d_out, n * sizeof(float), ctx->stream));
     cudaError_t e = rtd::jpeg_pixels_device(img, d_out, ctx->stream, ms_device);
     float* host = e == cudaSuccess ? static_cast<float*>(malloc(n * sizeof(float))) : nullptr;
     if (e == cudaSuccess && host) {

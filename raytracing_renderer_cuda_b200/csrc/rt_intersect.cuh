@@ -102,20 +102,14 @@ RT_DEV Hit closest_hit_list(const DScene& sc, const RayQ& q, float tmin) {
     Hit best{FLT_MAX, RT_INVALID_ID};
     float t;
     if (sc.n_list != 0u) { // small scene: sphere data from the kernel parameters (constant bank, uniform loads)
-#ifdef RT_LIST_ROLLED
+        // (rolled on purpose: unrolled over the compile-time index the sphere data become immediate constant operands,
+        // but the kernel grows from 3 800 to 5 200 instructions and loses more to instruction-cache misses than the
+        // loop control costs — C1 8.01 ms unrolled, 7.41 ms rolled, 7.74 ms with the global-memory list, 8.47 ms round 1;
+        // profiles/r02_c1_instruction_diet.md)
 #pragma unroll 1
         for (uint32_t i = 0; i < sc.n_static; ++i) {
             if (sphere_root_static(q, sc.lst_a[i], tmin, t)) consider(sc, i, t, best);
         }
-#else
-        // unrolled over the compile-time index: the sphere's centre and radius are immediate constant-bank operands of
-        // the FADD/FFMA instructions — no load, no address, no loop counter
-#pragma unroll
-        for (uint32_t i = 0; i < RT_LIST_MAX; ++i) {
-            if (i >= sc.n_static) break;
-            if (sphere_root_static(q, sc.lst_a[i], tmin, t)) consider(sc, i, t, best);
-        }
-#endif
 #pragma unroll 1
         for (uint32_t i = sc.n_static; i < sc.n_spheres; ++i) {
             if (sphere_root_moving(q, sc.lst_a[i], sc.lst_b[i], sc.lst_dt[i], tmin, t)) consider(sc, i, t, best);

@@ -630,6 +630,7 @@ bool grow(T*& p, size_t& cap, size_t need) {
 } // namespace
 
 struct JpegState {
+    int sm_count = 0; // of the device the state was created on (launch sizing)
     JpegTables* d_tab = nullptr;
     int quality = -1;
     std::vector<uint8_t> header;
@@ -659,7 +660,10 @@ struct JpegState {
 
 JpegState* jpeg_create() {
     JpegState* s = new JpegState();
-    bool ok = cudaMalloc(&s->d_tab, sizeof(JpegTables)) == cudaSuccess;
+    int dev = 0;
+    bool ok = cudaGetDevice(&dev) == cudaSuccess &&
+              cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_tab, sizeof(JpegTables)) == cudaSuccess;
     ok = ok && cudaMallocHost(&s->h_pin, 2 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaEventCreate(&s->ev[0]) == cudaSuccess && cudaEventCreate(&s->ev[1]) == cudaSuccess;
     if (!ok) {
@@ -733,7 +737,8 @@ cudaError_t jpeg_encode(JpegState* s, const uint8_t* rgb8_dev, int w, int h, int
                                                                                                    s->d_tab, s->coef, s->ac_bits);
     }
     unsigned ent_grid = unsigned((n_blocks + JPG_ENT_THREADS / 32 - 1) / (JPG_ENT_THREADS / 32));
-    if (ent_grid > 148u * 8u) ent_grid = 148u * 8u; // persistent warps, 8 CTAs of 256 threads per SM
+    const unsigned ent_cap = unsigned(s->sm_count > 0 ? s->sm_count : 1) * 8u; // persistent warps, 8 CTAs of 256 threads per SM
+    if (ent_grid > ent_cap) ent_grid = ent_cap;
     JPG_TRY(cudaMemsetAsync(s->bits + n_blocks, 0, sizeof(unsigned long long), st));
     if (s->subsample)
         k_jpeg_entropy<false><<<ent_grid, JPG_ENT_THREADS, 0, st>>>(s->coef, uint32_t(n_blocks), 1, s->d_tab, s->bits, nullptr, nullptr);

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "rt_jpeg_decode.cuh"
+#include "rt_kernels.cuh"
 
 namespace rtd {
 
@@ -249,13 +250,13 @@ cudaError_t jpeg_pixels_device(const rtj::CoefficientImage& img, float* out_dev,
         int16_t* d_coeff = nullptr;
         uint8_t* d_plane = nullptr;
         int *d_near = nullptr, *d_far = nullptr;
-        JD_TRY(cudaMallocAsync(&d_coeff, c.coeff.size() * sizeof(int16_t), st));
+        JD_TRY(rtd::malloc_async(&d_coeff, c.coeff.size() * sizeof(int16_t), st));
         owned.push_back(d_coeff);
-        JD_TRY(cudaMallocAsync(&d_plane, size_t(c.w2) * c.h2, st));
+        JD_TRY(rtd::malloc_async(&d_plane, size_t(c.w2) * c.h2, st));
         owned.push_back(d_plane);
-        JD_TRY(cudaMallocAsync(&d_near, size_t(img.height) * sizeof(int), st));
+        JD_TRY(rtd::malloc_async(&d_near, size_t(img.height) * sizeof(int), st));
         owned.push_back(d_near);
-        JD_TRY(cudaMallocAsync(&d_far, size_t(img.height) * sizeof(int), st));
+        JD_TRY(rtd::malloc_async(&d_far, size_t(img.height) * sizeof(int), st));
         owned.push_back(d_far);
         JD_TRY(cudaMemcpyAsync(d_coeff, c.coeff.data(), c.coeff.size() * sizeof(int16_t), cudaMemcpyHostToDevice, st));
         jpeg_row_tables(img, k, rows[2 * k], rows[2 * k + 1]);

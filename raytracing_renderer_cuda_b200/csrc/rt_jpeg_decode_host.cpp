@@ -19,13 +19,19 @@ const uint8_t kDezigzag[64 + 15] = { // position in the zigzag stream -> row-maj
     39, 46, 53, 60, 61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
 
 struct Huffman { // stb:1875-1886, 1942-1984
-    uint8_t values[256];
-    uint8_t size[257];
-    uint32_t maxcode[18];
-    int delta[17];
-    uint16_t code[256];
-    uint8_t fast[512]; // top 9 bits of the stream -> index into values[], 255 = longer code
+    uint8_t values[256] = {};
+    uint8_t size[257] = {};
+    uint32_t maxcode[18] = {};
+    int delta[17] = {};
+    uint16_t code[256] = {};
+    uint8_t fast[512] = {}; // top 9 bits of the stream -> index into values[], 255 = longer code
+    bool defined = false;   // a DHT segment has filled this table (a scan that selects an undefined one is rejected)
+    Huffman() {
+        memset(fast, 255, sizeof fast);
+        maxcode[17] = 0xffffffffu; // the sentinel of the code-length search, whatever happens to the table later
+    }
     bool build(const int* count) {
+        defined = false;
         int k = 0;
         for (int i = 0; i < 16; ++i)
             for (int j = 0; j < count[i]; ++j) {
@@ -54,6 +60,7 @@ struct Huffman { // stb:1875-1886, 1942-1984
                 for (int q = 0; q < m; ++q) fast[c + q] = uint8_t(i);
             }
         }
+        defined = true;
         return true;
     }
 };
@@ -507,6 +514,14 @@ struct Decoder {
         } else {
             if (spec_start != 0 || succ_high != 0 || succ_low != 0) return fail("bad SOS");
             spec_end = 63;
+        }
+        // the tables this scan decodes with must exist by now (stb decodes against whatever its table memory holds;
+        // here that would be undefined behaviour on untrusted input).  Refinement scans of DC coefficients read raw bits.
+        for (int i = 0; i < scan_n; ++i) {
+            const auto& c = img.comp[order[i]];
+            const bool needs_dc = img.progressive ? (spec_start == 0 && succ_high == 0) : true;
+            const bool needs_ac = img.progressive ? spec_start != 0 : true;
+            if ((needs_dc && !huff_dc[c.hd].defined) || (needs_ac && !huff_ac[c.ha].defined)) return fail("undefined huffman table");
         }
         return true;
     }

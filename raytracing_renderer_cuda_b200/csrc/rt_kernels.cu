@@ -243,22 +243,26 @@ __global__ void __launch_bounds__(256) k_reduce_tonemap(const __grid_constant__ 
 }
 
 void launch_reduce_tonemap(const void* const* peer_accum, int n_peers, const void* multicast, int width, int height,
-                           int row_begin, int row_end, float* out_rgb, uint8_t* out_rgb8, float4* out_sum, cudaStream_t st) {
+                           int row_begin, int row_end, float* out_rgb, uint8_t* out_rgb8, float4* out_sum, int sm_count,
+                           cudaStream_t st) {
     if (row_end <= row_begin || width <= 0) return;
     PeerPtrs pp{};
-    for (int k = 0; k < n_peers && k < 16; ++k) pp.p[k] = static_cast<const float4*>(peer_accum[k]);
+    if (peer_accum) // (NULL with a multicast address: the kernel then never reads the table)
+        for (int k = 0; k < n_peers && k < 16; ++k) pp.p[k] = static_cast<const float4*>(peer_accum[k]);
     size_t npix = size_t(row_end - row_begin) * size_t(width);
     size_t want = (npix + 255) / 256;
-    unsigned blocks = unsigned(want < 148 * 8 ? want : 148 * 8);
+    const size_t cap = size_t(sm_count > 0 ? sm_count : 1) * 8u; // 8 CTAs of 256 threads per SM, grid-stride beyond
+    unsigned blocks = unsigned(want < cap ? want : cap);
     k_reduce_tonemap<<<blocks, 256, 0, st>>>(pp, n_peers, static_cast<const float4*>(multicast), width, height, row_begin, row_end,
                                              out_rgb, out_rgb8, out_sum);
 }
 
-void launch_tonemap(const float4* accum, int width, int height, float* out_rgb, uint8_t* out_rgb8, cudaStream_t st) {
+void launch_tonemap(const float4* accum, int width, int height, float* out_rgb, uint8_t* out_rgb8, int sm_count, cudaStream_t st) {
     size_t npix = size_t(width) * height;
     if (npix == 0) return;
     size_t want = (npix + 255) / 256;
-    unsigned blocks = unsigned(want < 148 * 16 ? want : 148 * 16);
+    const size_t cap = size_t(sm_count > 0 ? sm_count : 1) * 16u;
+    unsigned blocks = unsigned(want < cap ? want : cap);
     k_tonemap<<<blocks, 256, 0, st>>>(accum, width, height, out_rgb, out_rgb8);
 }
 
@@ -267,10 +271,11 @@ __global__ void __launch_bounds__(256) k_rgb_to_rgba(const float* __restrict__ r
         rgba[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 1.f);
 }
 
-void launch_rgb_to_rgba(const float* rgb, float4* rgba, size_t n_texels, cudaStream_t st) {
+void launch_rgb_to_rgba(const float* rgb, float4* rgba, size_t n_texels, int sm_count, cudaStream_t st) {
     if (n_texels == 0) return;
     size_t want = (n_texels + 255) / 256;
-    unsigned blocks = unsigned(want < 148 * 16 ? want : 148 * 16);
+    const size_t cap = size_t(sm_count > 0 ? sm_count : 1) * 16u;
+    unsigned blocks = unsigned(want < cap ? want : cap);
     k_rgb_to_rgba<<<blocks, 256, 0, st>>>(rgb, rgba, n_texels);
 }
 

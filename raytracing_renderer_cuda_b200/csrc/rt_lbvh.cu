@@ -5,6 +5,7 @@
 // single-thread recursive median split with an in-thread sort per level (bvh.h:75-113),
 // which is O(N log^2 N) on one GPU thread and cannot build 10^6 primitives in useful time.
 #include "rt_lbvh.cuh"
+#include "rt_kernels.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -301,12 +302,12 @@ cudaError_t bvh_collapse4(const BvhNode* nodes, uint32_t n_nodes, uint32_t root,
             return e_;          \
         }                       \
     } while (0)
-    C4_TRY(cudaMallocAsync(&wide, size_t(n_nodes) * sizeof(BvhNode4), st));
-    C4_TRY(cudaMallocAsync(&level, size_t(n_nodes + 1) * sizeof(uint32_t), st));
-    C4_TRY(cudaMallocAsync(&used, size_t(n_nodes + 1) * sizeof(uint32_t), st));
-    C4_TRY(cudaMallocAsync(&idx, size_t(n_nodes + 1) * sizeof(uint32_t), st));
+    C4_TRY(rtd::malloc_async(&wide, size_t(n_nodes) * sizeof(BvhNode4), st));
+    C4_TRY(rtd::malloc_async(&level, size_t(n_nodes + 1) * sizeof(uint32_t), st));
+    C4_TRY(rtd::malloc_async(&used, size_t(n_nodes + 1) * sizeof(uint32_t), st));
+    C4_TRY(rtd::malloc_async(&idx, size_t(n_nodes + 1) * sizeof(uint32_t), st));
     C4_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, used, idx, int(n_nodes + 1), st));
-    C4_TRY(cudaMallocAsync(&tmp, tmp_bytes, st));
+    C4_TRY(rtd::malloc_async(&tmp, tmp_bytes, st));
     const unsigned blocks = (n_nodes + 255) / 256;
     k_collapse4<<<blocks, 256, 0, st>>>(nodes, n_nodes, wide);
     C4_TRY(cudaMemsetAsync(level, 0, size_t(n_nodes + 1) * sizeof(uint32_t), st));
@@ -356,18 +357,18 @@ cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n_stat
             return e;          \
         }                      \
     } while (0)
-    LB_TRY(cudaMallocAsync(&lo, n * sizeof(float4), st));
-    LB_TRY(cudaMallocAsync(&hi, n * sizeof(float4), st));
-    LB_TRY(cudaMallocAsync(&keys, n * sizeof(unsigned long long), st));
-    LB_TRY(cudaMallocAsync(&keys_out, n * sizeof(unsigned long long), st));
-    LB_TRY(cudaMallocAsync(&vals, n * sizeof(uint32_t), st));
-    LB_TRY(cudaMallocAsync(&vals_out, n * sizeof(uint32_t), st));
-    LB_TRY(cudaMallocAsync(&parent_inner, n * sizeof(int), st));
-    LB_TRY(cudaMallocAsync(&parent_leaf, n * sizeof(int), st));
-    LB_TRY(cudaMallocAsync(&visits, n * sizeof(unsigned), st));
-    LB_TRY(cudaMallocAsync(&scal, 16 * sizeof(unsigned), st));
+    LB_TRY(rtd::malloc_async(&lo, n * sizeof(float4), st));
+    LB_TRY(rtd::malloc_async(&hi, n * sizeof(float4), st));
+    LB_TRY(rtd::malloc_async(&keys, n * sizeof(unsigned long long), st));
+    LB_TRY(rtd::malloc_async(&keys_out, n * sizeof(unsigned long long), st));
+    LB_TRY(rtd::malloc_async(&vals, n * sizeof(uint32_t), st));
+    LB_TRY(rtd::malloc_async(&vals_out, n * sizeof(uint32_t), st));
+    LB_TRY(rtd::malloc_async(&parent_inner, n * sizeof(int), st));
+    LB_TRY(rtd::malloc_async(&parent_leaf, n * sizeof(int), st));
+    LB_TRY(rtd::malloc_async(&visits, n * sizeof(unsigned), st));
+    LB_TRY(rtd::malloc_async(&scal, 16 * sizeof(unsigned), st));
     LB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, vals_out, int(n), 0, 63, st));
-    LB_TRY(cudaMallocAsync(&tmp, tmp_bytes, st));
+    LB_TRY(rtd::malloc_async(&tmp, tmp_bytes, st));
     LB_TRY(cudaEventCreate(&e0));
     LB_TRY(cudaEventCreate(&e1));
 

@@ -116,3 +116,35 @@ def test_reference_texture_decodes_to_the_bytes_stb_decodes():
     got = _decode_cpu(data)
     assert np.array_equal(got, oa.ref_stb_load_jpeg(data))
     assert np.array_equal(got, np.asarray(Image.open(ROOT / "assets" / "earth_stb.png").convert("RGB")))
+
+
+def _strip_segments(data: bytes, marker: int) -> bytes:
+    """removes every segment with the given marker from the header part of a JPEG file (up to the first SOS)"""
+    out, i = bytearray(data[:2]), 2
+    while i + 4 <= len(data) and data[i] == 0xFF:
+        m, ln = data[i + 1], (data[i + 2] << 8) | data[i + 3]
+        if m == 0xDA:
+            break
+        if m != marker:
+            out += data[i:i + 2 + ln]
+        i += 2 + ln
+    return bytes(out + data[i:])
+
+
+def test_scan_that_selects_an_undefined_huffman_table_is_rejected(golden):
+    """the tables were uninitialised until a DHT segment filled them, so a file whose scan names a table that
+    was never defined decoded against stack garbage (out-of-bounds reads in the code-length search).  Such a file is now
+    an error, for baseline and progressive files alike, and the outcome is deterministic."""
+    tried = 0
+    for key in list(golden.files)[:12]:
+        if not key.startswith("file"):
+            continue
+        data = golden[key].tobytes()
+        cut = _strip_segments(data, 0xC4)
+        assert len(cut) < len(data)
+        for _ in range(2):
+            with pytest.raises(capi.RtError) as e:
+                capi.jpeg_parse(cut)
+            assert e.value.status == capi.RT_ERR_INVALID_ARG and "huffman" in str(e.value)
+        tried += 1
+    assert tried >= 4

@@ -112,3 +112,25 @@ def test_cli_help_runs():
         subprocess.check_call(["make", "-C", str(ROOT / "apps")])
     out = subprocess.run([str(app), "--help"], capture_output=True, text=True)
     assert out.returncode == 0 and "--scene" in out.stdout and "--quality" in out.stdout
+
+
+def test_integer_fields_are_exact_and_range_checked():
+    """seed / ids went through float (123456789 became 123456792) and out-of-range values were cast (UB)."""
+    doc = {"camera": {"lookfrom": [0, 0, 1], "lookat": [0, 0, 0]},
+           "textures": {"a": {"type": "constant", "color": [0.1, 0.2, 0.3]}}, "materials": {"l": {"type": "lambertian", "texture": "a"}},
+           "objects": [{"type": "sphere", "center": [0, 0, 0], "radius": 1, "material": "l", "id": 4000000001}],
+           "render": {"seed": 123456789, "width": 16777217, "height": 1}}
+    p = rt.default_params()
+    owner = rt.SceneDesc.from_json(json.dumps(doc), params=p)
+    assert p.seed == 123456789 and p.width == 16777217
+    assert int(owner.spheres()["id"][0]) == 4000000001
+    for key, bad in (("seed", -1), ("seed", 2 ** 32), ("spp", 1.5), ("width", 0), ("max_depth", 2 ** 23)):
+        d2 = json.loads(json.dumps(doc))
+        d2["render"][key] = bad
+        with pytest.raises(capi.RtError) as e:
+            rt.SceneDesc.from_json(json.dumps(d2), params=rt.default_params())
+        assert e.value.status == capi.RT_ERR_INVALID_ARG and key in str(e.value)
+    d3 = json.loads(json.dumps(doc))
+    d3["objects"][0]["radius"] = 1e39  # not a finite float
+    with pytest.raises(capi.RtError):
+        rt.SceneDesc.from_json(json.dumps(d3))
