@@ -6,6 +6,7 @@
 //   render_scene [scene] [width height spp] [out] [earth.ppm]            (positional, as before)
 //   render_scene --scene <name | file.json> [--width W --height H --spp N --depth D --seed S]
 //                [--out render.jpg|.ppm] [--quality 100] [--earth assets/earth_stb.ppm] [--passes K] [--emitter-sampling]
+//                [--gpus N]
 //     scene: earth_emitter (default) | book1_final | perlin_motion | random_spheres:N | a JSON document
 //            (include/rt/scene_json.hpp; the reference's compile-time scene and WIDTH/HEIGHT/SAMPLES_PER_PIXEL/SEED
 //            macros, main.cu:15,188-356, common.h:13-20, become runtime input)
@@ -14,6 +15,9 @@
 //     --emitter-sampling: RT_RENDER_EMITTER_SAMPLING — lambertian hits aim half of their scatter directions at the
 //            emitter spheres and weight the path accordingly (the reference README's "Improve Sampling on emitter
 //            objects", README.md:27-28); same expected image, less noise where emitters light the scene
+//     --gpus N: N devices from this one process (rt_multi_*; 0 = every visible device): the samples per pixel are split
+//            across the devices, the float4 accumulators are summed and finalised by one fused kernel per device over
+//            NVLink peer memory.  The output file is written from the 8-bit frame (JPEG through rt_jpeg_encode).
 //     --passes K: progressive accumulation, K passes of --spp samples each into one accumulator; the output file is
 //            rewritten after every pass (PPM only)
 //
@@ -45,6 +49,7 @@ int main(int argc, char** argv) {
     std::string scene_name = "earth_emitter", out_path = "render.jpg", earth_path = "assets/earth_stb.ppm";
     int quality = 100; // main.cu:491
     int passes = 1;
+    int gpus = 1; // 1: the single-device path below; anything else: rt_multi_*
     bool emitter_sampling = false;
     rt_render_params p;
     rt_default_render_params(&p); // 1200x600x100, depth 50, seed 1000, tmin 1e-5 (common.h:13-20, main.cu:15,45)
@@ -69,10 +74,11 @@ int main(int argc, char** argv) {
         else if (a == "--quality") quality = atoi(next("--quality"));
         else if (a == "--earth") earth_path = next("--earth");
         else if (a == "--passes") passes = atoi(next("--passes"));
+        else if (a == "--gpus") gpus = atoi(next("--gpus"));
         else if (a == "--emitter-sampling") emitter_sampling = true;
         else if (a == "--help" || a == "-h") {
             printf("render_scene --scene <name|file.json> [--width W --height H --spp N --depth D --seed S] [--out f.jpg|f.ppm] "
-                   "[--quality Q] [--earth earth.ppm] [--passes K] [--emitter-sampling]\n");
+                   "[--quality Q] [--earth earth.ppm] [--passes K] [--emitter-sampling] [--gpus N]\n");
             return 0;
         } else pos.push_back(a);
     }
@@ -124,6 +130,25 @@ int main(int argc, char** argv) {
     }
 
     if (emitter_sampling) p.flags |= RT_RENDER_EMITTER_SAMPLING;
+    if (gpus != 1) { // several devices, one process
+        rt_multi* m = nullptr;
+        CHECK(rt_multi_create(nullptr, gpus, &m));
+        CHECK(rt_multi_set_scene(m, &desc));
+        printf("Rendering a %dx%d image (%d samples per pixel) on %d devices\n", p.width, p.height, p.spp, rt_multi_size(m));
+        std::vector<uint8_t> img(size_t(p.width) * p.height * 3);
+        rt_stats st;
+        float ms_reduce = 0.f;
+        CHECK(rt_multi_render(m, &p, nullptr, img.data(), &st, &ms_reduce));
+        printf("took %.0fus.  (%.1f Mpaths/s, %.1f Mrays/s over %d devices; slowest device %.3f ms, fused reduce + finalisation %.3f ms)\n",
+               st.ms_d2h * 1e3, st.paths / st.ms_d2h / 1e3, st.rays / st.ms_d2h / 1e3, rt_multi_size(m), st.ms_total, ms_reduce);
+        if (ends_with(out_path, ".jpg") || ends_with(out_path, ".jpeg")) CHECK(rt_write_jpg(ctx, out_path.c_str(), p.width, p.height, img.data(), quality));
+        else CHECK(rt_write_ppm(out_path.c_str(), p.width, p.height, img.data()));
+        rt_multi_destroy(m);
+        rt_context_destroy(ctx);
+        rt_free(earth);
+        rt_scene_desc_free(json_desc);
+        return 0;
+    }
     rt_scene* scene = nullptr;
     CHECK(rt_scene_create(ctx, &desc, &scene));
     rt_scene_info info;

@@ -3,17 +3,23 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4|c5] [--impl ours|reference]
 
-A "step" is one frame of the configured scene: zero the float4 accumulator, render `spp`
-samples per pixel into it (wavefront pipeline, librt_b200.so), [N > 1: sum the accumulators of
-all ranks onto rank 0 with one NCCL reduce over NVLink], tonemap (/spp, saturate, sqrt) and
-quantise on the device.  N > 1 shards SAMPLES: rank r renders sample indices [r*spp, (r+1)*spp)
-of every pixel, so the job renders N*spp samples per pixel ("weak" scaling: per-GPU work fixed).
+A "step" is one frame of the configured scene: zero the float4 accumulator, render `spp` samples per pixel into it
+(wavefront pipeline, librt_b200.so), sum the accumulators of all ranks and finalise (/spp, saturate, sqrt, Y-flip +
+quantise) on the device.  N > 1 shards SAMPLES through the C-ABI's rt_group_* entries (one process per GPU, CUDA IPC peer
+mappings, flag barriers, one fused peer-load reduce + finalisation kernel per GPU over NVLink): rank r renders sample
+indices [r*spp, (r+1)*spp) of every pixel, so the job renders N*spp samples per pixel ("weak" scaling: per-GPU work fixed).
+torch / torch.distributed are plumbing only: device selection, the stream, timing events, the barrier around the timed
+region and the all_gather that carries the IPC handles.
 
-`value` is device-timed (CUDA events on the stream the kernels run on) with the scene resident
-in HBM; `e2e` goes through the C-ABI with HOST buffers: scene upload (H2D) + render + read-back
-of the finished frame (D2H) inside the timed region.  `--impl reference` times the reference's
-own main.cu rebuilt unchanged for sm_100 (oracle/_ref/ref_main: BASELINE.json's stated baseline —
-the reference ships no CPU renderer) for c1, and the reference harness for the other configs.
+`value` is device-timed (CUDA events on the stream the kernels run on) with the scene resident in HBM; `e2e` goes through
+the C-ABI with HOST buffers: scene upload (H2D) + render + read-back of the finished frame (D2H) inside the timed region.
+The N = 1 line also carries `other_configs` (short C2 / C3 / C4 lines, each with the roofline that bounds it); an N > 1 line
+carries `c5` (the 8K frame: 531 MB accumulators, reduce time and NVLink GB/s broken out) and `strong` (a FIXED number of
+samples per pixel split across the ranks).
+
+`--impl reference` times the reference's own main.cu rebuilt unchanged for sm_100 (oracle/_ref/ref_main: BASELINE.json's
+stated baseline — the reference ships no CPU renderer) for c1, and the reference harness for the other configs; that arm
+never loads librt_b200.so: the scenes are flat files written at build time (oracle/_ref/scenes/) and read with pure ctypes.
 The `cpu_baseline` leg times the reference headers compiled for the host cores on a bounded sample.
 """
 from __future__ import annotations
@@ -47,7 +53,9 @@ CONFIGS = {
                name="C5 book-1 final 7680x4320, 16 spp per step and GPU (4096 spp = 256 steps)"),
 }
 FLOP_PER_RAY = {"c1": 420.0, "c2": 420.0, "c3": 615.0, "c4": 815.0, "c5": 420.0}  # SURVEY.md §8(d), frozen
+NODE_BYTES_PER_RAY_C4 = 1340.0                                                     # BVH node traffic of a C4 ray
 STATE_BYTES_PER_RAY = 120.0
+NVLINK_PEER_GBS = 770.0  # measured peer copy per direction per GPU on this pool (B200_PROFILING.md)
 
 
 def load_peaks():
@@ -112,8 +120,9 @@ def cpu_baseline(cfg_key: str, desc, target_s: float = 12.0) -> dict:
     cfg = CONFIGS[cfg_key]
     cores = os.cpu_count() or 1
     w, h = cfg["width"] // 4, cfg["height"] // 4
-
-    import raytracing_renderer_cuda_b200 as rt
+    rt = None
+    if not oa.REFCPU_RN_SO.exists():
+        import raytracing_renderer_cuda_b200 as rt  # (the oracle port's parameter block comes from the product's defaults)
 
     if oa.REFCPU_RN_SO.exists():
         kind = "reference"
@@ -146,13 +155,13 @@ def cpu_baseline(cfg_key: str, desc, target_s: float = 12.0) -> dict:
             + ("reference headers via oracle/shim, _rz intrinsics rounding to nearest" if kind == "reference" else "oracle/rt_oracle.cpp")}
 
 
-def build_desc(cfg_key: str):
+def build_desc(cfg_key: str, n_override: int = 0):
     import raytracing_renderer_cuda_b200 as rt
     from raytracing_renderer_cuda_b200.assets import load_earth
 
     cfg = CONFIGS[cfg_key]
     image = load_earth() if cfg["scene"] == "earth_emitter" else None
-    return rt.SceneDesc.builtin(cfg["scene"], image, n=cfg["n"])
+    return rt.SceneDesc.builtin(cfg["scene"], image, n=n_override or cfg["n"])
 
 
 def desc_h2d_bytes(desc) -> int:
@@ -165,13 +174,175 @@ def desc_h2d_bytes(desc) -> int:
     return int(b)
 
 
+def kernel_name_of(info) -> str:
+    return ("k_wf_step_pt" if int(info.n_spheres) >= 4096 else "k_wf_step_warp") if int(info.n_nodes) else "k_wf_step_cta"
+
+
+def measure_l2_gbs(torch, stream) -> float:
+    """L2 bandwidth the way MEASURED_PEAKS.json measures HBM: a plain device copy, here of a working set that stays in the
+    126 MB L2 (2 x 16 MiB), read + write bytes, best of 5 batches of 50 copies."""
+    a = torch.empty(16 << 20, dtype=torch.uint8, device="cuda")
+    b = torch.empty_like(a)
+    a.fill_(1)
+    for _ in range(10):
+        b.copy_(a)
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(50):
+            b.copy_(a)
+        e1.record(stream)
+        e1.synchronize()
+        best = max(best, 50 * 2 * a.numel() / (e0.elapsed_time(e1) / 1e3) / 1e9)
+    return best
+
+
 # ------------------------------------------------------------------------------------------ ours
+class FrameLoop:
+    """One configuration on this rank: scene, accumulator, the per-step sequence, device timing."""
+
+    def __init__(self, torch, dist, rt, ctx, stream, cfg_key, spp_rank, sample_offset, rank, world, collective, n_override=0):
+        self.torch, self.dist, self.rt, self.ctx, self.stream = torch, dist, rt, ctx, stream
+        self.cfg_key, self.cfg, self.rank, self.world = cfg_key, CONFIGS[cfg_key], rank, world
+        self.W, self.H, self.spp = self.cfg["width"], self.cfg["height"], spp_rank
+        self.desc = build_desc(cfg_key, n_override)
+        self.scene = rt.Scene(ctx, self.desc)
+        self.info = self.scene.info()
+        self.params = rt.default_params(width=self.W, height=self.H, spp=spp_rank, sample_offset=sample_offset)
+        self.group, self.symm = None, None
+        self.collective = "none"
+        H, W = self.H, self.W
+        if world > 1 and collective in ("auto", "ipc"):
+            def exchange(blob):
+                table = [None] * world
+                dist.all_gather_object(table, blob)
+                return table
+
+            self.group = rt.Group(ctx, rank, world, W, H, exchange)
+            self.accum_ptr = self.group.accum_ptr
+            self.collective = "rt_group (C-ABI): CUDA IPC peer mappings + flag barriers + fused peer-load reduce/finalise kernel over NVLink"
+        elif world > 1 and collective in ("multimem", "peer"):
+            import torch.distributed._symmetric_memory as symm
+
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self.accum = symm.empty((H, W, 4), dtype=torch.float32, device=dev)
+            self.rgb = symm.empty((H, W, 3), dtype=torch.float32, device=dev)
+            self.rgb8 = symm.empty((H, W, 3), dtype=torch.uint8, device=dev)
+            hdl = symm.rendezvous(self.accum, dist.group.WORLD)
+            h_rgb, h_rgb8 = symm.rendezvous(self.rgb, dist.group.WORLD), symm.rendezvous(self.rgb8, dist.group.WORLD)
+            mc = int(hdl.multicast_ptr or 0) if collective == "multimem" else 0
+            self.symm = dict(hdl=hdl, peers=[int(p) for p in hdl.buffer_ptrs], mc=mc, rgb=int(h_rgb.buffer_ptrs[0]), rgb8=int(h_rgb8.buffer_ptrs[0]),
+                             rows=rt.shard_rows(H, rank, world))
+            self.accum_ptr = self.accum.data_ptr()
+            self.collective = "A/B: torch symmetric memory + " + ("NVLS multimem.ld_reduce" if mc else "NVLink peer loads") + " in the fused kernel"
+        else:
+            self.accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+            self.rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+            self.rgb8 = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+            self.accum_ptr = self.accum.data_ptr()
+            if world > 1:
+                self.collective = "A/B: NCCL reduce(SUM) to rank 0 + tonemap"
+
+    # -- the step --
+    def begin(self):
+        if self.group is not None:
+            self.group.begin_frame()
+        else:
+            self.accum.zero_()
+
+    def render(self, want_stats=False):
+        return self.scene.render_accum_device(self.params, self.accum_ptr, want_stats=want_stats)
+
+    def finish(self):
+        """sum over ranks + pixel finalisation; the frame ends up on rank 0"""
+        rt = self.rt
+        if self.group is not None:
+            self.group.finish_frame(want_rgb8=True)
+        elif self.symm is not None:
+            s = self.symm
+            s["hdl"].barrier(0)
+            rt.reduce_tonemap_peers(self.ctx, s["peers"], s["mc"], self.W, self.H, s["rows"][0], s["rows"][1], s["rgb"], s["rgb8"])
+            s["hdl"].barrier(1)
+        else:
+            if self.world > 1:
+                self.dist.reduce(self.accum, dst=0, op=self.dist.ReduceOp.SUM)
+            if self.rank == 0:
+                rt.tonemap_device(self.ctx, self.accum_ptr, self.W, self.H, self.rgb.data_ptr(), self.rgb8.data_ptr())
+
+    def step(self):
+        self.begin()
+        self.render()
+        self.finish()
+
+    def sync_all(self):
+        self.stream.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, steps, warmup, flush):
+        """-> (ms per step, ms of the render span, ms of the finish span, rays of this rank per step, launches, iterations)"""
+        torch, stream = self.torch, self.stream
+        self.begin()
+        st = self.render(want_stats=True)  # deterministic: the RNG is keyed on pixel/sample/bounce
+        self.finish()
+        rays, launches, iters = int(st.rays), int(st.launches), int(st.iterations)
+        for _ in range(warmup):
+            self.step()
+        self.sync_all()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+        for k in range(steps):
+            flush.fill_(k & 255)  # L2 flush between timed iterations, outside the timed span
+            ev[k][0].record(stream)
+            self.begin()
+            ev[k][1].record(stream)
+            self.render()
+            ev[k][2].record(stream)
+            self.finish()
+            ev[k][3].record(stream)
+        self.sync_all()
+        ms = float(np.mean([e[0].elapsed_time(e[3]) for e in ev]))
+        ms_render = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+        ms_finish = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
+        return ms, ms_render, ms_finish, rays, launches, iters
+
+    def close(self):
+        if self.group is not None:
+            self.group.close()
+        self.scene.close()
+
+
+def roofline_of(cfg_key, rays_rank, ms_render, n_step_launches, peaks, l2_gbs, kernel_name):
+    fp32_peak = peaks["sm_count"] * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s at the measured max SM clock
+    flop_launch = rays_rank / n_step_launches * FLOP_PER_RAY[cfg_key]
+    dur_launch_s = ms_render / 1e3 / n_step_launches
+    fp32 = flop_launch / dur_launch_s / 1e12
+    hbm = rays_rank * STATE_BYTES_PER_RAY / (ms_render / 1e3) / 1e9
+    common = {"kernel": kernel_name, "launches_per_step": n_step_launches, "avg_launch_ms": dur_launch_s * 1e3}
+    if cfg_key == "c4":
+        # SURVEY 8d: a C4 ray is bound by the L2 -> SM bandwidth of its BVH node fetches (1.34 KB of nodes per ray, served by L2:
+        # the node array is pinned there), not by FP32 issue
+        l2 = rays_rank * NODE_BYTES_PER_RAY_C4 / (ms_render / 1e3) / 1e9
+        return {"bound": "l2", "achieved": l2, "peak": l2_gbs, "unit": "GB/s", "frac": l2 / l2_gbs if l2_gbs else None, "traffic": None,
+                "bytes_per_ray": NODE_BYTES_PER_RAY_C4,
+                "peak_source": "L2-resident device copy (2 x 16 MiB, read + write) measured by this run, the method of MEASURED_PEAKS.json's hbm_gbs",
+                "fp32": {"achieved": fp32, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32 / fp32_peak, "flop_per_ray": FLOP_PER_RAY[cfg_key]},
+                **common}
+    return {"bound": "fp32", "achieved": fp32, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32 / fp32_peak, "traffic": None,
+            "flop_per_ray": FLOP_PER_RAY[cfg_key],
+            "peak_source": f"{peaks['sm_count']} SM x 128 lanes x 2 flop x {peaks['sm_max_mhz']:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peaks['source']})",
+            "note": "no dense contraction and L2-resident state: the bounding roofline is FP32 issue (SURVEY.md 8d), not hbm/tensor",
+            "hbm": {"achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"],
+                    "bytes_per_ray": STATE_BYTES_PER_RAY, "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})"},
+            **common}
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
     import raytracing_renderer_cuda_b200 as rt
-    from raytracing_renderer_cuda_b200 import capi
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -187,103 +358,32 @@ def run_ours(args) -> None:
     cfg = CONFIGS[args.config]
     W, H = cfg["width"], cfg["height"]
     spp = args.spp or cfg["spp"]
-    desc = build_desc(args.config)
     ctx = rt.Context(local_rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    scene = rt.Scene(ctx, desc)
-    info = scene.info()
-    params = rt.default_params(width=W, height=H, spp=spp, sample_offset=rank * spp)
+    peaks = load_peaks()
+    peaks["sm_count"] = torch.cuda.get_device_properties(local_rank).multi_processor_count
 
     with torch.cuda.stream(stream):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-        collective = "none"
-        hdl = None
-        if world > 1 and args.collective != "nccl":
-            # symmetric memory: every rank maps every rank's accumulator (NVLink peer pointers + NVLS multicast)
-            try:
-                import torch.distributed._symmetric_memory as symm
-
-                accum = symm.empty((H, W, 4), dtype=torch.float32, device=torch.device("cuda", local_rank))
-                rgb = symm.empty((H, W, 3), dtype=torch.float32, device=torch.device("cuda", local_rank))
-                rgb8 = symm.empty((H, W, 3), dtype=torch.uint8, device=torch.device("cuda", local_rank))
-                hdl = symm.rendezvous(accum, dist.group.WORLD)
-                h_rgb = symm.rendezvous(rgb, dist.group.WORLD)
-                h_rgb8 = symm.rendezvous(rgb8, dist.group.WORLD)
-                peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
-                mc_ptr = int(hdl.multicast_ptr or 0) if args.collective in ("auto", "multimem") else 0  # 0: no NVLS multicast
-                root_rgb, root_rgb8 = int(h_rgb.buffer_ptrs[0]), int(h_rgb8.buffer_ptrs[0])
-                row0, row1 = rank * H // world, (rank + 1) * H // world
-                collective = "fused peer-memory reduce+tonemap (" + ("NVLS multimem.ld_reduce" if mc_ptr else "NVLink peer loads") + ")"
-            except Exception as ex:  # noqa: BLE001
-                if args.collective != "auto":
-                    raise
-                print(f"[bench] symmetric memory unavailable ({ex!r}); using the NCCL reduce", file=sys.stderr)
-                hdl = None
-        if hdl is None:
-            accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
-            rgb = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
-            rgb8 = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
-            if world > 1:
-                collective = "NCCL reduce(SUM) to rank 0 + tonemap"
-
-        def finish():
-            """sum over ranks + pixel finalisation; the frame ends up on rank 0"""
-            if hdl is not None:
-                hdl.barrier(0)  # every rank has finished rendering into its accumulator
-                rt.reduce_tonemap_peers(ctx, peer_ptrs, mc_ptr, W, H, row0, row1, root_rgb, root_rgb8)
-                hdl.barrier(1)  # every band is in rank 0's image; accumulators may be reused
-            else:
-                if world > 1:
-                    dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-                if rank == 0:
-                    rt.tonemap_device(ctx, accum.data_ptr(), W, H, rgb.data_ptr(), rgb8.data_ptr())
-
-        def step():
-            accum.zero_()
-            scene.render_accum_device(params, accum.data_ptr())
-            finish()
-
-        # one instrumented step: rays and launches per step (deterministic: the RNG is keyed on pixel/sample/bounce)
-        accum.zero_()
-        st = scene.render_accum_device(params, accum.data_ptr(), want_stats=True)
-        rays_rank, launches_step, iters = int(st.rays), int(st.launches) + 1, int(st.iterations)
-        for _ in range(args.warmup):
-            step()
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        loop = FrameLoop(torch, dist, rt, ctx, stream, args.config, spp, rank * spp, rank, world, args.collective)
         sampler = ClockSampler(local_rank) if rank == 0 else None
+        # (the warm-up, incl. one instrumented step, runs before the clock sampler starts)
+        loop.step()
+        loop.sync_all()
         if sampler:
             sampler.start()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        rv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         t_wall0 = time.perf_counter()
-        for k in range(args.steps):
-            flush.fill_(k & 255)  # L2 flush between timed iterations, outside the timed span
-            ev[k][0].record(stream)
-            accum.zero_()
-            rv[k][0].record(stream)
-            scene.render_accum_device(params, accum.data_ptr())
-            rv[k][1].record(stream)
-            finish()
-            ev[k][1].record(stream)
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        ms_step, ms_render, ms_finish, rays_rank, launches_render, iters = loop.timed(args.steps, args.warmup, flush)
         t_wall = time.perf_counter() - t_wall0
         clocks = sampler.stop() if sampler else None
-        ms_steps = [a.elapsed_time(b) for a, b in ev]
-        ms_render = [a.elapsed_time(b) for a, b in rv]
-        ms_step = float(np.mean(ms_steps))
-        ms_kernel_span = float(np.mean(ms_render))
+        launches_finish = (3 if loop.group is not None or loop.symm is not None else 1) if (world > 1 or rank == 0) else 0
+        launches_step = launches_render + launches_finish
 
         # ---- end to end through the C-ABI with HOST buffers: scene upload + render + read-back each step ----
+        desc = loop.desc
         h2d = desc_h2d_bytes(desc)
         out_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
-        acc_host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory() if world > 1 else None
         cudart = torch.cuda.cudart()
         for i in range(desc.desc.n_images):  # pin the host image the scene upload reads
             im = desc.desc.images[i]
@@ -292,21 +392,22 @@ def run_ours(args) -> None:
         def e2e_step():
             sc = rt.Scene(ctx, desc)  # H2D: spheres, materials, textures, image; BVH build
             if world == 1:
-                sc.render(params, out_host.numpy())  # render + tonemap + D2H, synchronous
+                sc.render(loop.params, out_host.numpy())  # render + tonemap + D2H, synchronous
             else:
-                accum.zero_()
-                sc.render_accum_device(params, accum.data_ptr())
-                finish()
-                if rank == 0:
-                    out_host.copy_(rgb, non_blocking=True)
-                stream.synchronize()
+                loop.begin()
+                sc.render_accum_device(loop.params, loop.accum_ptr)
+                loop.finish()
+                if loop.group is not None:
+                    loop.group.read_frame(out_host.numpy() if rank == 0 else None)
+                else:
+                    if rank == 0:
+                        out_host.copy_(loop.rgb, non_blocking=True)
+                    stream.synchronize()
             sc.close()
 
         for _ in range(min(args.warmup, 2)):
             e2e_step()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        loop.sync_all()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
@@ -316,76 +417,121 @@ def run_ours(args) -> None:
         # ---- output stage on the device: render + finalise + flip/quantise + JPEG, only the file is read back ----
         jpeg = None
         if world == 1:
-            sc = rt.Scene(ctx, desc)
             file_host = torch.empty(int(ctx.lib.rt_jpeg_max_bytes(W, H)), dtype=torch.uint8).pin_memory()
             for _ in range(min(args.warmup, 2)):
-                sc.render_jpeg(params, 100, file_host.numpy())
+                loop.scene.render_jpeg(loop.params, 100, file_host.numpy())
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                f_bytes, st_j = sc.render_jpeg(params, 100, file_host.numpy())
+                f_bytes, st_j = loop.scene.render_jpeg(loop.params, 100, file_host.numpy())
             t_j = (time.perf_counter() - t0) / args.steps
-            sc.close()
             jpeg = {"value": float(W) * H * spp / t_j / 1e6, "unit": "Mpaths/s", "ms_per_step": t_j * 1e3,
                     "ms_device_jpeg": float(st_j.ms_d2h), "d2h_bytes_per_step": int(f_bytes.size), "quality": 100,
                     "gb_per_s_pixels": W * H * 3 / (float(st_j.ms_d2h) / 1e3) / 1e9 if st_j.ms_d2h > 0 else None,
                     "what": "rt_render_jpeg: render + finalise + Y-flip/quantise + baseline JPEG (byte-identical to the reference's "
                             "stbi_write_jpg, main.cu:475-491) on the device; the D2H copy moves the finished file only"}
+        info, kernel_name = loop.info, kernel_name_of(loop.info)
+        collective = loop.collective
+        loop.close()
 
-    vals = torch.tensor([ms_step, ms_kernel_span, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    rays_t = torch.tensor([rays_rank], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
-    ms_step, ms_kernel_span, e2e_ms = (float(x) for x in vals.tolist())
-    rays_total = float(rays_t.item())
+        def reduce_max(*xs):
+            t = torch.tensor(xs, dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return [float(x) for x in t.tolist()]
+
+        def reduce_sum(x):
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+
+        ms_step, ms_render, ms_finish, e2e_ms = reduce_max(ms_step, ms_render, ms_finish, e2e_s * 1e3)
+        rays_total = reduce_sum(rays_rank)
+
+        # ---- the other configurations, short (N = 1), each with the roofline that bounds it ----
+        other = {}
+        l2_gbs = None
+        if world == 1 and not args.no_other_configs and args.config == "c1":
+            l2_gbs = measure_l2_gbs(torch, stream)
+            for key in ("c2", "c3", "c4"):
+                lp = FrameLoop(torch, dist, rt, ctx, stream, key, CONFIGS[key]["spp"], 0, 0, 1, "none")
+                lp.step()
+                m, mr, mf, rays_k, launches_k, it_k = lp.timed(2, 1, flush)
+                c = CONFIGS[key]
+                paths = float(c["width"]) * c["height"] * c["spp"]
+                other[key] = {"workload": c["name"], "value": paths / m / 1e3, "unit": "Mpaths/s", "ms_per_step": m, "steps": 2, "warmup": 3,
+                              "mrays_per_s": rays_k / m / 1e3, "rays_per_path": rays_k / paths, "n_spheres": int(lp.info.n_spheres),
+                              "bvh_nodes": int(lp.info.n_nodes), "wavefront_iterations": it_k,
+                              "roofline": roofline_of(key, rays_k, mr, max(1, launches_k - 1), peaks, l2_gbs, kernel_name_of(lp.info))}
+                lp.close()
+
+        # ---- N > 1: the 8K frame (C5) and strong scaling, through the same rt_group path ----
+        c5 = strong = None
+        if world > 1 and not args.no_other_configs and args.config == "c1":
+            lp = FrameLoop(torch, dist, rt, ctx, stream, "c5", CONFIGS["c5"]["spp"], rank * CONFIGS["c5"]["spp"], rank, world, args.collective)
+            lp.step()
+            m, mr, mf = reduce_max(*lp.timed(2, 1, flush)[:3])
+            c = CONFIGS["c5"]
+            npix = float(c["width"]) * c["height"]
+            # every GPU pulls its band of the other N-1 accumulators over NVLink: (N-1)/N x 16 B x pixels per GPU
+            link_bytes = npix * 16.0 * (world - 1) / world
+            c5 = {"workload": c["name"], "value": npix * c["spp"] * world / m / 1e3, "unit": "Mpaths/s", "ms_per_step": m, "ms_render": mr,
+                  "ms_reduce_finalise": mf, "steps": 2, "spp_per_gpu": c["spp"], "spp_total": c["spp"] * world, "scaling": "weak",
+                  "accumulator_bytes_per_gpu": npix * 16.0, "nvlink_bytes_in_per_gpu": link_bytes,
+                  "nvlink_gbs_per_gpu": link_bytes / (mf / 1e3) / 1e9, "nvlink_peak_gbs": NVLINK_PEER_GBS,
+                  "nvlink_frac": link_bytes / (mf / 1e3) / 1e9 / NVLINK_PEER_GBS,
+                  "note": "ms_reduce_finalise spans barrier + fused reduce/finalise kernel + barrier, i.e. it includes the skew between the ranks' renders"}
+            lp.close()
+            strong = {}
+            for key, total in (("c1", CONFIGS["c1"]["spp"]), ("c5", 64)):
+                first, count = rt.shard_samples(total, rank, world)
+                lp = FrameLoop(torch, dist, rt, ctx, stream, key, count, first, rank, world, args.collective)
+                lp.step()
+                m, mr, mf = reduce_max(*lp.timed(3 if key == "c1" else 2, 1, flush)[:3])
+                c = CONFIGS[key]
+                strong[key] = {"workload": f"{c['scene']} {c['width']}x{c['height']}, {total} spp in TOTAL split over {world} GPUs", "scaling": "strong",
+                               "value": float(c["width"]) * c["height"] * total / m / 1e3, "unit": "Mpaths/s", "ms_per_step": m, "ms_render": mr,
+                               "ms_reduce_finalise": mf, "spp_total": total}
+                lp.close()
 
     if rank == 0:
-        peaks = load_peaks()
         paths_total = float(W) * H * spp * world
         value = paths_total / ms_step / 1e3
-        n_step_launches = max(1, launches_step - 2)  # k_wf_step launches (excl. k_wf_init, tonemap)
-        kernel_name = ("k_wf_step_pt" if int(info.n_spheres) >= 4096 else "k_wf_step_warp") if int(info.n_nodes) else "k_wf_step_cta"
-        grain = os.environ.get("RT_WF_GRAIN", "")
-        if grain.startswith("r") and iters == 1:  # experimental single-launch kernel: k_ring_fill + k_ring_commit + k_wf_ring
-            kernel_name, n_step_launches = "k_wf_ring", 1
-        fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s at the measured max SM clock
-        flop_launch = rays_rank / n_step_launches * FLOP_PER_RAY[args.config]
-        dur_launch_s = ms_kernel_span / 1e3 / n_step_launches
-        achieved = flop_launch / dur_launch_s / 1e12
-        hbm_achieved = rays_rank * STATE_BYTES_PER_RAY / (ms_kernel_span / 1e3) / 1e9
-        traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-        ncu_static = None  # what that capture says about issue utilisation / lanes / stalls (static: not measured by this run)
+        n_step_launches = max(1, launches_render - 1)  # k_wf_step launches (excl. k_wf_init)
+        roof = roofline_of(args.config, rays_rank, ms_render, n_step_launches, peaks, l2_gbs or 0.0, kernel_name)
         tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
+        if tp.exists():  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (static)
             ent = json.loads(tp.read_text()).get(args.config) or {}
-            traffic = ent.get("bytes_per_launch")
-            ncu_static = ent.get("ncu")
+            roof["traffic"] = ent.get("bytes_per_launch")
+            roof["ncu"] = ent.get("ncu")
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "mrays_per_s": rays_total / ms_step / 1e3, "ms_per_frame": ms_step,
-            "rays_per_path": rays_total / paths_total,
+            "data": "synthetic", "mrays_per_s": rays_total / ms_step / 1e3, "ms_per_frame": ms_step, "ms_render": ms_render,
+            "ms_reduce_finalise": ms_finish, "rays_per_path": rays_total / paths_total,
             "config": {"workload": cfg["name"], "scene": cfg["scene"], "width": W, "height": H, "spp_per_gpu": spp,
                        "spp_total": spp * world, "max_depth": 50, "n_spheres": int(info.n_spheres), "bvh_nodes": int(info.n_nodes),
-                       "bvh_mode": int(info.bvh_mode), "pipeline": "wavefront" + (f" (RT_WF_GRAIN={os.environ['RT_WF_GRAIN']})" if os.environ.get("RT_WF_GRAIN") else ""), "parallelism": f"samples x{world}", "collective": collective,
+                       "bvh_mode": int(info.bvh_mode), "pipeline": "wavefront", "parallelism": f"samples x{world}", "collective": collective,
                        "l2": "flushed between timed steps (256 MiB fill, outside the timed spans)",
-                       "timing": "sum of per-step CUDA-event spans on the launching stream, max over ranks"},
-            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": traffic, "ncu": ncu_static, "kernel": kernel_name, "launches_per_step": n_step_launches,
-                         "avg_launch_ms": dur_launch_s * 1e3, "flop_per_ray": FLOP_PER_RAY[args.config],
-                         "peak_source": f"148 SM x 128 lanes x 2 flop x {peaks['sm_max_mhz']:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peaks['source']})",
-                         "note": "no dense contraction and L2-resident state: the bounding roofline is FP32 issue (SURVEY.md 8d), not hbm/tensor",
-                         "hbm": {"achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
-                                 "bytes_per_ray": STATE_BYTES_PER_RAY, "peak_source": f"MEASURED_PEAKS.json ({peaks['source']})"}},
+                       "timing": "mean of per-step CUDA-event spans on the launching stream, max over ranks"},
+            "roofline": roof,
             "e2e": {"value": paths_total / e2e_ms / 1e3, "unit": "Mpaths/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": W * H * 3 * 4,
-                    "what": "rt_scene_create (H2D scene + texture, BVH build) + rt_render to a pinned host buffer, wall clock"},
-            "gpu_launches": int(args.steps * launches_step),  # k_wf_init + k_wf_step x iterations + tonemap / fused reduce-tonemap
+                    "what": "rt_scene_create (H2D scene + texture, BVH build) + rt_render to a pinned host buffer, wall clock"
+                    if world == 1 else "rt_scene_create (H2D) on every rank + rt_group frame + D2H of the root's frame, wall clock, max over ranks"},
+            "gpu_launches": int(args.steps * launches_step),  # k_wf_init + k_wf_step x iterations + tonemap / barrier-reduce-barrier
             "wavefront_iterations": iters, "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         if jpeg is not None:
             line["output_stage"] = jpeg
+        if other:
+            line["other_configs"] = other
+            line["l2_gbs_measured"] = l2_gbs
+        if c5 is not None:
+            line["c5"] = c5
+        if strong is not None:
+            line["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.config, desc)
         print(json.dumps(line), flush=True)
@@ -395,6 +541,18 @@ def run_ours(args) -> None:
 
 
 # ------------------------------------------------------------------------------------------ reference
+def child_json(*argv, timeout=900):
+    """Runs this script in a CHILD process (which may load librt_b200.so and the oracle) and returns the JSON it prints: the
+    reference arm's own process stays free of the product library."""
+    o = subprocess.run([sys.executable, str(Path(__file__).resolve()), *argv], capture_output=True, text=True, timeout=timeout)
+    if o.returncode != 0:
+        return None
+    try:
+        return json.loads(o.stdout.strip().splitlines()[-1])
+    except (ValueError, IndexError):
+        return None
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -402,10 +560,25 @@ def run_reference(args) -> None:
     cfg = CONFIGS[args.config]
     ref = ROOT / "oracle" / "_ref"
     W, H = cfg["width"], cfg["height"]
-    desc = build_desc(args.config)
-    cb = None if args.no_cpu_baseline else cpu_baseline(args.config, desc)
+    # the scene of the configuration as a flat file written at build time (oracle/_ref/scenes/, __graft_entry__.build()),
+    # read with pure ctypes: nothing in this arm's process tree loads librt_b200.so.  Without the file (build() not run)
+    # a child process writes it.
+    scene_file = ref / "scenes" / f"{args.config}.rtsc"
+
+    def host_core_baseline():
+        if scene_file.exists():
+            from tests import oracle_api as oa
+
+            if oa.REFCPU_RN_SO.exists():
+                return cpu_baseline(args.config, oa.FileDesc(scene_file))
+        return child_json("--child", "cpu-baseline", "--config", args.config)
+
+    cb = None if args.no_cpu_baseline else host_core_baseline()
     if args.ref_device == "cpu":
-        v = cb or cpu_baseline(args.config, desc)
+        v = cb or host_core_baseline()
+        if not v:
+            print(json.dumps({"impl": "reference", "unavailable": "host-core baseline failed"}))
+            return
         line = {"impl": "reference", "metric": "Mpaths/s", "value": v["value"], "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": 1,
                 "warmup": 0, "ms_per_step": v["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": {"workload": cfg["name"], "device": "host cores"},
@@ -417,6 +590,7 @@ def run_reference(args) -> None:
         return
     spp = args.spp or cfg["spp"]
     took_ms, kernel_ms, rays = [], None, None
+    how = ""
     if args.config == "c1" and not args.spp:
         # the UNCHANGED binary: its own timing window (init_rand_state + render + syncs, main.cu:431-454)
         for k in range(args.warmup + args.steps):
@@ -428,26 +602,27 @@ def run_reference(args) -> None:
             if k >= args.warmup:
                 took_ms.append(int(m.group(1)) / 1e3)
         how = "reference src/main.cu rebuilt unchanged (-arch=sm_100), its own chrono window (init_rand_state + render + syncs)"
-    with tempfile.TemporaryDirectory() as td:
-        sp = Path(td) / "scene.rtsc"
-        desc.save(str(sp))
-        if args.config == "c4":
-            cap = 10_000  # the reference builds its BVH on ONE device thread, O(N log^2 N) with virtual calls (bvh.h:75-113):
-            #               10^5 spheres did not finish in 20 minutes on a B200, 10^6 is out of reach
-            import raytracing_renderer_cuda_b200 as rt
-
-            rt.SceneDesc.builtin("random_spheres", n=cap).save(str(sp))
-        o = subprocess.run([str(ref / "ref_harness"), "render", str(sp), str(W), str(H), str(spp), str(Path(td) / "o.f32"), "1", "1",
-                            str(max(1, min(args.steps, 3)))], capture_output=True, text=True, timeout=900)
-        if o.returncode == 0:
+    else:
+        with tempfile.TemporaryDirectory() as td:
+            # the reference builds its BVH on ONE device thread, O(N log^2 N) with virtual calls (bvh.h:75-113): 10^5 spheres did
+            # not finish in 20 minutes on a B200, 10^6 is out of reach -> C4 is run at 10^4
+            n_over = 10_000 if args.config == "c4" else 0
+            sp = scene_file
+            if not sp.exists():
+                sp = Path(td) / "scene.rtsc"
+                if child_json("--child", "dump-scene", "--config", args.config, "--scene-n", str(n_over), "--out", str(sp)) is None:
+                    print(json.dumps({"impl": "reference", "unavailable": "could not write the scene file"}))
+                    return
+            o = subprocess.run([str(ref / "ref_harness"), "render", str(sp), str(W), str(H), str(spp), str(Path(td) / "o.f32"), "1", "1",
+                                str(max(1, min(args.steps, 3)))], capture_output=True, text=True, timeout=1500)
+            if o.returncode != 0:
+                print(json.dumps({"impl": "reference", "unavailable": "ref_harness failed: " + o.stderr[-200:]}))
+                return
             info = json.loads(o.stdout.strip().splitlines()[-1])
             kernel_ms, rays = info["ms_render"] + info["ms_init_rand"], info["rays"]
-    if not took_ms:
-        if kernel_ms is None:
-            print(json.dumps({"impl": "reference", "unavailable": "ref_harness failed: " + o.stderr[-200:]}))
-            return
-        took_ms = [kernel_ms]
-        how = "reference translation unit through oracle/ref_harness.cu (runtime sizes), CUDA events around init_rand_state + render"
+            took_ms = [kernel_ms]
+            how = "reference translation unit through oracle/ref_harness.cu (runtime sizes), CUDA events around init_rand_state + render" + (
+                "; scene reduced to 10^4 spheres (the reference cannot build its BVH for more)" if n_over else "")
     ms = float(np.mean(took_ms))
     paths = float(W) * H * spp
     value = paths / ms / 1e3
@@ -461,6 +636,15 @@ def run_reference(args) -> None:
     if cb:
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
+
+
+def run_child(args) -> None:
+    """helper modes executed in a child process of the reference arm"""
+    if args.child == "cpu-baseline":
+        print(json.dumps(cpu_baseline(args.config, build_desc(args.config))), flush=True)
+    elif args.child == "dump-scene":
+        build_desc(args.config, args.scene_n).save(args.out)
+        print(json.dumps({"ok": True}), flush=True)
 
 
 def main() -> None:
@@ -477,9 +661,17 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--ref-device", choices=["gpu", "cpu"], default="gpu")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--collective", choices=["auto", "multimem", "peer", "nccl"], default="auto",
-                    help="N > 1: fused peer-memory reduce+tonemap (NVLS multimem / peer loads) or the plain NCCL reduce")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the other_configs / c5 / strong sub-records")
+    ap.add_argument("--collective", choices=["auto", "ipc", "multimem", "peer", "nccl"], default="auto",
+                    help="N > 1: rt_group of the C-ABI (auto / ipc), or the A/B forms: torch symmetric memory with NVLS multimem / "
+                         "peer loads in the fused kernel, or the plain NCCL reduce")
+    ap.add_argument("--child", choices=["cpu-baseline", "dump-scene"], default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--scene-n", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--out", default="", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.child:
+        run_child(args)
+        return
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

@@ -316,6 +316,57 @@ rt_status rt_reduce_tonemap_peers(rt_context* ctx, const void* const* peer_accum
                                   const void* multicast_accum, int32_t width, int32_t height, int32_t row_begin,
                                   int32_t row_end, void* out_rgb_dev, void* out_rgb8_dev, void* out_sum_dev);
 
+/* ---- multi-GPU (BASELINE.json north_star (4)) ---------------------------------------------------
+ * Samples per pixel are split across the GPUs of one box: GPU r renders sample indices [first_r, first_r + count_r) of
+ * EVERY pixel (rt_render_params.sample_offset; the Philox keys use the global sample index, so the image does not depend
+ * on the number of GPUs) into its own float4 accumulator; the accumulators are summed in rank order and finalised by
+ * one fused kernel per GPU that reads the peers' accumulators over NVLink and writes its band of rows into the root's
+ * image.  The reference's main() (main.cu:368-509) is a single-device program: these entries are what its device
+ * selection, cudaMallocManaged frame buffer and render launch become on an 8-GPU box. */
+/* contiguous sample ranges, the remainder spread over the low ranks; row bands of the fused reduce (no device needed) */
+rt_status rt_shard_samples(int32_t spp_total, int32_t rank, int32_t world, int32_t* first, int32_t* count);
+rt_status rt_shard_rows(int32_t height, int32_t rank, int32_t world, int32_t* row_begin, int32_t* row_end);
+
+/* (a) ONE process, n devices.  devices == NULL / n_devices <= 0: every visible device.  Creates a context per device
+ * and enables peer access between all of them (RT_ERR_UNSUPPORTED without a P2P path). */
+typedef struct rt_multi rt_multi;
+rt_status rt_multi_create(const int32_t* devices, int32_t n_devices, rt_multi** out);
+int32_t rt_multi_size(const rt_multi* m);
+/* uploads the scene to every device (the uploads and BVH builds run side by side) */
+rt_status rt_multi_set_scene(rt_multi* m, const rt_scene_desc* desc);
+/* p->spp is the TOTAL sample count of the frame.  out_rgb (HOST, layout of rt_render) and/or out_rgb8 (HOST, Y-flipped
+ * bytes as main.cu:476-487).  stats (may be NULL): paths, rays and launches summed over the devices, ms_total = the slowest
+ * device's render, ms_tonemap = device time from the root's render end to the last band of the reduce, ms_d2h = wall
+ * clock of the whole call.  ms_reduce (may be NULL) = stats->ms_tonemap. */
+rt_status rt_multi_render(rt_multi* m, const rt_render_params* p, float* out_rgb, uint8_t* out_rgb8, rt_stats* stats, float* ms_reduce);
+/* the un-finalised float4 accumulator of one member after rt_multi_render (HOST, the size of the largest frame rendered
+ * so far): lets a caller check the fused reduce against its own rank-ordered sum */
+rt_status rt_multi_read_accum(rt_multi* m, int32_t member, float* out_accum);
+void rt_multi_destroy(rt_multi* m);
+
+/* (b) one PROCESS per GPU (torchrun, MPI, ...): `world` members, member `rank` lives on ctx's device.  Every member
+ * allocates its accumulator (and member 0 the image) with cudaMalloc and exports it as a CUDA IPC handle; the caller
+ * gathers the RT_GROUP_HANDLE_BYTES blobs of all members in rank order by any means it has and passes the table to
+ * rt_group_connect.  Per frame, on every member:
+ *     rt_group_begin_frame(g);                                   zero the accumulator
+ *     rt_render_accum_device(ctx, scene, &p_shard, rt_group_accum(g), NULL);      p_shard from rt_shard_samples
+ *     rt_group_finish_frame(g, want_rgb8, NULL);                 barrier, fused reduce + finalisation of this member's band, barrier
+ *     rt_group_read_frame(g, out_rgb, out_rgb8);                 member 0: D2H of the image; every member: synchronise
+ * All of it is stream-ordered on the context's stream; the two barriers are flag exchanges in peer memory (every member
+ * runs on its own GPU).  A member that never arrives turns into RT_ERR_CUDA from rt_group_read_frame after a few
+ * seconds instead of a hung GPU.  ms_reduce (may be NULL; synchronises): device time of barrier + reduce + barrier. */
+typedef struct rt_group rt_group;
+#define RT_GROUP_HANDLE_BYTES 192
+rt_status rt_group_create(rt_context* ctx, int32_t rank, int32_t world, int32_t width, int32_t height, rt_group** out);
+rt_status rt_group_export(const rt_group* g, void* handle);
+rt_status rt_group_connect(rt_group* g, const void* handles);
+void* rt_group_accum(const rt_group* g);
+rt_status rt_group_begin_frame(rt_group* g);
+rt_status rt_group_finish_frame(rt_group* g, int32_t want_rgb8, float* ms_reduce);
+rt_status rt_group_read_frame(rt_group* g, float* out_rgb, uint8_t* out_rgb8);
+rt_status rt_group_read_accum(rt_group* g, float* out_accum); /* this member's float4 accumulator (HOST, width*height*4 floats) */
+void rt_group_destroy(rt_group* g);
+
 /* Host restatement of the writer loop main.cu:475-488 (Y flip + int(255.999f*c)&255). */
 rt_status rt_quantize_rgb8(const float* rgb, int32_t width, int32_t height, uint8_t* out_rgb8);
 rt_status rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t* rgb8);

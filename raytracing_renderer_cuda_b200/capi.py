@@ -144,6 +144,23 @@ _SIGNATURES = {
     "rt_tonemap_device": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP]),
     "rt_reduce_tonemap_peers": (C.c_int, [_VP, C.POINTER(_VP), C.c_int32, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           _VP, _VP, _VP]),
+    "rt_shard_samples": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "rt_shard_rows": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "rt_multi_create": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(_VP)]),
+    "rt_multi_size": (C.c_int32, [_VP]),
+    "rt_multi_set_scene": (C.c_int, [_VP, C.POINTER(rt_scene_desc)]),
+    "rt_multi_render": (C.c_int, [_VP, C.POINTER(rt_render_params), _VP, _VP, C.POINTER(rt_stats), C.POINTER(C.c_float)]),
+    "rt_multi_read_accum": (C.c_int, [_VP, C.c_int32, _VP]),
+    "rt_multi_destroy": (None, [_VP]),
+    "rt_group_create": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_VP)]),
+    "rt_group_export": (C.c_int, [_VP, _VP]),
+    "rt_group_connect": (C.c_int, [_VP, _VP]),
+    "rt_group_accum": (_VP, [_VP]),
+    "rt_group_begin_frame": (C.c_int, [_VP]),
+    "rt_group_finish_frame": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_float)]),
+    "rt_group_read_frame": (C.c_int, [_VP, _VP, _VP]),
+    "rt_group_read_accum": (C.c_int, [_VP, _VP]),
+    "rt_group_destroy": (None, [_VP]),
     "rt_quantize_rgb8": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP]),
     "rt_write_ppm": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, _VP]),
     "rt_read_ppm_f32": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
@@ -411,6 +428,105 @@ class Scene:
 def tonemap_device(ctx: Context, accum_ptr: int, width: int, height: int, out_rgb_ptr: int = 0, out_rgb8_ptr: int = 0):
     _check(ctx.lib, ctx.lib.rt_tonemap_device(ctx._h, _VP(accum_ptr), width, height, _VP(out_rgb_ptr or None),
                                               _VP(out_rgb8_ptr or None)))
+
+
+RT_GROUP_HANDLE_BYTES = 192
+
+
+def shard_samples(spp_total: int, rank: int, world: int):
+    """rt_shard_samples: (first sample index, sample count) of `rank`."""
+    lib = load_library()
+    first, count = C.c_int32(), C.c_int32()
+    _check(lib, lib.rt_shard_samples(spp_total, rank, world, C.byref(first), C.byref(count)))
+    return first.value, count.value
+
+
+def shard_rows(height: int, rank: int, world: int):
+    """rt_shard_rows: [row_begin, row_end) of the band `rank` reduces."""
+    lib = load_library()
+    a, b = C.c_int32(), C.c_int32()
+    _check(lib, lib.rt_shard_rows(height, rank, world, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+class Multi:
+    """rt_multi_*: ONE process driving n devices (sample-sharded render + fused NVLink reduce)."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        self._h = _VP()
+        if devices is None:
+            _check(self.lib, self.lib.rt_multi_create(None, 0, C.byref(self._h)))
+        else:
+            arr = (C.c_int32 * len(devices))(*devices)
+            _check(self.lib, self.lib.rt_multi_create(arr, len(devices), C.byref(self._h)))
+        self.size = int(self.lib.rt_multi_size(self._h))
+
+    def set_scene(self, desc: "SceneDesc") -> None:
+        _check(self.lib, self.lib.rt_multi_set_scene(self._h, desc._ptr))
+
+    def render(self, params: rt_render_params, want_rgb8: bool = False):
+        rgb = np.empty((params.height, params.width, 3), np.float32)
+        rgb8 = np.empty((params.height, params.width, 3), np.uint8) if want_rgb8 else None
+        st, ms = rt_stats(), C.c_float()
+        _check(self.lib, self.lib.rt_multi_render(self._h, C.byref(params), rgb.ctypes.data, rgb8.ctypes.data if want_rgb8 else None,
+                                                  C.byref(st), C.byref(ms)))
+        return rgb, rgb8, st, ms.value
+
+    def read_accum(self, member: int, width: int, height: int) -> np.ndarray:
+        out = np.empty((height, width, 4), np.float32)
+        _check(self.lib, self.lib.rt_multi_read_accum(self._h, member, out.ctypes.data))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.rt_multi_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """rt_group_*: this process's member of a one-process-per-GPU group.  `exchange(blob) -> [blob of rank 0, ...]`
+    moves the IPC handle blobs between the processes (e.g. torch.distributed.all_gather_object)."""
+
+    def __init__(self, ctx: "Context", rank: int, world: int, width: int, height: int, exchange):
+        self.lib, self.ctx, self.rank, self.world, self.width, self.height = ctx.lib, ctx, rank, world, width, height
+        self._h = _VP()
+        _check(self.lib, self.lib.rt_group_create(ctx._h, rank, world, width, height, C.byref(self._h)))
+        blob = C.create_string_buffer(RT_GROUP_HANDLE_BYTES)
+        _check(self.lib, self.lib.rt_group_export(self._h, blob))
+        if world > 1:
+            table = b"".join(bytes(b) for b in exchange(bytes(blob.raw)))
+            assert len(table) == world * RT_GROUP_HANDLE_BYTES
+            _check(self.lib, self.lib.rt_group_connect(self._h, C.create_string_buffer(table, len(table))))
+        self.accum_ptr = int(self.lib.rt_group_accum(self._h))
+
+    def begin_frame(self) -> None:
+        _check(self.lib, self.lib.rt_group_begin_frame(self._h))
+
+    def finish_frame(self, want_rgb8: bool = False, timed: bool = False) -> float:
+        ms = C.c_float()
+        _check(self.lib, self.lib.rt_group_finish_frame(self._h, int(want_rgb8), C.byref(ms) if timed else None))
+        return ms.value
+
+    def read_frame(self, out_rgb: "np.ndarray | None" = None, out_rgb8: "np.ndarray | None" = None) -> None:
+        _check(self.lib, self.lib.rt_group_read_frame(self._h, out_rgb.ctypes.data if out_rgb is not None else None,
+                                                      out_rgb8.ctypes.data if out_rgb8 is not None else None))
+
+    def read_accum(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), np.float32)
+        _check(self.lib, self.lib.rt_group_read_accum(self._h, out.ctypes.data))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.rt_group_destroy(self._h)
+            self._h = _VP()
 
 
 def reduce_tonemap_peers(ctx: Context, peer_ptrs, multicast_ptr: int, width: int, height: int, row_begin: int, row_end: int,

@@ -77,39 +77,7 @@ namespace {
 
 } // namespace
 
-struct rt_context {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = true;
-    int sm_count = 0;             // multiProcessorCount of the device (launch sizing)
-    cudaMemPool_t pool = nullptr; // scene allocations (stream-ordered, private to the context)
-    unsigned long long* d_ray_counter = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float4* accum = nullptr; // scratch for rt_render / rt_render_accum
-    size_t accum_px = 0;
-    float* out_rgb = nullptr;
-    size_t out_px = 0;
-    rtd::WavefrontState* wf = nullptr;
-    rtd::JpegState* jpg = nullptr; // device JPEG writer (rt_jpeg.cu), created on first use
-    uint8_t* rgb8 = nullptr;       // flipped, quantised frame: input of the JPEG writer
-    size_t rgb8_px = 0;
-    // cudaArray allocations cost milliseconds; arrays of destroyed scenes are kept for the next scene of the
-    // same image size (a frame loop that re-uploads its scene every frame then allocates nothing)
-    struct CachedArray {
-        int32_t width, height;
-        cudaArray_t arr;
-    };
-    std::vector<CachedArray> array_cache;
-};
-
-struct rt_scene {
-    rt_context* ctx = nullptr;
-    rtd::DScene d{};
-    rt_scene_info info{};
-    std::vector<void*> allocs;
-    std::vector<rt_context::CachedArray> arrays;
-    std::vector<cudaTextureObject_t> texobjs;
-};
+#include "rt_internal.hpp"
 
 namespace {
 

@@ -210,6 +210,49 @@ class RefCpuScene:
         return r
 
 
+class FileDesc:
+    """A flat scene file (rt_scene_desc_save, include/rt_api.h) read WITHOUT the product library: pure ctypes / numpy.
+    Quacks like capi.SceneDesc for the checkers (`._ptr`, `.desc`).  Used by bench.py's reference arm, whose process must
+    not load librt_b200.so."""
+
+    def __init__(self, path):
+        raw = Path(path).read_bytes()
+        hdr = np.frombuffer(raw, np.uint32, 7)
+        if hdr[0] != 0x43535452 or hdr[1] != 1:
+            raise ValueError(f"{path}: not a scene file")
+        n_s, n_m, n_t, n_i, bvh = (int(x) for x in hdr[2:7])
+        off = 28
+        d = capi.rt_scene_desc()
+        C.memmove(C.byref(d.camera), raw[off:off + C.sizeof(capi.rt_camera)], C.sizeof(capi.rt_camera))
+        off += C.sizeof(capi.rt_camera)
+        self._keep = []
+
+        def take(T, n):
+            nonlocal off
+            arr = (T * max(n, 1))()
+            C.memmove(arr, raw[off:off + n * C.sizeof(T)], n * C.sizeof(T))
+            off += n * C.sizeof(T)
+            self._keep.append(arr)
+            return arr
+
+        d.spheres, d.n_spheres = take(capi.rt_sphere, n_s), n_s
+        d.materials, d.n_materials = take(capi.rt_material, n_m), n_m
+        d.textures, d.n_textures = take(capi.rt_texture, n_t), n_t
+        imgs = (capi.rt_image * max(n_i, 1))()
+        for i in range(n_i):
+            w, h = (int(x) for x in np.frombuffer(raw, np.int32, 2, off))
+            off += 8
+            px = np.frombuffer(raw, np.float32, w * h * 3, off).copy()
+            off += px.nbytes
+            self._keep.append(px)
+            imgs[i].rgb = px.ctypes.data_as(C.POINTER(C.c_float))
+            imgs[i].width, imgs[i].height = w, h
+        self._keep.append(imgs)
+        d.images, d.n_images, d.bvh_mode = imgs, n_i, bvh
+        self.desc = d
+        self._ptr = C.pointer(d)
+
+
 def camera_rays(desc: capi.SceneDesc, n: int, seed: int = 1) -> np.ndarray:
     """Pin-hole rays through random image positions of the scene camera with random shutter times
     (host float math; test INPUT only — both sides of every comparison receive the same rays)."""

@@ -1,6 +1,6 @@
-"""Host logic of the sample-sharded multi-GPU path, exercised on CPU with two gloo ranks: each rank renders its
-sample range (the oracle in product-sampler mode stands in for the GPU), the float4 accumulators are reduced
-onto rank 0, and the result must equal the single-rank render."""
+"""Host logic of the sample-sharded multi-GPU path (rt_shard_samples / rt_shard_rows of the C-ABI), exercised on CPU
+with two gloo ranks: each rank renders its sample range (the oracle in product-sampler mode stands in for the GPU), the
+float4 accumulators are summed onto rank 0, and the result must equal the single-rank render."""
 import os
 import socket
 import subprocess
@@ -9,22 +9,47 @@ import sys
 import numpy as np
 import pytest
 
-from raytracing_renderer_cuda_b200.multi_gpu import sample_range
+import raytracing_renderer_cuda_b200 as rt
+from raytracing_renderer_cuda_b200 import capi
 from tests.conftest import ROOT
 
 
 def test_sample_ranges_partition_the_samples():
     for total in (0, 1, 7, 100, 4096):
-        for world in (1, 2, 3, 8):
-            got = [sample_range(total, r, world) for r in range(world)]
+        for world in (1, 2, 3, 8, 16):
+            got = [rt.shard_samples(total, r, world) for r in range(world)]
             assert sum(c for _, c in got) == total
             nxt = 0
             for first, count in got:
                 assert first == nxt and count >= 0
                 nxt += count
             assert max(c for _, c in got) - min(c for _, c in got) <= 1
-    with pytest.raises(ValueError):
-        sample_range(10, 2, 2)
+    with pytest.raises(capi.RtError):
+        rt.shard_samples(10, 2, 2)
+    with pytest.raises(capi.RtError):
+        rt.shard_samples(-1, 0, 2)
+
+
+def test_row_bands_partition_the_frame():
+    for height in (0, 1, 7, 600, 4320):
+        for world in (1, 2, 3, 8, 16):
+            bands = [rt.shard_rows(height, r, world) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == height
+            for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+                assert a1 == b0 and a0 <= a1 and b0 <= b1
+    with pytest.raises(capi.RtError):
+        rt.shard_rows(10, 3, 3)
+
+
+def test_multi_gpu_entries_need_a_device():
+    """No CPU fallback: without a CUDA device the single-process entry reports RT_ERR_NO_DEVICE."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(capi.RtError) as e:
+        rt.Multi()
+    assert e.value.status == capi.RT_ERR_NO_DEVICE
 
 
 WORKER = r"""
@@ -34,7 +59,6 @@ import torch
 import torch.distributed as dist
 sys.path.insert(0, os.environ["RT_ROOT"])
 import raytracing_renderer_cuda_b200 as rt
-from raytracing_renderer_cuda_b200.multi_gpu import render_sharded
 from tests.oracle_api import Oracle
 
 dist.init_process_group("gloo")
@@ -42,13 +66,11 @@ rank, world = dist.get_rank(), dist.get_world_size()
 desc = rt.SceneDesc.builtin("book1_final")
 sc = Oracle().scene(desc)
 W, H, SPP = 40, 24, 6
-
-def render_range(first, count):
-    p = rt.default_params(width=W, height=H, spp=count, sample_offset=first)
-    acc, _ = sc.render(p, sampler=1, arith=1, nthreads=2)
-    return torch.from_numpy(acc)
-
-acc = render_sharded(render_range, SPP, rank, world, lambda t: dist.reduce(t, dst=0, op=dist.ReduceOp.SUM))
+first, count = rt.shard_samples(SPP, rank, world)
+p = rt.default_params(width=W, height=H, spp=count, sample_offset=first)
+acc, _ = sc.render(p, sampler=1, arith=1, nthreads=2)
+acc = torch.from_numpy(acc)
+dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
 if rank == 0:
     np.save(os.environ["RT_OUT"], acc.numpy())
 dist.barrier()
@@ -57,8 +79,6 @@ dist.destroy_process_group()
 
 
 def test_two_rank_gloo_reduce_equals_single_rank(tmp_path, oracle):
-    import raytracing_renderer_cuda_b200 as rt
-
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]

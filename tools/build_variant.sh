@@ -5,7 +5,7 @@ name=$1; shift
 cd "$(dirname "$0")/.."
 out=gpurun_variants/obj_$name; mkdir -p $out
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v"
-for f in rt_api rt_kernels rt_wavefront rt_lbvh rt_jpeg rt_jpeg_decode; do
+for f in rt_api rt_kernels rt_wavefront rt_lbvh rt_jpeg rt_jpeg_decode rt_multi; do
   $NV "$@" -c raytracing_renderer_cuda_b200/csrc/$f.cu -o $out/$f.o 2> $out/$f.log &
 done
 g++ -std=c++17 -O2 -fPIC -c raytracing_renderer_cuda_b200/csrc/rt_host.cpp -o $out/rt_host.o &
