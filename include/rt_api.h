@@ -268,6 +268,12 @@ rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info);
 rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n,
                            float tmin, int use_bvh, rt_hit* hits);
 
+/* Self-test of the renderer's own round-toward-zero division and square root (csrc/rt_device.cuh: the reference's vec3
+ * operator/ and length() are __fdiv_rz / __fsqrt_rz, vec3.h:153-166,334-347; the library computes them from the
+ * round-to-nearest forms and one exact FMA residual): out[4i .. 4i+3] = { div_rz(x, y), __fdiv_rz(x, y), sqrt_rz(x),
+ * __fsqrt_rz(x) } for n caller-supplied operand pairs (HOST arrays), so a test can require bit equality. */
+rt_status rt_selftest_rz(rt_context* ctx, const float* x, const float* y, size_t n, float* out);
+
 /* Second parity hook: closest hit + one shading step per ray (see rt_shade_sample). */
 rt_status rt_shade_probe(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n,
                          const rt_render_params* p, int use_bvh, rt_shade_sample* out);

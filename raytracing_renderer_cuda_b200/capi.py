@@ -136,6 +136,7 @@ _SIGNATURES = {
     "rt_scene_destroy": (None, [_VP]),
     "rt_scene_get_info": (C.c_int, [_VP, C.POINTER(rt_scene_info)]),
     "rt_trace_primary": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.c_float, C.c_int, _VP]),
+    "rt_selftest_rz": (C.c_int, [_VP, _VP, _VP, C.c_size_t, _VP]),
     "rt_shade_probe": (C.c_int, [_VP, _VP, _VP, C.c_size_t, C.POINTER(rt_render_params), C.c_int, _VP]),
     "rt_render": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
     "rt_render_accum": (C.c_int, [_VP, _VP, C.POINTER(rt_render_params), _VP, C.POINTER(rt_stats)]),
@@ -431,6 +432,14 @@ def tonemap_device(ctx: Context, accum_ptr: int, width: int, height: int, out_rg
 
 
 RT_GROUP_HANDLE_BYTES = 192
+
+
+def selftest_rz(ctx: "Context", x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """rt_selftest_rz -> [n, 4] float32: div_rz(x, y), __fdiv_rz(x, y), sqrt_rz(x), __fsqrt_rz(x)."""
+    x, y = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(y, np.float32)
+    out = np.empty((x.size, 4), np.float32)
+    _check(ctx.lib, ctx.lib.rt_selftest_rz(ctx._h, x.ctypes.data, y.ctypes.data, x.size, out.ctypes.data))
+    return out
 
 
 def shard_samples(spp_total: int, rank: int, world: int):

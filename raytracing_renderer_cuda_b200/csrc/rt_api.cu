@@ -854,6 +854,33 @@ rt_status rt_tonemap_device(rt_context* ctx, const void* accum_dev, int32_t widt
     return RT_OK;
 } RT_API_CATCH
 
+rt_status rt_selftest_rz(rt_context* ctx, const float* x, const float* y, size_t n, float* out) try {
+    ARG_CHECK(ctx && (n == 0 || (x && y && out)), "ctx/x/y/out is NULL");
+    if (n == 0) return RT_OK;
+    rt_status st = make_current(ctx);
+    if (st != RT_OK) return st;
+    float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    CUDA_TRY(rtd::malloc_async(&dx, n * sizeof(float), ctx->stream));
+    cudaError_t e = rtd::malloc_async(&dy, n * sizeof(float), ctx->stream);
+    if (e == cudaSuccess) e = rtd::malloc_async(&dout, 4 * n * sizeof(float), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dx, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        rtd::launch_selftest_rz(dx, dy, n, dout, ctx->stream);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (dx) cudaFreeAsync(dx, ctx->stream);
+    if (dy) cudaFreeAsync(dy, ctx->stream);
+    if (dout) cudaFreeAsync(dout, ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("rt_selftest_rz: %s", cudaGetErrorString(e));
+        return RT_ERR_CUDA;
+    }
+    return RT_OK;
+} RT_API_CATCH
+
 rt_status rt_reduce_tonemap_peers(rt_context* ctx, const void* const* peer_accum_dev, int32_t n_peers, const void* multicast_accum,
                                   int32_t width, int32_t height, int32_t row_begin, int32_t row_end, void* out_rgb_dev,
                                   void* out_rgb8_dev, void* out_sum_dev) try {

@@ -30,13 +30,37 @@ RT_DEV V3 operator-(V3 a, V3 b) { return V3{__fsub_rz(a.x, b.x), __fsub_rz(a.y, 
 RT_DEV V3 operator*(V3 a, V3 b) { return V3{__fmul_rz(a.x, b.x), __fmul_rz(a.y, b.y), __fmul_rz(a.z, b.z)}; }
 RT_DEV V3 operator*(V3 a, float t) { return V3{__fmul_rz(a.x, t), __fmul_rz(a.y, t), __fmul_rz(a.z, t)}; }
 RT_DEV V3 operator*(float t, V3 a) { return V3{__fmul_rz(a.x, t), __fmul_rz(a.y, t), __fmul_rz(a.z, t)}; }
-RT_DEV V3 operator/(V3 a, float t) { return V3{__fdiv_rz(a.x, t), __fdiv_rz(a.y, t), __fdiv_rz(a.z, t)}; } // vec3.h:334-347
+// __fdiv_rz / __fsqrt_rz, bit for bit, without the out-of-line subroutine ptxas emits for the .rz forms (div.rz.f32: a
+// CALL into ~66 instructions of exponent juggling per quotient; ncu on C1: the three quotients of n = (p - c) / r were
+// 12 % of all instructions a shaded hit executes, profiles/r02_c1_instruction_diet.md).  The round-to-NEAREST forms have
+// an inline fast path; the correctly rounded nearest result q is either the truncated one or one ulp beyond it, and ONE
+// exact FMA residual tells which: q*y - x (resp. s*s - x) is computed exactly before its single rounding, so its sign
+// is exact, and it has the sign of x (is positive) exactly when q (s) was rounded away from zero.  Stepping the bit
+// pattern down by one then gives the truncated result — also from +-inf to +-FLT_MAX when the quotient overflows, as
+// div.rz does.  NaN and x/0 fall through unchanged (every comparison with the NaN residual is false).  Operands so small
+// that the residual itself could underflow to zero take the library path.
+RT_DEV float div_rz(float x, float y) {
+    if (!(fabsf(x) >= 8.6736174e-19f)) return __fdiv_rz(x, y); // |x| < 2^-60 (or NaN): rare, exact by construction
+    const float q = __fdiv_rn(x, y);
+    const float rem = __fmaf_rn(q, y, -x);
+    const bool away = (x > 0.f && rem > 0.f) || (x < 0.f && rem < 0.f);
+    return away ? __int_as_float(__float_as_int(q) - 1) : q;
+}
+RT_DEV float sqrt_rz(float x) {
+    if (!(x >= 8.6736174e-19f)) return __fsqrt_rz(x); // tiny, zero, negative, NaN
+    const float s = __fsqrt_rn(x);
+    const float rem = __fmaf_rn(s, s, -x);
+    return rem > 0.f ? __int_as_float(__float_as_int(s) - 1) : s;
+}
+// vec3 / float (vec3.h:334-347).  Inline: one out-of-line copy per kernel is 350 instructions smaller but its call spills
+// around every use (C1 8.07 ms against 7.43 ms inline; profiles/r02_c1_instruction_diet.md).
+RT_DEV V3 operator/(V3 a, float t) { return V3{div_rz(a.x, t), div_rz(a.y, t), div_rz(a.z, t)}; }
 RT_DEV V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
 // vec3::dot (vec3.h:208-219): RZ products, RN sums, left to right
 RT_DEV float dot(V3 a, V3 b) {
     return __fadd_rn(__fadd_rn(__fmul_rz(a.x, b.x), __fmul_rz(a.y, b.y)), __fmul_rz(a.z, b.z));
 }
-RT_DEV float length(V3 a) { return __fsqrt_rz(dot(a, a)); } // vec3.h:153-166
+RT_DEV float length(V3 a) { return sqrt_rz(dot(a, a)); } // vec3.h:153-166
 RT_DEV V3 normalize(V3 a) {                                  // vec3.h:199-205
     if (a.x == 0.f && a.y == 0.f && a.z == 0.f) return a;
     return a / length(a);

@@ -168,10 +168,10 @@ __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accu
     size_t npix = size_t(width) * height;
     for (size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < npix; idx += size_t(gridDim.x) * blockDim.x) {
         float4 a = __ldg(&accum[idx]);
-        float inv = __fdiv_rz(1.0f, a.w);
-        float r = __fsqrt_rz(__saturatef(__fmul_rz(a.x, inv)));
-        float g = __fsqrt_rz(__saturatef(__fmul_rz(a.y, inv)));
-        float b = __fsqrt_rz(__saturatef(__fmul_rz(a.z, inv)));
+        float inv = div_rz(1.0f, a.w);
+        float r = sqrt_rz(__saturatef(__fmul_rz(a.x, inv)));
+        float g = sqrt_rz(__saturatef(__fmul_rz(a.y, inv)));
+        float b = sqrt_rz(__saturatef(__fmul_rz(a.z, inv)));
         if (out_rgb) {
             out_rgb[idx * 3 + 0] = r;
             out_rgb[idx * 3 + 1] = g;
@@ -223,10 +223,10 @@ __global__ void __launch_bounds__(256) k_reduce_tonemap(const __grid_constant__ 
             }
         }
         if (out_sum) out_sum[idx] = a;
-        float inv = __fdiv_rz(1.0f, a.w);
-        float r = __fsqrt_rz(__saturatef(__fmul_rz(a.x, inv)));
-        float g = __fsqrt_rz(__saturatef(__fmul_rz(a.y, inv)));
-        float b = __fsqrt_rz(__saturatef(__fmul_rz(a.z, inv)));
+        float inv = div_rz(1.0f, a.w);
+        float r = sqrt_rz(__saturatef(__fmul_rz(a.x, inv)));
+        float g = sqrt_rz(__saturatef(__fmul_rz(a.y, inv)));
+        float b = sqrt_rz(__saturatef(__fmul_rz(a.z, inv)));
         if (out_rgb) {
             out_rgb[idx * 3 + 0] = r;
             out_rgb[idx * 3 + 1] = g;
@@ -255,6 +255,19 @@ void launch_reduce_tonemap(const void* const* peer_accum, int n_peers, const voi
     unsigned blocks = unsigned(want < cap ? want : cap);
     k_reduce_tonemap<<<blocks, 256, 0, st>>>(pp, n_peers, static_cast<const float4*>(multicast), width, height, row_begin, row_end,
                                              out_rgb, out_rgb8, out_sum);
+}
+
+// --------------------------------------------------------------- self-test of the arithmetic helpers ----
+__global__ void k_selftest_rz(const float* __restrict__ x, const float* __restrict__ y, size_t n, float* __restrict__ out) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        out[4 * i + 0] = div_rz(x[i], y[i]);
+        out[4 * i + 1] = __fdiv_rz(x[i], y[i]);
+        out[4 * i + 2] = sqrt_rz(x[i]);
+        out[4 * i + 3] = __fsqrt_rz(x[i]);
+    }
+}
+void launch_selftest_rz(const float* x, const float* y, size_t n, float* out, cudaStream_t st) {
+    if (n) k_selftest_rz<<<1024, 256, 0, st>>>(x, y, n, out);
 }
 
 void launch_tonemap(const float4* accum, int width, int height, float* out_rgb, uint8_t* out_rgb8, int sm_count, cudaStream_t st) {

@@ -254,7 +254,7 @@ RT_DEV bool refract(V3 v, V3 n, float mu, V3& refracted) {
     float in = dot(i, n);
     // Written with explicit single roundings: left to the compiler, `1 - in * in` was fused into an FMA in some kernels
     // and not in others (same source, different inlining context), and the refracted rays of the persistent-lane kernel
-    // left the megakernel's by an ulp — 3.8 % of the pixels of the million-sphere frame (gpurun_out/pt_debug.log).
+    // left the megakernel's by an ulp — 3.8 % of the pixels of the million-sphere frame (round-1 debugging run).
     float delta = __fsub_rn(1.f, __fmul_rn(__fmul_rn(mu, mu), __fsub_rn(1.f, __fmul_rn(in, in))));
     if (delta > 0) {
         refracted = mu * (i - n * in) - n * sqrtf(delta);
@@ -265,7 +265,7 @@ RT_DEV bool refract(V3 v, V3 n, float mu, V3& refracted) {
 
 // utils::shlick (utils.h:124-137)
 RT_DEV float shlick(float cosine, float ref_id) {
-    float r0 = __fdiv_rz((1.f - ref_id), (1.f + ref_id));
+    float r0 = div_rz((1.f - ref_id), (1.f + ref_id));
     r0 = __fmul_rz(r0, r0);
     return r0 + __fmul_rz((1.f - r0), __powf(1.f - cosine, 5.f));
 }
@@ -406,7 +406,7 @@ RT_DEV void scatter_dielectric(const RayQ& q, V3 p, V3 n, float ri, U4 r, Ray& o
         refraction_normal = -n;
         mu = ri;
         cosine = __fdiv_rn(ddn, length(q.d));
-        cosine = __fsqrt_rz(__fsub_rn(1.f, __fmul_rn(__fmul_rn(ri, ri), __fsub_rn(1.f, __fmul_rn(cosine, cosine))))); // no contraction, as above
+        cosine = sqrt_rz(__fsub_rn(1.f, __fmul_rn(__fmul_rn(ri, ri), __fsub_rn(1.f, __fmul_rn(cosine, cosine))))); // no contraction, as above
     } else {
         refraction_normal = n;
         mu = 1.f / ri;

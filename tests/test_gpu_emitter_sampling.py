@@ -29,7 +29,7 @@ def test_flagged_render_matches_oracle_same_random_numbers(ctx, oracle, pipe, bv
     assert abs(int(st.rays) - int(nrays)) <= nrays // 100
     # Same Philox blocks, same formulas: the paths coincide, so most pixels agree to rounding.  The rest are the r = 1000
     # floor's self-intersections (tmin = 1e-5 < ulp(1000), SURVEY.md 8a' item 2) flipping with the last ulp of a direction
-    # — about 5 % of the PATHS of this scene with and without the flag (gpurun_out/nee_debug.npz).
+    # — about 5 % of the PATHS of this scene with and without the flag (round-1 debugging run).
     diff = np.abs(got[..., :3] - want[..., :3]).max(axis=2)
     assert (diff < 1e-5).mean() > 0.75, float((diff < 1e-5).mean())
     mg, mw = float(got[..., :3].mean()), float(want[..., :3].mean())

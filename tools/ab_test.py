@@ -28,7 +28,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
             out[f"{key}_{pn}_it"] = st.iterations
     print(json.dumps(out))
 else:
-    for v in sys.argv[1:]:
-        lib = ROOT / "gpurun_variants" / f"librt_{v}.so"
-        o = subprocess.run([sys.executable, __file__, "--child", str(lib)], capture_output=True, text=True)
+    for v in sys.argv[1:]:  # name[@ENV=value[,ENV=value...]]
+        name, _, envs = v.partition("@")
+        lib = ROOT / "gpurun_variants" / f"librt_{name}.so"
+        env = dict(os.environ)
+        for kv in filter(None, envs.split(",")):
+            k, _, val = kv.partition("=")
+            env[k] = val
+        o = subprocess.run([sys.executable, __file__, "--child", str(lib)], capture_output=True, text=True, env=env)
         print(v, os.environ.get("RT_WF_POOL", ""), o.stdout.strip() or o.stderr[-400:], flush=True)

@@ -1,6 +1,7 @@
-"""Renders the C1 frame (1200x600x100) three times; used under `ncu --metrics gpu__time_duration.sum` for the launch list."""
-import sys
+"""Renders the C1 frame three times with the record-block kernel (RT_WF_GRAIN=blk); used under ncu."""
+import os, sys
 from pathlib import Path
+os.environ["RT_WF_GRAIN"] = "blk"
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from raytracing_renderer_cuda_b200 import capi
