@@ -97,11 +97,15 @@ RT_DEV void test_prim(const DScene& sc, const RayQ& q, uint32_t prim, float tmin
     }
 }
 
-// hitable_list::hit with bvh == nullptr (hitable_list.h:66-78)
+// hitable_list::hit with bvh == nullptr (hitable_list.h:66-78).  FORM: 0 = decide at run time (the parity hooks and the
+// megakernel), 1 = the constant-bank list only, 2 = the global-memory list only — the wavefront kernel of list scenes is
+// instantiated for the form its scene uses, so the other loop is not in its instruction stream (the C1 kernel's time follows
+// its code size: L1.5 instruction cache = 32 KB).
+template <int FORM = 0>
 RT_DEV Hit closest_hit_list(const DScene& sc, const RayQ& q, float tmin) {
     Hit best{FLT_MAX, RT_INVALID_ID};
     float t;
-    if (sc.n_list != 0u) { // small scene: sphere data from the kernel parameters (constant bank, uniform loads)
+    if (FORM == 1 || (FORM == 0 && sc.n_list != 0u)) { // small scene: sphere data from the kernel parameters (constant bank, uniform loads)
         // (rolled on purpose: unrolled over the compile-time index the sphere data become immediate constant operands,
         // but the kernel grows from 3 800 to 5 200 instructions and loses more to instruction-cache misses than the
         // loop control costs — C1 8.01 ms unrolled, 7.41 ms rolled, 7.74 ms with the global-memory list, 8.47 ms round 1;
@@ -116,6 +120,7 @@ RT_DEV Hit closest_hit_list(const DScene& sc, const RayQ& q, float tmin) {
         }
         return best;
     }
+    if (FORM == 1) return best; // (not reached)
     // two spheres per trip: the second sphere's load is in flight while the first is tested
 #pragma unroll 2
     for (uint32_t i = 0; i < sc.n_static; ++i) {

@@ -102,8 +102,6 @@ struct WavefrontState {
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
     int persist_max = -1, window_max = 0; // L2 persistence limits of this state's device, queried on first use
-    struct WfBlkBuffers* blk = nullptr;   // record-block queues (k_wf_blk), allocated on first use
-    unsigned long long* h_blk_counts = nullptr; // pinned [2][3 * NQ]
 };
 
 // Streaming accesses to data that is read once and written once per iteration (path records, queue entries): L1
@@ -190,119 +188,6 @@ struct WfLane {
 // scatter.  Returns true when a new ray (ln.r) has to be extended.  Otherwise the entry is finished here —
 // emitter, absorbed ray, depth limit, or no path left — and `out_q` says where the slot goes (Q_NEW / Q_NONE).
 // NEE = RT_RENDER_EMITTER_SAMPLING (a separate instantiation: the reference estimator's kernels do not change).
-// The record of a path between two iterations, as four 16-byte vectors (WfRecord / the planes of a record block)
-struct RecVals {
-    float4 o, d, a;
-    uint4 ids;
-};
-template <bool NEE>
-RT_DEV bool wf_begin_core(const DScene& sc, const DRenderParams& rp, const PerlinTab& pt, int kind, bool valid, const RecVals& rv,
-                          uint32_t slot, uint32_t idx, const PathMap& pm, float4* __restrict__ accum, WfLane& ln, int& out_q) {
-    const V3 bloom = mk(rp.bloom, rp.bloom, rp.bloom);
-    bool has_ray = false;   // a ray to extend
-    bool finished = false;  // path ended: add `A` to the pixel
-    bool slot_free = false; // hand the slot to Q_NEW
-    V3 A = mk(0.f, 0.f, 0.f);
-    bool nee_vertex = false;
-    uint32_t shadow_rays = 0;
-    uint32_t pixel = 0, sample = 0, bounce = 0;
-    Ray r;
-    r.o = r.d = mk(0.f, 0.f, 0.f);
-    r.time = 0.f;
-
-    if (valid) {
-        if (kind == Q_NEW) {
-            if (idx < pm.n_valid) {
-                const uint32_t x = pm.pix_base + idx, q = fastdiv(x, rp.div_npix);
-                pixel = x - q * rp.div_npix.d;
-                sample = pm.smp_base + q + uint32_t(rp.sample_offset);
-                A = mk(rp.world_r, rp.world_g, rp.world_b);
-                if (rp.max_depth > 0) {
-                    r = camera_ray(sc, rp, pixel, sample);
-                    has_ray = true;
-                } else { // exceeded recursion before the first hit test (main.cu:42,70)
-                    A = mk(0.f, 0.f, 0.f);
-                    finished = true;
-                    slot_free = true;
-                }
-            } // else: no paths left; the slot retires
-        } else {
-            const float4 ro = rv.o, rd = rv.d, ra = rv.a;
-            const uint4 ids = rv.ids;
-            pixel = ids.x;
-            sample = ids.y;
-            bounce = ids.z;
-            RayQ q;
-            q.o = mk(ro.x, ro.y, ro.z);
-            q.d = mk(rd.x, rd.y, rd.z);
-            q.time = ro.w;
-            q.a = 0.f; // not needed for shading
-            Hit h{rd.w, __float_as_uint(ra.w)};
-            A = mk(ra.x, ra.y, ra.z);
-            V3 p, n;
-            hit_surface(sc, q, h, p, n);
-            if (kind == Q_EMIT) { // emitter::emit (material.h:50-52): value = tex * intensity + bloom; A is dropped
-                DTexture t = load_tex(sc, int32_t(ids.w));
-                float intensity = __ldg(reinterpret_cast<const float4*>(sc.mats + __ldg(&sc.sph_c[h.prim]).y) + 1).y;
-                A = texture_leaf_value(sc, pt, t, n, p) * intensity + bloom;
-                finished = true;
-                slot_free = true;
-            } else {
-                const V3 E = mk(0.f, 0.f, 0.f) + bloom; // material::emit (material.h:14-16) + bloom
-                const U4 rn = rng_block(rp.seed, pixel, sample, bounce, 0);
-                V3 att;
-                bool scattered = true;
-                if (kind == Q_METAL) {
-                    DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
-                    att = mk(m.ax, m.ay, m.az);
-                    scattered = scatter_metal(q, p, n, m.param, rn, r);
-                } else if (kind == Q_DIEL) {
-                    DMaterial m = load_mat(sc, __ldg(&sc.sph_c[h.prim]).y);
-                    att = mk(m.ax, m.ay, m.az);
-                    scatter_dielectric(q, p, n, m.param, rn, r);
-                } else {
-                    DTexture t = load_tex(sc, int32_t(ids.w));
-                    if (kind == Q_LAMB_CONST) att = tex_constant(t);
-                    else if (kind == Q_LAMB_NOISE1) att = t.kind == RT_TEX_WOOD ? tex_wood(pt, t, p) : tex_perlin(pt, t, p);
-                    else if (kind == Q_LAMB_NOISE6) att = t.kind == RT_TEX_NOISE_MARBLE ? tex_marble(pt, t, p) : tex_turbulence(pt, t, p);
-                    else att = tex_image(sc, t, n);
-                    scatter_lambertian(q, p, n, rn, r);
-                    if (NEE && int(bounce) < rp.max_depth) { // the hit's shadow/emission ray (rt_shade.cuh), traced right here
-                        const V3 c = emitter_sample(sc, rp, pt, p, n, q.time, pixel, sample, bounce, shadow_rays);
-                        if (c.x != 0.f || c.y != 0.f || c.z != 0.f) atomicAdd(&accum[pixel], make_float4(c.x, c.y, c.z, 0.f));
-                        nee_vertex = true;
-                    }
-                }
-                if (!scattered) { // absorbed (material.h:129-130): the path's value is E (main.cu:53-54)
-                    A = E;
-                    finished = true;
-                    slot_free = true;
-                } else {
-                    A = E + att * A; // main.cu:51
-                    if (int(bounce) >= rp.max_depth) { // exceeded recursion (main.cu:70)
-                        A = mk(0.f, 0.f, 0.f);
-                        finished = true;
-                        slot_free = true;
-                    } else {
-                        has_ray = true;
-                    }
-                }
-            }
-        }
-    }
-    if (finished) atomicAdd(&accum[pixel], make_float4(A.x, A.y, A.z, 1.f));
-    out_q = slot_free ? int(Q_NEW) : Q_NONE;
-    ln.nee_vertex = nee_vertex;
-    ln.shadow_rays = shadow_rays;
-    ln.slot = slot;
-    ln.pixel = pixel;
-    ln.sample = sample;
-    ln.bounce = bounce;
-    ln.A = A;
-    ln.r = r;
-    return has_ray;
-}
-
 template <bool NEE, int STREAM>
 RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind, bool valid,
                      uint32_t slot, uint32_t idx, const PathMap& pm, float4* __restrict__ accum, WfLane& ln, int& out_q) {
@@ -414,39 +299,6 @@ RT_DEV bool wf_begin(const DScene& sc, const DRenderParams& rp, const WfBuffers&
 
 // Second half: the closest hit `h` of ln.r is known.  Miss / constant emitter: the path ends (accumulate, slot to
 // Q_NEW); otherwise the record is stored and the slot goes to the shading queue of the hit.  Returns that queue.
-// (core: the record to keep is returned in `rv`; the callers store it where their queue form wants it)
-template <bool NEE>
-RT_DEV int wf_finish_core(const DScene& sc, const DRenderParams& rp, float4* __restrict__ accum, WfLane& ln, const RayQ& q, Hit h,
-                          RecVals& rv) {
-    const uint32_t bounce = ln.bounce + 1u;
-    V3 A = ln.A;
-    int out_q;
-    bool finished = false;
-    if (h.prim == RT_INVALID_ID) { // miss: the path's value is A (main.cu:66-67)
-        finished = true;
-    } else {
-        int32_t leaf;
-        V3 value;
-        out_q = classify_hit(sc, rp, q, h, leaf, value);
-        if (NEE && ln.nee_vertex && (out_q == Q_NONE || out_q == Q_EMIT) && light_listed(sc, h.prim)) {
-            A = mk(0.f, 0.f, 0.f); // this emitter was counted by the shadow ray of the hit the ray comes from
-            finished = true;
-        } else if (out_q == Q_NONE) { // constant emitter: terminate here
-            A = value;
-            finished = true;
-        } else {
-            rv.o = make_float4(ln.r.o.x, ln.r.o.y, ln.r.o.z, ln.r.time);
-            rv.d = make_float4(ln.r.d.x, ln.r.d.y, ln.r.d.z, h.t);
-            rv.a = make_float4(A.x, A.y, A.z, __uint_as_float(h.prim));
-            rv.ids = make_uint4(ln.pixel, ln.sample, bounce, uint32_t(leaf));
-        }
-    }
-    if (finished) {
-        atomicAdd(&accum[ln.pixel], make_float4(A.x, A.y, A.z, 1.f));
-        out_q = Q_NEW;
-    }
-    return out_q;
-}
 template <bool NEE, int STREAM>
 RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, float4* __restrict__ accum, WfLane& ln,
                      const RayQ& q, Hit h) {
@@ -483,7 +335,7 @@ RT_DEV int wf_finish(const DScene& sc, const DRenderParams& rp, const WfBuffers&
 
 // One whole queue entry (the CTA-chunk and warp-chunk kernels): begin, closest hit, finish.  Called by all 32 lanes of
 // the warp (the BVH traversal is warp-cooperative); `valid` = false for lanes past the end of the queue.
-template <bool USE_BVH, bool NEE, int ACC = WF_STREAM>
+template <bool USE_BVH, bool NEE, int ACC = WF_STREAM, int LIST = 0>
 RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfBuffers& wb, const PerlinTab& pt, int kind,
                             bool valid, uint32_t slot, uint32_t idx, const PathMap& pm, float4* __restrict__ accum,
                             unsigned long long& nrays) {
@@ -505,7 +357,7 @@ RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfB
         }
     } else if (has_ray) {
         const RayQ q = make_rayq(ln.r);
-        const Hit h = closest_hit_list(sc, q, rp.tmin);
+        const Hit h = closest_hit_list<LIST>(sc, q, rp.tmin);
         ++nrays;
         out_q = wf_finish<NEE, ACC>(sc, rp, wb, accum, ln, q, h);
     }
@@ -526,7 +378,7 @@ RT_DEV bool wf_frame_done(const uint32_t (&n_q)[NQ], unsigned long long path_bas
 // block-wide barriers per chunk.  Best when all rays of a chunk cost the same (brute-force scenes): C1 runs 11 % faster
 // this way than with warp chunks, whose atomic traffic (~1 atomic per 3.5 ns and queue counter) saturates the L2
 // atomic units.
-template <bool USE_BVH, bool NEE>
+template <bool USE_BVH, bool NEE, int LIST = 0>
 __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     k_wf_step_cta(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
@@ -614,7 +466,7 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
         const uint32_t idx = ck.first + threadIdx.x;
         const bool valid = idx < ck.n_kind;
 
-        const int out_q = wf_process_entry<USE_BVH, NEE>(sc, rp, wb, pt, ck.kind, valid, slot, idx, pm, accum, nrays);
+        const int out_q = wf_process_entry<USE_BVH, NEE, WF_STREAM, LIST>(sc, rp, wb, pt, ck.kind, valid, slot, idx, pm, accum, nrays);
 
         // ---- queue push: warp ballot -> shared counters -> one global atomic per queue ----
         uint32_t local = 0;
@@ -662,9 +514,6 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
 #endif
 #ifndef RT_WF_BATCH
 #define RT_WF_BATCH 8u // launches enqueued between two looks at the polled queue sizes
-#endif
-#ifndef RT_WF_BLK_DEFAULT
-#define RT_WF_BLK_DEFAULT 0 // 1: list and small-BVH scenes render with the record-block kernel unless RT_WF_GRAIN says otherwise
 #endif
 #ifndef RT_PT_MIN_SPHERES
 #define RT_PT_MIN_SPHERES 4096u // persistent-lane kernel from this many primitives on (measured: see profiles/)
@@ -961,309 +810,6 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
     if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
 }
 
-// ============================================================================================================
-// Work granularity, variant 4 (round 2): RECORD BLOCKS.  The queues hold the path records themselves instead of slot
-// indices into a pool: a shading class is a list of 8 KB blocks, a block is 128 records in SoA form (four planes of
-// 128 x 16 bytes: origin+time | direction+t | attenuation+prim | pixel, sample, bounce, leaf), and the blocks of the
-// two iteration parities live in one arena each.
-//   * input of a warp trip = 32 consecutive records of ONE plane quadruple: four contiguous 512-byte runs, fetched by
-//     the TMA engine (cp.async.bulk, one elected lane, completion on an mbarrier) into a 2 KB warp-private buffer while
-//     the warp still shades the previous 32 records — no slot-index load, no dependent record load, no registers held
-//     by the prefetch (ncu, round-1 kernel: 40 % of the stall samples sat in the queue / record plumbing that issues 18 %
-//     of the instructions; profiles/r02_c1_instruction_diet.md);
-//   * output: a warp keeps ONE open block per shading class (block id + fill in lane `class`), appends the records of a
-//     trip with four coalesced 16-byte stores per lane, and registers a block in the class list of the next iteration
-//     when it is full — one global atomic per 128 records and class instead of one per trip and class, and no block
-//     barrier anywhere (the only __syncthreads is the one behind the Perlin table);
-//   * no free-slot queue: a finished path simply is not written; the number of paths an iteration starts is
-//     min(pool - live records, paths left), derived by every warp from the class counters;
-//   * a warp draws work a whole block (or 128 new paths) at a time from the ticket counter, heavy classes first.
-// Arena blocks are handed out by a bump counter (one spare per warp is requested ahead of need, so the atomic's latency
-// never sits on the critical path); blocks that stay partially filled at the end of a launch are registered with their
-// count and cost their consumers a few idle lanes in the last 32-record trip (< 3 % of the lane slots).
-constexpr uint32_t kBlkRecs = 128u;
-constexpr uint32_t kBlkNone = 0xffffffffu;
-#ifndef WF_BLK_THREADS
-#define WF_BLK_THREADS 128
-#endif
-#ifndef WF_BLK_MINBLOCKS
-#define WF_BLK_MINBLOCKS 8 // 64 registers/thread: 32 warps per SM
-#endif
-struct WfBlkBuffers {
-    float4* arena;                 // [2][nb][4][128]: parity, block, plane, record
-    uint32_t* lists;               // [2][NQ][nb]: (block << 8) | (records - 1)
-    unsigned long long* counts;    // [3][NQ] rotating like WfBuffers::counts: low word = blocks in the list, high word = records
-    uint32_t* arena_ctr;           // [3] same rotation: blocks handed out of the arena the iteration WRITES
-    uint32_t* tickets;             // [3]
-    unsigned long long* next_path; // [2]
-    uint2* next_ps;                // [2]
-    uint32_t nb;                   // blocks per parity
-    uint32_t pool;                 // most records alive at once
-};
-RT_DEV uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-RT_DEV void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-RT_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-RT_DEV void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) { // TMA, 1-D: SASS UBLKCP
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-RT_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WF_MBAR_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@!p bra WF_MBAR_WAIT_%=;\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
-}
-RT_DEV float4* blk_plane(const WfBlkBuffers& bb, int parity, uint32_t blk, uint32_t plane) {
-    return bb.arena + ((size_t(parity) * bb.nb + blk) * 4u + plane) * kBlkRecs;
-}
-RT_DEV uint32_t* blk_list(const WfBlkBuffers& bb, int parity, int q) { return bb.lists + (size_t(parity) * NQ + size_t(q)) * bb.nb; }
-
-template <bool USE_BVH, bool NEE>
-__global__ void __launch_bounds__(WF_BLK_THREADS, WF_BLK_MINBLOCKS)
-    k_wf_blk(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBlkBuffers bb, int it,
-             float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
-    WF_PDL_PROLOGUE();
-    extern __shared__ __align__(16) uint32_t smem[]; // the Perlin table (scenes with noise textures)
-    constexpr uint32_t kWarps = WF_BLK_THREADS / 32;
-    __shared__ __align__(128) float4 s_rec[kWarps][4][32]; // per warp: the 32 records of the next trip, plane by plane
-    __shared__ __align__(8) uint64_t s_bar[kWarps];
-
-    const PerlinTab pt{smem, threadIdx.x & 31u};
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-
-    const unsigned long long* cnt_cur = bb.counts + (it % 3) * NQ;
-    unsigned long long* cnt_next = bb.counts + ((it + 1) % 3) * NQ;
-    uint32_t* arena_next = bb.arena_ctr + ((it + 1) % 3);
-    if (blockIdx.x == 0 && threadIdx.x < NQ) bb.counts[((it + 2) % 3) * NQ + threadIdx.x] = 0ull; // next iteration's targets
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        bb.arena_ctr[(it + 2) % 3] = 0u;
-        bb.tickets[(it + 2) % 3] = 0u;
-    }
-    uint32_t* ticket = bb.tickets + (it % 3);
-    const unsigned long long path_base = bb.next_path[it & 1]; // paths started by earlier iterations
-    const int par_cur = it & 1, par_next = par_cur ^ 1;
-    const unsigned long long npix = (unsigned long long)rp.width * rp.height;
-    const unsigned long long npaths = npix * (unsigned long long)rp.spp;
-
-    // chunk table: the blocks of every class, most expensive classes first, then the new paths 128 at a time
-    const int order[NQ] = {Q_LAMB_NOISE6, Q_LAMB_NOISE1, Q_LAMB_IMAGE, Q_EMIT, Q_DIEL, Q_METAL, Q_LAMB_CONST, Q_NEW};
-    __shared__ uint32_t s_chunk_end[NQ]; // (shared, not per-thread: the table is consulted once per 128 records)
-    uint32_t total_chunks = 0, live = 0, noise_chunks = 0, n_emit = 0;
-#pragma unroll
-    for (int k = 0; k < NQ - 1; ++k) {
-        const unsigned long long c = cnt_cur[order[k]];
-        total_chunks += uint32_t(c);
-        live += uint32_t(c >> 32);
-        if (threadIdx.x == 0) s_chunk_end[k] = total_chunks;
-        if (k == 1) noise_chunks = total_chunks;
-        if (order[k] == Q_EMIT) n_emit = uint32_t(c);
-    }
-    const unsigned long long left = npaths > path_base ? npaths - path_base : 0ull;
-    const uint32_t room = bb.pool > live ? bb.pool - live : 0u;
-    const uint32_t n_new = left < room ? uint32_t(left) : room;
-    total_chunks += (n_new + kBlkRecs - 1u) / kBlkRecs;
-    if (threadIdx.x == 0) s_chunk_end[NQ - 1] = total_chunks;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const unsigned long long next = path_base + n_new;
-        bb.next_path[(it + 1) & 1] = next;
-        bb.next_ps[(it + 1) & 1] = make_uint2(uint32_t(next % npix), uint32_t(next / npix));
-    }
-    if (blockIdx.x * kWarps >= total_chunks) return; // (also: the frame is finished — no live record, no path left)
-    const uint2 ps = bb.next_ps[it & 1];
-    const PathMap pm{ps.x, ps.y, n_new};
-    if (sc.has_noise && (noise_chunks != 0u || n_emit != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
-    if (lane == 0) mbar_init(&s_bar[warp], 1u);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads(); // the only block-wide barrier of the kernel
-
-    unsigned long long nrays = 0;
-    float4(*rec_in)[32] = s_rec[warp];
-    uint64_t* bar = &s_bar[warp];
-    uint32_t phase = 0u;
-
-    // ---- output side: lane q (1 <= q < NQ) keeps the open block of class q; lane 8 the warp's spare block ----
-    uint32_t my_blk = kBlkNone, my_fill = 0u;
-    uint32_t spare = 0u;
-    if (lane == 8u) spare = atomicAdd(arena_next, 1u);
-    // lane q only: one atomic per 128 records of a class (its round trip is a stall of this warp alone, once per ~4 trips)
-    auto register_block = [&](uint32_t blk, uint32_t count) {
-        const unsigned long long old = atomicAdd(cnt_next + lane, ((unsigned long long)count << 32) | 1ull);
-        blk_list(bb, par_next, int(lane))[uint32_t(old)] = (blk << 8) | (count - 1u);
-    };
-
-    // ---- input side: chunk number -> (class, block, records) ----
-    struct Chunk {
-        int kind;        // shading class, -1: none
-        uint32_t blk;    // arena block (record classes) / first Q_NEW entry (new paths)
-        uint32_t count;  // records / paths in it
-    };
-    auto locate = [&](uint32_t chunk) -> Chunk { // warp-uniform; the list entry is loaded by every lane from one address
-        Chunk c{-1, 0u, 0u};
-        if (chunk < total_chunks) {
-            int kpos = 0;
-#pragma unroll
-            for (int k = 0; k < NQ - 1; ++k) kpos += (chunk >= s_chunk_end[k]) ? 1 : 0;
-            const uint32_t i = chunk - (kpos ? s_chunk_end[kpos - 1] : 0u);
-            constexpr uint32_t kOrder = uint32_t(Q_LAMB_NOISE6) | uint32_t(Q_LAMB_NOISE1) << 4 | uint32_t(Q_LAMB_IMAGE) << 8 | uint32_t(Q_EMIT) << 12 |
-                                        uint32_t(Q_DIEL) << 16 | uint32_t(Q_METAL) << 20 | uint32_t(Q_LAMB_CONST) << 24 | uint32_t(Q_NEW) << 28;
-            c.kind = int((kOrder >> (4 * kpos)) & 15u); // order[kpos], as nibbles
-            if (c.kind == Q_NEW) {
-                c.blk = i * kBlkRecs;
-                c.count = min(kBlkRecs, n_new - c.blk);
-            } else {
-                const uint32_t e = __ldg(blk_list(bb, par_cur, c.kind) + i);
-                c.blk = e >> 8;
-                c.count = (e & 255u) + 1u;
-            }
-        }
-        return c;
-    };
-    auto prefetch = [&](const Chunk& c, uint32_t sub) { // records [32 sub, 32 sub + n) of the block -> the warp's buffer
-        if (c.kind < 0 || c.kind == Q_NEW) return;
-        const uint32_t n = min(32u, c.count - 32u * sub);
-        if (lane == 0u) {
-            mbar_expect_tx(bar, 4u * 16u * n);
-#pragma unroll
-            for (uint32_t k = 0; k < 4u; ++k) bulk_load(rec_in[k], blk_plane(bb, par_cur, c.blk, k) + 32u * sub, 16u * n, bar);
-        }
-    };
-    auto draw = [&]() -> uint32_t {
-        uint32_t c = 0u;
-        if (lane == 0u) c = atomicAdd(ticket, 1u);
-        return c;
-    };
-
-    const uint32_t n_warps_total = gridDim.x * kWarps;
-    Chunk cur = locate(blockIdx.x * kWarps + warp); // the first chunk of a warp is implicit
-    uint32_t ticket_next = draw();
-    prefetch(cur, 0u);
-    while (cur.kind >= 0) {
-        Chunk nxt{-1, 0u, 0u};
-        const uint32_t n_sub = (cur.count + 31u) / 32u;
-        for (uint32_t sub = 0; sub < n_sub; ++sub) {
-            const uint32_t n_valid = min(32u, cur.count - 32u * sub);
-            const bool valid = lane < n_valid;
-            RecVals rv;
-            if (cur.kind != Q_NEW) {
-                mbar_wait(bar, phase);
-                phase ^= 1u;
-                if (valid) {
-                    rv.o = rec_in[0][lane];
-                    rv.d = rec_in[1][lane];
-                    rv.a = rec_in[2][lane];
-                    rv.ids = *reinterpret_cast<const uint4*>(&rec_in[3][lane]);
-                }
-                __syncwarp(); // every lane holds its record: the buffer may be overwritten
-            }
-            if (sub == 0u) { // the chunk after this one: its ticket was drawn a whole chunk ago
-                const uint32_t chunk_next = n_warps_total + __shfl_sync(0xffffffffu, ticket_next, 0);
-                nxt = locate(chunk_next);
-                if (nxt.kind >= 0) ticket_next = draw();
-            }
-            if (sub + 1u < n_sub) prefetch(cur, sub + 1u);
-            else prefetch(nxt, 0u);
-
-            // ---- shade, scatter, extend, classify ----
-            WfLane ln;
-            int out_q;
-            const bool has_ray = wf_begin_core<NEE>(sc, rp, pt, cur.kind, valid, rv, 0u, cur.blk + 32u * sub + lane, pm, accum, ln, out_q);
-            if (NEE) nrays += ln.shadow_rays;
-            RecVals out;
-            if (USE_BVH) {
-                const RayQ q = make_rayq(ln.r);
-                const Hit h = closest_hit_bvh_warp(sc, q, rp.tmin, has_ray);
-                if (has_ray) {
-                    ++nrays;
-                    out_q = wf_finish_core<NEE>(sc, rp, accum, ln, q, h, out);
-                }
-            } else if (has_ray) {
-                const RayQ q = make_rayq(ln.r);
-                const Hit h = closest_hit_list(sc, q, rp.tmin);
-                ++nrays;
-                out_q = wf_finish_core<NEE>(sc, rp, accum, ln, q, h, out);
-            }
-            if (out_q == Q_NEW) out_q = Q_NONE; // a finished path leaves nothing behind
-
-            // ---- push: the records of class q go to the open block of lane q ----
-            uint32_t cq = 0u; // lane q: records of class q in this trip
-#pragma unroll
-            for (int qk = 1; qk < NQ; ++qk) {
-                const unsigned b = __ballot_sync(0xffffffffu, out_q == qk);
-                if (int(lane) == qk) cq = uint32_t(__popc(b));
-            }
-            // classes whose open block cannot take the trip's records get the spare (one at a time: rarely more than one)
-            uint32_t new_blk = kBlkNone;
-            unsigned need = __ballot_sync(0xffffffffu, cq != 0u && (my_blk == kBlkNone || my_fill + cq > kBlkRecs));
-            while (need) {
-                const int ql = __ffs(need) - 1;
-                const uint32_t got = __shfl_sync(0xffffffffu, spare, 8);
-                if (lane == 8u) spare = atomicAdd(arena_next, 1u);
-                if (int(lane) == ql) new_blk = got;
-                need &= need - 1u;
-            }
-            uint32_t d_blk0 = 0u, d_pos0 = 0u, d_room = 0u;
-            if (cq != 0u) {
-                if (my_blk == kBlkNone) { // first block of the class in this warp
-                    my_blk = new_blk;
-                    my_fill = 0u;
-                    new_blk = kBlkNone;
-                }
-                d_blk0 = my_blk;
-                d_pos0 = my_fill;
-                d_room = kBlkRecs - my_fill;
-                if (cq < d_room) {
-                    my_fill += cq;
-                } else { // the open block is full now
-                    register_block(my_blk, kBlkRecs);
-                    my_blk = new_blk; // kBlkNone when the records fitted exactly
-                    my_fill = cq - d_room;
-                }
-            }
-            const unsigned peers = __match_any_sync(0xffffffffu, out_q);
-            const int src = out_q > 0 ? out_q : 0; // (lanes without a record read lane 0's values and ignore them)
-            const uint32_t blk0 = __shfl_sync(0xffffffffu, d_blk0, src), pos0 = __shfl_sync(0xffffffffu, d_pos0, src);
-            const uint32_t room0 = __shfl_sync(0xffffffffu, d_room, src), blk1 = __shfl_sync(0xffffffffu, new_blk, src);
-            if (out_q > 0) {
-                const uint32_t r = uint32_t(__popc(peers & lt_mask));
-                const bool first = r < room0;
-                const uint32_t blk = first ? blk0 : blk1, pos = first ? pos0 + r : r - room0;
-                float4* dst = blk_plane(bb, par_next, blk, 0u) + pos;
-                __stcs(dst, out.o);
-                __stcs(dst + kBlkRecs, out.d);
-                __stcs(dst + 2u * kBlkRecs, out.a);
-                __stcs(reinterpret_cast<uint4*>(dst + 3u * kBlkRecs), out.ids);
-            }
-            __syncwarp();
-        }
-        cur = nxt;
-    }
-    // the blocks that stay partially filled, and the last registrations
-    if (lane >= 1u && lane < uint32_t(NQ) && my_blk != kBlkNone && my_fill != 0u) register_block(my_blk, my_fill);
-    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
-    if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
-}
-
-__global__ void k_wf_blk_init(const __grid_constant__ WfBlkBuffers bb) {
-    const uint32_t i = threadIdx.x;
-    if (i < 3 * NQ) bb.counts[i] = 0ull;
-    if (i < 3) bb.arena_ctr[i] = bb.tickets[i] = 0u;
-    if (i < 2) {
-        bb.next_path[i] = 0ull;
-        bb.next_ps[i] = make_uint2(0u, 0u);
-    }
-}
-
 // fills Q_NEW of iteration 0 with every slot and resets the path counter
 __global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1280,11 +826,9 @@ WavefrontState* wavefront_create(size_t pool_paths, cudaStream_t st) {
     WavefrontState* ws = new WavefrontState();
     ws->stream = st;
     ws->b.pool = uint32_t(pool_paths);
-    // (the queues themselves — 2 GiB for the slot form, 2.8 GiB for the block form at 16 Mi paths — are allocated by the
-    // first frame that uses the form: ensure_slot_buffers / ensure_blk_buffers)
+    // (the pool and its queues — 2 GiB at 16 Mi paths — are allocated by the first frame: ensure_slot_buffers)
     bool ok = cudaMallocHost(&ws->h_status, 2 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ws->h_counts, 2 * 3 * NQ * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && cudaMallocHost(&ws->h_blk_counts, 2 * 3 * NQ * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ws->poll_ev[0], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ws->poll_ev[1], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
@@ -1306,30 +850,6 @@ static bool ensure_slot_buffers(WavefrontState* ws) {
     return ok;
 }
 
-static bool ensure_blk_buffers(WavefrontState* ws, uint32_t max_warps) {
-    const uint32_t nb = ws->b.pool / kBlkRecs + 9u * max_warps + 64u; // full blocks + per warp 7 partial, 1 spare, 1 in flight
-    if (ws->blk && ws->blk->nb >= nb) return true;
-    if (!ws->blk) ws->blk = new WfBlkBuffers();
-    WfBlkBuffers& bb = *ws->blk;
-    if (bb.arena) cudaFree(bb.arena);
-    if (bb.lists) cudaFree(bb.lists);
-    bb.arena = nullptr;
-    bb.lists = nullptr;
-    bb.nb = nb;
-    bb.pool = ws->b.pool;
-    bool ok = cudaMalloc(&bb.arena, size_t(2) * nb * 4u * kBlkRecs * sizeof(float4)) == cudaSuccess;
-    ok = ok && cudaMalloc(&bb.lists, size_t(2) * NQ * nb * sizeof(uint32_t)) == cudaSuccess;
-    if (!bb.counts) {
-        ok = ok && cudaMalloc(&bb.counts, 3 * NQ * sizeof(unsigned long long)) == cudaSuccess;
-        ok = ok && cudaMalloc(&bb.arena_ctr, 3 * sizeof(uint32_t)) == cudaSuccess;
-        ok = ok && cudaMalloc(&bb.tickets, 3 * sizeof(uint32_t)) == cudaSuccess;
-        ok = ok && cudaMalloc(&bb.next_path, 2 * sizeof(unsigned long long)) == cudaSuccess;
-        ok = ok && cudaMalloc(&bb.next_ps, 2 * sizeof(uint2)) == cudaSuccess;
-    }
-    if (!ok) bb.nb = 0;
-    return ok;
-}
-
 void wavefront_destroy(WavefrontState* ws) {
     if (!ws) return;
     if (ws->b.rec) cudaFree(ws->b.rec);
@@ -1338,100 +858,14 @@ void wavefront_destroy(WavefrontState* ws) {
     if (ws->b.tickets) cudaFree(ws->b.tickets);
     if (ws->b.next_path) cudaFree(ws->b.next_path);
     if (ws->b.next_ps) cudaFree(ws->b.next_ps);
-    if (ws->blk) {
-        WfBlkBuffers& bb = *ws->blk;
-        if (bb.arena) cudaFree(bb.arena);
-        if (bb.lists) cudaFree(bb.lists);
-        if (bb.counts) cudaFree(bb.counts);
-        if (bb.arena_ctr) cudaFree(bb.arena_ctr);
-        if (bb.tickets) cudaFree(bb.tickets);
-        if (bb.next_path) cudaFree(bb.next_path);
-        if (bb.next_ps) cudaFree(bb.next_ps);
-        delete ws->blk;
-    }
     for (auto& e : ws->poll_ev)
         if (e) cudaEventDestroy(e);
     if (ws->h_status) cudaFreeHost(ws->h_status);
     if (ws->h_counts) cudaFreeHost(ws->h_counts);
-    if (ws->h_blk_counts) cudaFreeHost(ws->h_blk_counts);
     delete ws;
 }
 
 size_t wavefront_pool(const WavefrontState* ws) { return ws ? ws->b.pool : 0; }
-
-// The frame loop of the record-block form (k_wf_blk): the same batching and polling as the slot form below.
-static bool wavefront_render_blk(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, bool nee, size_t smem,
-                                 unsigned long long npaths, float4* accum, unsigned long long* ray_counter, int sm_count,
-                                 cudaStream_t st, uint32_t* launches, uint32_t* iterations) {
-    constexpr unsigned kWarps = WF_BLK_THREADS / 32;
-    const unsigned cap = unsigned(sm_count) * WF_BLK_MINBLOCKS; // resident CTAs only: work is drawn dynamically
-    if (!ensure_blk_buffers(ws, cap * kWarps)) return false;
-    const WfBlkBuffers bb = *ws->blk;
-    const unsigned long long slots = npaths < bb.pool ? npaths : bb.pool;
-    const unsigned need = unsigned((slots / kBlkRecs + kWarps) / kWarps) + 1u;
-    const unsigned grid = need < cap ? need : cap;
-    k_wf_blk_init<<<1, 32, 0, st>>>(bb);
-    ++*launches;
-    auto launch = [&](auto kernel, int it) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(WF_BLK_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-#ifndef WF_NO_PDL
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-#else
-        attr[0].val.programmaticStreamSerializationAllowed = 0;
-#endif
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, kernel, sc, rp, bb, it, accum, ray_counter);
-    };
-    uint32_t it = 0;
-    auto enqueue = [&](uint32_t count) {
-        for (uint32_t k = 0; k < count; ++k, ++it) {
-            if (nee) {
-                if (use_bvh) launch(k_wf_blk<true, true>, int(it));
-                else launch(k_wf_blk<false, true>, int(it));
-            } else {
-                if (use_bvh) launch(k_wf_blk<true, false>, int(it));
-                else launch(k_wf_blk<false, false>, int(it));
-            }
-            ++*launches;
-        }
-    };
-    uint32_t it_after[2] = {0u, 0u};
-    auto snapshot = [&](int par) {
-        cudaMemcpyAsync(ws->h_blk_counts + par * 3 * NQ, bb.counts, 3 * NQ * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(ws->h_status + par, bb.next_path + (it & 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-        cudaEventRecord(ws->poll_ev[par], st);
-        it_after[par] = it;
-    };
-    const unsigned long long generations = (npaths + slots - 1) / slots;
-    const unsigned long long max_iters = (generations + 1ull) * ((unsigned long long)rp.max_depth + 2ull) + 64ull; // see wavefront_render
-    bool complete = false;
-    enqueue(uint32_t(2ull * generations + 4ull < max_iters ? 2ull * generations + 4ull : max_iters));
-    snapshot(0);
-    int par = 0;
-    while (true) {
-        enqueue(RT_WF_BATCH);
-        snapshot(par ^ 1);
-        if (cudaEventSynchronize(ws->poll_ev[par]) != cudaSuccess) break;
-        const unsigned long long* c = ws->h_blk_counts + par * 3 * NQ + (it_after[par] % 3) * NQ; // the lists of the next iteration
-        unsigned long long live = 0;
-        for (int k = 1; k < NQ; ++k) live += c[k] >> 32;
-        if (live == 0 && ws->h_status[par] >= npaths) {
-            complete = true;
-            break;
-        }
-        if (it >= max_iters) break;
-        par ^= 1;
-    }
-    *iterations = it;
-    return complete;
-}
 
 bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams& rp, bool use_bvh, float4* accum,
                       unsigned long long* ray_counter, int sm_count, cudaStream_t st, uint32_t* launches,
@@ -1446,13 +880,6 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     const size_t smem = sc.has_noise ? RT_PERLIN_SMEM_WORDS * sizeof(uint32_t) : 0;
     // emitter importance sampling: a scene without emitters renders with the reference estimator's kernels
     const bool nee = (rp.flags & RT_RENDER_EMITTER_SAMPLING) != 0u && sc.n_lights > 0u;
-    // Queue form: record blocks (k_wf_blk) or slot indices (the round-1 kernels).  RT_WF_GRAIN=blk|cta|warp|pt overrides.
-    {
-        const char* e = getenv("RT_WF_GRAIN");
-        const bool big = use_bvh && sc.n_spheres >= RT_PT_MIN_SPHERES; // persistent lanes (slot form) walk large trees
-        const bool want_blk = e ? e[0] == 'b' : (RT_WF_BLK_DEFAULT != 0 && !big);
-        if (want_blk) return wavefront_render_blk(ws, sc, rp, use_bvh, nee, smem, npaths, accum, ray_counter, sm_count, st, launches, iterations);
-    }
     if (!ensure_slot_buffers(ws)) return false;
     // slots in use: never more than there are paths
     WfBuffers wb = ws->b;
@@ -1551,10 +978,12 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
             } else {
                 if (nee) {
                     if (use_bvh) launch(k_wf_step_cta<true, true>, sc, rp, wb, int(it), accum, ray_counter);
-                    else launch(k_wf_step_cta<false, true>, sc, rp, wb, int(it), accum, ray_counter);
+                    else if (sc.n_list) launch(k_wf_step_cta<false, true, 1>, sc, rp, wb, int(it), accum, ray_counter);
+                    else launch(k_wf_step_cta<false, true, 2>, sc, rp, wb, int(it), accum, ray_counter);
                 } else {
                     if (use_bvh) launch(k_wf_step_cta<true, false>, sc, rp, wb, int(it), accum, ray_counter);
-                    else launch(k_wf_step_cta<false, false>, sc, rp, wb, int(it), accum, ray_counter);
+                    else if (sc.n_list) launch(k_wf_step_cta<false, false, 1>, sc, rp, wb, int(it), accum, ray_counter);
+                    else launch(k_wf_step_cta<false, false, 2>, sc, rp, wb, int(it), accum, ray_counter);
                 }
             }
             ++*launches;
