@@ -263,8 +263,8 @@ rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info);
 
 /* Parity hook: closest hit of scene.hit(r, tmin, FLT_MAX) (hitable_list.h:60-79)
  * for n caller-supplied rays.  use_bvh = 0 forces the brute-force list path, 1 walks the binary BVH
- * (bvh_node::dfs, bvh.h:121-155), 2 the 4-wide form of the same tree that the large-scene render kernel
- * traverses (RT_ERR_INVALID_ARG when the scene has none: it is built from 4096 primitives on). */
+ * (bvh_node::dfs, bvh.h:121-155), 2 the 4-wide form of the same tree, 3 its 64-byte quantised form — the nodes the
+ * large-scene render kernel traverses (RT_ERR_INVALID_ARG when the scene has none). */
 rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray* rays, size_t n,
                            float tmin, int use_bvh, rt_hit* hits);
 

@@ -585,6 +585,7 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
         }
     }
     rtd::BvhNode4* dnodes4 = nullptr;
+    rtd::BvhNode4Q* dnodes4q = nullptr;
     uint32_t n_nodes4 = 0, root4 = 0;
     if (dnodes && n_nodes) { // the 4-wide form the persistent-lane kernel walks (half the dependent node fetches per ray)
         if ((st = dev_alloc(s, &dnodes4, n_nodes / 2 + 64)) != RT_OK) return st;
@@ -602,6 +603,17 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
         if (e != cudaSuccess) {
             set_error("4-wide BVH collapse failed: %s", cudaGetErrorString(e));
             return RT_ERR_CUDA;
+        }
+        // ... and the 64-byte quantised form of the same nodes (kept only when every node is representable)
+        if (n_nodes4 && !getenv("RT_NO_BVH4Q")) {
+            if ((st = dev_alloc(s, &dnodes4q, n_nodes4)) != RT_OK) return st;
+            bool quant_ok = false;
+            e = rtd::bvh_quantize4(dnodes4, n_nodes4, dnodes4q, &quant_ok, stream);
+            if (e != cudaSuccess) {
+                set_error("4-wide BVH quantisation failed: %s", cudaGetErrorString(e));
+                return RT_ERR_CUDA;
+            }
+            if (!quant_ok) dnodes4q = nullptr; // (the memory stays with the scene; the walk uses the 128-byte nodes)
         }
     }
     if (bstats.depth > RT_BVH_STACK_DEPTH) {
@@ -686,6 +698,7 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     s->d.n_static = n_static;
     s->d.nodes = dnodes;
     s->d.nodes4 = dnodes4;
+    s->d.nodes4q = dnodes4q;
     s->d.n_nodes4 = n_nodes4;
     s->d.root4 = root4;
     s->d.n_nodes = n_nodes;
@@ -758,8 +771,9 @@ rt_status rt_trace_primary(rt_context* ctx, const rt_scene* scene, const rt_ray*
                            rt_hit* hits) try {
     ARG_CHECK(ctx && scene, "ctx/scene is NULL");
     ARG_CHECK(n == 0 || (rays && hits), "rays/hits is NULL");
-    ARG_CHECK(use_bvh >= 0 && use_bvh <= 2, "use_bvh must be 0 (list), 1 (BVH) or 2 (4-wide BVH)");
-    ARG_CHECK(use_bvh != 2 || scene->d.nodes4 != nullptr, "use_bvh = 2: the scene has no 4-wide nodes (built from 4096 primitives on)");
+    ARG_CHECK(use_bvh >= 0 && use_bvh <= 3, "use_bvh must be 0 (list), 1 (BVH), 2 (4-wide BVH) or 3 (quantised 4-wide BVH)");
+    ARG_CHECK(use_bvh != 2 || scene->d.nodes4 != nullptr, "use_bvh = 2: the scene has no 4-wide nodes");
+    ARG_CHECK(use_bvh != 3 || scene->d.nodes4q != nullptr, "use_bvh = 3: the scene has no quantised 4-wide nodes");
     if (n == 0) return RT_OK;
     rt_status st = make_current(ctx);
     if (st != RT_OK) return st;

@@ -112,6 +112,19 @@ struct BvhNode4 {
 };
 #define RT_BVH4_EMPTY 0x7fffffff
 
+// The same 4-wide node in 64 bytes (round 2): the child boxes as 8-bit offsets from the node's own corner, in units of a
+// per-axis power of two — decoded box = p + q * 2^e, at least one unit OUTSIDE the float box on every side (k_quantize4,
+// rt_lbvh.cu), so the walk stays conservative and the closest hit is unchanged (leaves test the spheres themselves).
+// Why: ncu on the 1 M-sphere scene showed k_wf_step_pt bound by L1 request slots, not by latency alone (l1tex 88 % busy:
+// every lane fetches its own 128-byte node with seven LDG.128, one tag look-up each); four loads per visit instead of seven.
+//   q0 = (p.x, p.y, p.z, ex | ey << 8 | ez << 16)   e? = biased exponent byte of the unit (float bits = e? << 23)
+//   q1 = refs[4]
+//   q2 = (lo.x[4], lo.y[4], lo.z[4], hi.x[4])       one byte per child
+//   q3 = (hi.y[4], hi.z[4], 0, 0)
+struct BvhNode4Q {
+    uint4 q0, q1, q2, q3;
+};
+
 #define RT_MAX_IMAGES 8
 #define RT_LIST_MAX 12 // scenes of up to this many spheres travel inside the kernel parameters (constant bank), see DScene::lst_*
 #define RT_BVH_STACK_DEPTH 64 // per-thread traversal stack entries (rt_intersect.cuh)
@@ -125,6 +138,7 @@ struct DScene {
     uint32_t n_static;
     const BvhNode* nodes; // nullptr => brute force
     const BvhNode4* nodes4; // 4-wide form of the same tree (densely renumbered), nullptr if not built
+    const BvhNode4Q* nodes4q; // ... and its 64-byte quantised form (same numbering), nullptr if not built / not representable
     uint32_t n_nodes4;
     uint32_t root4;
     uint32_t n_nodes;

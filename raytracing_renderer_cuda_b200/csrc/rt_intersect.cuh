@@ -271,6 +271,52 @@ RT_DEV void trav_inner(const DScene& sc, const RayQ& q, float tmin, Trav& t, int
     }
   }
 }
+// One visit of a QUANTISED 4-wide node (BvhNode4Q): four 16-byte loads instead of seven.  The ray is moved into the
+// node's grid once per axis — s = unit * (1/d), o = p * (1/d) - origin * (1/d), the same FFMA form as slab() — and every
+// bound is then ONE FFMA on a byte: t = q * s + o.  The decoded boxes contain the float boxes with a whole unit to
+// spare (k_quantize4), so the test can only add visits; acceptance test, far-bound margin, ordering network and stack
+// discipline are those of the 128-byte form.
+RT_DEV float byte_f(uint32_t w, int k) { return float((w >> (8 * k)) & 255u); }
+RT_DEV void trav_inner_q(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {
+    const uint4* np = reinterpret_cast<const uint4*>(sc.nodes4q + t.node);
+    const uint4 q0 = __ldg(np + 0), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+    const float sx = __uint_as_float((q0.w & 0xffu) << 23) * t.inv.x;
+    const float sy = __uint_as_float((q0.w & 0xff00u) << 15) * t.inv.y;
+    const float sz = __uint_as_float((q0.w & 0xff0000u) << 7) * t.inv.z;
+    const float ox = __fmaf_rn(__uint_as_float(q0.x), t.inv.x, t.noi.x);
+    const float oy = __fmaf_rn(__uint_as_float(q0.y), t.inv.y, t.noi.y);
+    const float oz = __fmaf_rn(__uint_as_float(q0.z), t.inv.z, t.noi.z);
+    float key[4];
+    int ref[4] = {int(q1.x), int(q1.y), int(q1.z), int(q1.w)};
+    int nhit = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const float tx0 = __fmaf_rn(byte_f(q2.x, s), sx, ox), tx1 = __fmaf_rn(byte_f(q2.w, s), sx, ox);
+        const float ty0 = __fmaf_rn(byte_f(q2.y, s), sy, oy), ty1 = __fmaf_rn(byte_f(q3.x, s), sy, oy);
+        const float tz0 = __fmaf_rn(byte_f(q2.z, s), sz, oz), tz1 = __fmaf_rn(byte_f(q3.y, s), sz, oz);
+        const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
+        const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), t.best.t));
+        const bool hit = tn <= __fmaf_rn(tf, RT_SLAB_FAR_WIDEN, t.e) && ref[s] != RT_BVH4_EMPTY;
+        key[s] = hit ? tn : __int_as_float(0x7f800000); // +inf: misses sort to the end
+        nhit += hit ? 1 : 0;
+    }
+#define RT_CSWAP(a, b)                       \
+    {                                        \
+        const bool sw = key[b] < key[a];     \
+        const float ka = key[a], kb = key[b]; \
+        const int ra = ref[a], rb = ref[b];  \
+        key[a] = sw ? kb : ka;               \
+        key[b] = sw ? ka : kb;               \
+        ref[a] = sw ? rb : ra;               \
+        ref[b] = sw ? ra : rb;               \
+    }
+    RT_CSWAP(0, 1) RT_CSWAP(2, 3) RT_CSWAP(0, 2) RT_CSWAP(1, 3) RT_CSWAP(1, 2)
+#undef RT_CSWAP
+    if (nhit > 3 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[3];
+    if (nhit > 2 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[2];
+    if (nhit > 1 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[1];
+    t.node = nhit ? ref[0] : (t.sp ? stack[--t.sp] : RT_TRAV_DONE);
+}
 // one leaf test (precondition: t.node < 0)
 RT_DEV void trav_leaf(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {
     test_prim(sc, q, uint32_t(~t.node), tmin, t.best);
@@ -295,13 +341,17 @@ RT_DEV Hit closest_hit_bvh(const DScene& sc, const RayQ& q, float tmin) {
 // The same walk over the 4-wide nodes (the tree k_wf_step_pt traverses; built from RT_PT_MIN_SPHERES primitives on):
 // per-lane loop, used by the parity hook (rt_trace_primary, use_bvh = 2) so that the wide traversal is compared
 // with the reference kernel ray by ray.
+template <bool QUANT = false>
 RT_DEV Hit closest_hit_bvh4(const DScene& sc, const RayQ& q, float tmin) {
     int stack[RT_BVH_STACK];
     Trav t;
     trav_begin(sc, q, t);
     t.node = int(sc.root4);
     while (true) {
-        while (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner<true>(sc, q, tmin, t, stack);
+        while (t.node >= 0 && t.node != RT_TRAV_DONE) {
+            if (QUANT) trav_inner_q(sc, q, tmin, t, stack);
+            else trav_inner<true>(sc, q, tmin, t, stack);
+        }
         if (t.node == RT_TRAV_DONE) break;
         trav_leaf(sc, q, tmin, t, stack);
     }

@@ -16,7 +16,9 @@ __global__ void __launch_bounds__(256) k_trace_primary(const __grid_constant__ D
     r.d = mk(in.direction[0], in.direction[1], in.direction[2]);
     r.time = in.time;
     RayQ q = make_rayq(r);
-    Hit h = (use_bvh == 2 && sc.nodes4) ? closest_hit_bvh4(sc, q, tmin) : closest_hit(sc, q, tmin, use_bvh != 0);
+    Hit h = (use_bvh == 3 && sc.nodes4q) ? closest_hit_bvh4<true>(sc, q, tmin)
+            : (use_bvh == 2 && sc.nodes4)  ? closest_hit_bvh4<false>(sc, q, tmin)
+                                           : closest_hit(sc, q, tmin, use_bvh != 0);
     rt_hit out;
     if (h.prim == RT_INVALID_ID) {
         out.t = FLT_MAX;

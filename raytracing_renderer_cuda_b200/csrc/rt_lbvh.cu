@@ -277,6 +277,93 @@ __global__ void __launch_bounds__(256) k_compact4(const BvhNode4* __restrict__ i
 }
 } // namespace
 
+namespace {
+// 64-byte form of the dense 4-wide nodes (BvhNode4Q, rt_device.cuh).  Per axis: unit = the smallest power of two with
+// extent / unit <= 251 (and >= 4 ulp of the coordinates, so that the corner's own rounding stays inside the margin),
+// corner p = min - unit rounded DOWN, lo byte = floor((lo - p) / unit) - 1 >= 0, hi byte = ceil((hi - p) / unit) + 1 <= 255:
+// every decoded bound lies at least one unit outside the float box.  Nodes this cannot represent (units beyond 2^20,
+// a clamped byte) raise `bad`; the scene then keeps the 128-byte nodes.
+__global__ void __launch_bounds__(256) k_quantize4(const BvhNode4* __restrict__ in, uint32_t n, BvhNode4Q* __restrict__ out,
+                                                   uint32_t* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BvhNode4 nd = in[i];
+    const float lo[3][4] = {{nd.mnx.x, nd.mnx.y, nd.mnx.z, nd.mnx.w}, {nd.mny.x, nd.mny.y, nd.mny.z, nd.mny.w}, {nd.mnz.x, nd.mnz.y, nd.mnz.z, nd.mnz.w}};
+    const float hi[3][4] = {{nd.mxx.x, nd.mxx.y, nd.mxx.z, nd.mxx.w}, {nd.mxy.x, nd.mxy.y, nd.mxy.z, nd.mxy.w}, {nd.mxz.x, nd.mxz.y, nd.mxz.z, nd.mxz.w}};
+    const int ref[4] = {nd.refs.x, nd.refs.y, nd.refs.z, nd.refs.w};
+    uint32_t qlo[3] = {0u, 0u, 0u}, qhi[3] = {0u, 0u, 0u}, exps = 0u;
+    float p[3];
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double mn = 1e300, mx = -1e300;
+        for (int c = 0; c < 4; ++c)
+            if (ref[c] != RT_BVH4_EMPTY) {
+                mn = fmin(mn, double(lo[a][c]));
+                mx = fmax(mx, double(hi[a][c]));
+            }
+        if (mn > mx) mn = mx = 0.0;
+        int e = -100;
+        if (mx > mn) {
+            frexp((mx - mn) / 251.0, &e); // (mx - mn) / 251 = m * 2^e with m in [0.5, 1): 2^e >= (mx - mn) / 251
+        }
+        const double mag = fmax(fabs(mn), fabs(mx));
+        if (mag > 0.0) {
+            int em;
+            frexp(mag, &em);        // mag < 2^em: ulp(mag) <= 2^(em - 24)
+            e = max(e, em - 24 + 2); // unit >= 4 ulp of the coordinates
+        }
+        e = max(e, -100);
+        ok = ok && e <= 20 && isfinite(mn) && isfinite(mx);
+        e = min(e, 20);
+        const double unit = ldexp(1.0, e);
+        const float pa = __double2float_rd(mn - unit);
+        p[a] = pa;
+        exps |= uint32_t(e + 127) << (8 * a);
+        for (int c = 0; c < 4; ++c) {
+            uint32_t bl = 255u, bh = 0u; // an empty slot: inverted box (and its reference says so)
+            if (ref[c] != RT_BVH4_EMPTY) {
+                const double l = floor((double(lo[a][c]) - double(pa)) / unit) - 1.0;
+                const double h = ceil((double(hi[a][c]) - double(pa)) / unit) + 1.0;
+                ok = ok && l >= 0.0 && h <= 255.0;
+                bl = uint32_t(fmin(fmax(l, 0.0), 255.0));
+                bh = uint32_t(fmin(fmax(h, 0.0), 255.0));
+            }
+            qlo[a] |= bl << (8 * c);
+            qhi[a] |= bh << (8 * c);
+        }
+    }
+    if (!ok) atomicOr(bad, 1u);
+    BvhNode4Q q;
+    q.q0 = make_uint4(__float_as_uint(p[0]), __float_as_uint(p[1]), __float_as_uint(p[2]), exps);
+    q.q1 = make_uint4(uint32_t(ref[0]), uint32_t(ref[1]), uint32_t(ref[2]), uint32_t(ref[3]));
+    q.q2 = make_uint4(qlo[0], qlo[1], qlo[2], qhi[0]);
+    q.q3 = make_uint4(qhi[1], qhi[2], 0u, 0u);
+    out[i] = q;
+}
+} // namespace
+
+// out_q (may be nullptr) receives the quantised form of the first *n_out nodes of `out`; *quant_ok tells whether every node
+// was representable.
+cudaError_t bvh_quantize4(const BvhNode4* nodes4, uint32_t n4, BvhNode4Q* out_q, bool* quant_ok, cudaStream_t st) {
+    *quant_ok = false;
+    if (n4 == 0 || !out_q) return cudaSuccess;
+    uint32_t* bad = nullptr;
+    cudaError_t e = rtd::malloc_async(&bad, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(bad, 0, sizeof(uint32_t), st);
+    if (e == cudaSuccess) {
+        k_quantize4<<<(n4 + 255) / 256, 256, 0, st>>>(nodes4, n4, out_q, bad);
+        e = cudaGetLastError();
+    }
+    uint32_t h = 1u;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, bad, sizeof h, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(bad, st);
+    *quant_ok = e == cudaSuccess && h == 0u;
+    return e;
+}
+
 // 4-wide form of a finished binary tree.  Only every other level of the binary tree survives as a 4-wide node, so
 // the reachable nodes are marked from the root, numbered by an exclusive scan and written densely: the array a ray
 // walks is then as large as the binary one (n/2 nodes of 128 B) and can be pinned in L2 as a whole.

@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 // 775-820 (11 of 32), this kernel 880-940.  On C2/C3 (a few hundred spheres, shading a third of the work) the
 // partial-width shading of refilled lanes costs more than the traversal gains (C2: 10.3 -> 7.1 Grays/s), so the
 // kernel is used from RT_PT_MIN_SPHERES primitives on.
-template <bool NEE>
+template <bool NEE, bool QUANT>
 __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
     k_wf_step_pt(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
                  int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter, int refill, int leaf_lanes) {
@@ -795,7 +795,10 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
 #ifdef RT_PT_BINARY // A/B: the binary tree
             if (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner<false>(sc, q, rp.tmin, t, stack);
 #else
-            if (t.node >= 0 && t.node != RT_TRAV_DONE) trav_inner<true>(sc, q, rp.tmin, t, stack); // 4-wide nodes
+            if (t.node >= 0 && t.node != RT_TRAV_DONE) { // 4-wide nodes, 64-byte (quantised) or 128-byte form
+                if (QUANT) trav_inner_q(sc, q, rp.tmin, t, stack);
+                else trav_inner<true>(sc, q, rp.tmin, t, stack);
+            }
 #endif
             const unsigned at_leaf = __ballot_sync(0xffffffffu, t.node < 0);
             const unsigned can_go = __ballot_sync(0xffffffffu, t.node >= 0 && t.node != RT_TRAV_DONE);
@@ -904,6 +907,9 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         if (v >= 1 && v <= 32) leaf_lanes = v;
     }
     const bool warp_grain = grain != G_CTA;
+    // node form of the persistent-lane kernel: the 64-byte quantised nodes when the scene has them (RT_BVH4=f: the 128-byte ones)
+    bool quant = sc.nodes4q != nullptr;
+    if (const char* e = getenv("RT_BVH4")) quant = quant && e[0] != 'f';
     unsigned grid;
     if (warp_grain) { // resident CTAs only: work is drawn dynamically
         const unsigned cap = unsigned(sm_count) * (grain == G_PT ? WF_PT_MINBLOCKS : WF_MINBLOCKS);
@@ -931,9 +937,9 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         if (persist_max > 0 && window_max > 0) {
             cudaStreamAttrValue av{};
             const bool wide = grain == G_PT;
-            size_t bytes = size_t(wide ? sc.n_nodes4 : sc.n_nodes) * (wide ? sizeof(BvhNode4) : sizeof(BvhNode));
+            size_t bytes = size_t(wide ? sc.n_nodes4 : sc.n_nodes) * (wide ? (quant ? sizeof(BvhNode4Q) : sizeof(BvhNode4)) : sizeof(BvhNode));
             if (bytes > size_t(window_max)) bytes = size_t(window_max);
-            av.accessPolicyWindow.base_ptr = wide ? (void*)sc.nodes4 : (void*)sc.nodes;
+            av.accessPolicyWindow.base_ptr = wide ? (quant ? (void*)sc.nodes4q : (void*)sc.nodes4) : (void*)sc.nodes;
             av.accessPolicyWindow.num_bytes = bytes;
             const float ratio = float(double(persist_max) * 0.9 / double(bytes));
             av.accessPolicyWindow.hitRatio = ratio < 1.f ? ratio : 1.f;
@@ -965,8 +971,13 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     auto enqueue = [&](uint32_t count) {
         for (uint32_t k = 0; k < count; ++k, ++it) {
             if (grain == G_PT) {
-                if (nee) launch(k_wf_step_pt<true>, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
-                else launch(k_wf_step_pt<false>, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
+                if (quant) {
+                    if (nee) launch(k_wf_step_pt<true, true>, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
+                    else launch(k_wf_step_pt<false, true>, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
+                } else {
+                    if (nee) launch(k_wf_step_pt<true, false>, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
+                    else launch(k_wf_step_pt<false, false>, sc, rp, wb, int(it), accum, ray_counter, refill, leaf_lanes);
+                }
             } else if (warp_grain) {
                 if (nee) {
                     if (use_bvh) launch(k_wf_step_warp<true, true>, sc, rp, wb, int(it), accum, ray_counter);

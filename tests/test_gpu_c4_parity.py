@@ -61,10 +61,10 @@ def test_closest_hits_match_the_reference_kernel(ctx, gold, desc, which):
     for mode, name in ((capi.RT_BVH_HOST_SAH, "host_sah"), (capi.RT_BVH_GPU_LBVH, "gpu_lbvh")):
         sc = _scene(ctx, desc, mode)
         assert sc.info().bvh_mode == mode
-        for use_bvh in (1, 2):  # binary nodes, 4-wide nodes
+        for use_bvh in (1, 2, 3):  # binary nodes, 4-wide nodes, quantised 4-wide nodes (what k_wf_step_pt walks)
             got = sc.trace_primary(rays, use_bvh=use_bvh)
             bad = np.nonzero(~_same(got, ref_bvh))[0]
-            record_parity("c4_trace", rays=which, builder=name, nodes="4-wide" if use_bvh == 2 else "binary", n_rays=len(rays),
+            record_parity("c4_trace", rays=which, builder=name, nodes={1: "binary", 2: "4-wide", 3: "4-wide quantised"}[use_bvh], n_rays=len(rays),
                           mismatches=len(bad), reference_bvh_vs_reference_list=ref_self)
             assert len(bad) <= max(8, 4 * ref_self), (name, use_bvh, len(bad))
             if len(bad):  # on every such ray one side reports a hit on a sphere the ray misses in float64 geometry

@@ -122,13 +122,14 @@ def test_bvh_equals_brute_force_on_many_spheres(ctx, n, spread):
         sc = _scene(ctx, d, mode)
         assert sc.info().bvh_mode == mode and sc.info().n_nodes == n
         for r, w in ((rays, lst), (sec, lst2)):
-            got = sc.trace_primary(r, use_bvh=True)
+          for use_bvh in (1, 2, 3):  # binary, 4-wide, quantised 4-wide nodes
+            got = sc.trace_primary(r, use_bvh=use_bvh)
             bad = np.nonzero((got["id"] != w["id"]) | (got["t"] != w["t"]))[0]
             if spread != 1.0:
-                assert len(bad) == 0, (mode, len(bad))
+                assert len(bad) == 0, (mode, use_bvh, len(bad))
                 assert got.tobytes() == w.tobytes()
             else:
-                assert len(bad) < 1e-3 * len(r), (mode, len(bad))
+                assert len(bad) < 1e-3 * len(r), (mode, use_bvh, len(bad))
                 assert (w["id"][bad] != capi.RT_INVALID_ID).all()           # the list claims a hit ...
                 assert (_true_miss_distance(r[bad], by_id, w["id"][bad]) > 0).all()  # ... on a sphere the ray misses
                 ok = np.setdiff1d(np.arange(len(r)), bad)
@@ -394,12 +395,24 @@ def test_million_sphere_scene_every_kernel_renders_the_same_image(ctx, monkeypat
     assert sc.info().bvh_mode == capi.RT_BVH_GPU_LBVH and sc.info().n_nodes == 1_000_000
     w, h, spp = 640, 360, 2
     ref, st_ref = sc.render_accum(rt.default_params(width=w, height=h, spp=spp, pipeline=capi.RT_PIPE_MEGAKERNEL))
-    for grain in ("pt", "warp"):
+    for grain, nodes in (("pt", "q"), ("pt", "f"), ("warp", "q")):  # (RT_BVH4: quantised 64-byte / float 128-byte 4-wide nodes)
         monkeypatch.setenv("RT_WF_GRAIN", grain)
+        monkeypatch.setenv("RT_BVH4", nodes)
         got, st = sc.render_accum(rt.default_params(width=w, height=h, spp=spp))
-        assert st.rays == st_ref.rays, grain
         assert np.array_equal(got[..., 3], ref[..., 3])
-        assert np.abs(got[..., :3] - ref[..., :3]).max() < 1e-5, grain
+        if nodes == "f" or grain == "warp":  # the float boxes of the binary tree, regrouped: the same leaves are visited
+            assert st.rays == st_ref.rays, (grain, nodes)
+            assert np.abs(got[..., :3] - ref[..., :3]).max() < 1e-5, (grain, nodes)
+        else:
+            # The quantised boxes are up to two units wider, so a few more leaves are visited — and at this geometry the float32
+            # sphere quadratic reports "phantom" hits on spheres the ray misses, which tighter boxes cull:
+            # the reference's own BVH and list disagree on 1.25e-4 of the camera rays of this generator (tests/golden/
+            # ref_gpu_golden_c4.npz).  Measured here: 27 of 1.77 M rays (1.5e-5).  Every closest hit is still checked ray by ray
+            # against the reference kernel and against brute force in test_gpu_c4_parity / test_bvh_equals_brute_force.
+            differ = (np.abs(got[..., :3] - ref[..., :3]).max(axis=2) > 1e-5).mean()
+            record_parity("million_spheres_quantised_nodes", rays=int(st.rays), rays_float_nodes=int(st_ref.rays), pixels_differing=float(differ))
+            assert abs(int(st.rays) - int(st_ref.rays)) <= 1e-4 * st_ref.rays, (grain, nodes)
+            assert differ <= 2e-4, differ
 
 
 def test_8k_frame_pixel_indices_beyond_2_pow_24(ctx, oracle, scene_descs):
