@@ -257,7 +257,10 @@ rt_status rt_context_synchronize(rt_context* ctx);
  * SoA sphere arrays and builds the acceleration structure. */
 rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene** out);
 /* A scene belongs to its context (device memory comes from the context's stream-ordered pool and is
- * released on the context stream): destroy scenes before their context. */
+ * released on the context stream): destroy scenes before their context.  A scene may be RENDERED through another
+ * context of the same device (frame pipelines: one context uploads scene k+1 on its stream while another renders
+ * frame k); the caller then destroys a scene only after the frames that use it have completed.  Contexts may be used
+ * from different host threads at the same time; one context is used by one thread at a time. */
 void rt_scene_destroy(rt_scene* scene); /* replaces free_scene<<<1,1>>> (main.cu:360-366) */
 rt_status rt_scene_get_info(const rt_scene* scene, rt_scene_info* info);
 

@@ -382,9 +382,10 @@ class Scene:
         _check(self.lib, self.lib.rt_render_accum(self.ctx._h, self._h, C.byref(params), out.ctypes.data, C.byref(st)))
         return out, st
 
-    def render_accum_device(self, params: rt_render_params, accum_ptr: int, want_stats: bool = False):
+    def render_accum_device(self, params: rt_render_params, accum_ptr: int, want_stats: bool = False, ctx: "Context | None" = None):
+        """rt_render_accum_device; `ctx` renders this scene through ANOTHER context of the same device (frame pipelines)."""
         st = rt_stats() if want_stats else None
-        _check(self.lib, self.lib.rt_render_accum_device(self.ctx._h, self._h, C.byref(params), _VP(accum_ptr),
+        _check(self.lib, self.lib.rt_render_accum_device((ctx or self.ctx)._h, self._h, C.byref(params), _VP(accum_ptr),
                                                          C.byref(st) if st is not None else None))
         return st
 

@@ -651,12 +651,15 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
             return RT_ERR_OOM;
         }
         cudaArray_t arr = nullptr;
-        for (size_t k = 0; k < ctx->array_cache.size(); ++k)
-            if (ctx->array_cache[k].width == im.width && ctx->array_cache[k].height == im.height) {
-                arr = ctx->array_cache[k].arr;
-                ctx->array_cache.erase(ctx->array_cache.begin() + long(k));
-                break;
-            }
+        {
+            std::lock_guard<std::mutex> lock(ctx->cache_mutex);
+            for (size_t k = 0; k < ctx->array_cache.size(); ++k)
+                if (ctx->array_cache[k].width == im.width && ctx->array_cache[k].height == im.height) {
+                    arr = ctx->array_cache[k].arr;
+                    ctx->array_cache.erase(ctx->array_cache.begin() + long(k));
+                    break;
+                }
+        }
         cudaChannelFormatDesc cd = cudaCreateChannelDesc<float4>();
         e = cudaMemcpyAsync(d_rgb, im.rgb, texels * 3 * sizeof(float), cudaMemcpyHostToDevice, stream);
         if (e == cudaSuccess) {
@@ -751,8 +754,15 @@ void rt_scene_destroy(rt_scene* scene) {
     // the scene's kernels are ordered before these on the context stream
     for (auto t : scene->texobjs) cudaDestroyTextureObject(t);
     for (auto& a : scene->arrays) {
-        if (scene->ctx && scene->ctx->array_cache.size() < 8) scene->ctx->array_cache.push_back(a);
-        else cudaFreeArray(a.arr);
+        bool kept = false;
+        if (scene->ctx) {
+            std::lock_guard<std::mutex> lock(scene->ctx->cache_mutex);
+            if (scene->ctx->array_cache.size() < 8) {
+                scene->ctx->array_cache.push_back(a);
+                kept = true;
+            }
+        }
+        if (!kept) cudaFreeArray(a.arr);
     }
     for (auto p : scene->allocs) {
         if (scene->ctx) cudaFreeAsync(p, scene->ctx->stream);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/rt_api.h"
@@ -38,6 +39,7 @@ struct rt_context {
         cudaArray_t arr;
     };
     std::vector<CachedArray> array_cache;
+    std::mutex cache_mutex; // a scene may be destroyed on one host thread while another creates the next one (frame pipelines)
 };
 
 struct rt_scene {

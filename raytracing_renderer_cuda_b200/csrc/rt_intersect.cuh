@@ -276,19 +276,43 @@ RT_DEV void trav_inner(const DScene& sc, const RayQ& q, float tmin, Trav& t, int
 // bound is then ONE FFMA on a byte: t = q * s + o.  The decoded boxes contain the float boxes with a whole unit to
 // spare (k_quantize4), so the test can only add visits; acceptance test, far-bound margin, ordering network and stack
 // discipline are those of the 128-byte form.
+#ifdef RT_TRAVQ_I2F // A/B: the first form — bytes converted with I2F.U8 (XU pipe), both bounds of every axis computed and ordered
 RT_DEV float byte_f(uint32_t w, int k) { return float((w >> (8 * k)) & 255u); }
+#else
+// byte K of `w` as the float 1 + byte * 2^-15: ONE byte permute (ALU pipe) drops it into the mantissa of 1.0f
+// three-input minimum / maximum (FMNMX3, sm_100)
+RT_DEV float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+RT_DEV float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+template <int K>
+RT_DEV float byte_m(uint32_t w) { return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t(K) << 4))); }
+#endif
 RT_DEV void trav_inner_q(const DScene& sc, const RayQ& q, float tmin, Trav& t, int* stack) {
     const uint4* np = reinterpret_cast<const uint4*>(sc.nodes4q + t.node);
     const uint4 q0 = __ldg(np + 0), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+#ifdef RT_TRAVQ_I2F
     const float sx = __uint_as_float((q0.w & 0xffu) << 23) * t.inv.x;
     const float sy = __uint_as_float((q0.w & 0xff00u) << 15) * t.inv.y;
     const float sz = __uint_as_float((q0.w & 0xff0000u) << 7) * t.inv.z;
+#else // 2^15 units per axis (the exponent bytes are at most 20 + 127)
+    const float Sx = __uint_as_float(((q0.w & 0xffu) << 23) + (15u << 23)) * t.inv.x;
+    const float Sy = __uint_as_float(((q0.w & 0xff00u) << 15) + (15u << 23)) * t.inv.y;
+    const float Sz = __uint_as_float(((q0.w & 0xff0000u) << 7) + (15u << 23)) * t.inv.z;
+#endif
     const float ox = __fmaf_rn(__uint_as_float(q0.x), t.inv.x, t.noi.x);
     const float oy = __fmaf_rn(__uint_as_float(q0.y), t.inv.y, t.noi.y);
     const float oz = __fmaf_rn(__uint_as_float(q0.z), t.inv.z, t.noi.z);
     float key[4];
     int ref[4] = {int(q1.x), int(q1.y), int(q1.z), int(q1.w)};
     int nhit = 0;
+#ifdef RT_TRAVQ_I2F
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const float tx0 = __fmaf_rn(byte_f(q2.x, s), sx, ox), tx1 = __fmaf_rn(byte_f(q2.w, s), sx, ox);
@@ -300,6 +324,31 @@ RT_DEV void trav_inner_q(const DScene& sc, const RayQ& q, float tmin, Trav& t, i
         key[s] = hit ? tn : __int_as_float(0x7f800000); // +inf: misses sort to the end
         nhit += hit ? 1 : 0;
     }
+#else
+    // The sign of 1/d says which face of a box the ray enters through, for all four children at once: the word of entry
+    // bytes and the word of exit bytes are selected per axis (6 selects per node) instead of ordering two bounds per axis
+    // and child (24 min/max).  With the byte in the mantissa — 1 + b * 2^-15 — the bound is t = f * S + O with
+    // S = 2^15 * s and O = o - S; O is rounded at the magnitude of the node's own extent, 2^-9 of a unit below the whole
+    // unit the quantised boxes have to spare (k_quantize4), so the test still only adds visits.
+    const float Ox = ox - Sx, Oy = oy - Sy, Oz = oz - Sz;
+    const bool px = t.inv.x >= 0.f, py = t.inv.y >= 0.f, pz = t.inv.z >= 0.f;
+    const uint32_t nx = px ? q2.x : q2.w, fx = px ? q2.w : q2.x;
+    const uint32_t ny = py ? q2.y : q3.x, fy = py ? q3.x : q2.y;
+    const uint32_t nz = pz ? q2.z : q3.y, fz = pz ? q3.y : q2.z;
+    const float far_max = t.best.t;
+#define RT_CHILD(S)                                                                                                               \
+    {                                                                                                                             \
+        const float tn = fmax3(__fmaf_rn(byte_m<S>(nx), Sx, Ox), __fmaf_rn(byte_m<S>(ny), Sy, Oy),                                \
+                               fmaxf(__fmaf_rn(byte_m<S>(nz), Sz, Oz), tmin));                                                    \
+        const float tf = fmin3(__fmaf_rn(byte_m<S>(fx), Sx, Ox), __fmaf_rn(byte_m<S>(fy), Sy, Oy),                                \
+                               fminf(__fmaf_rn(byte_m<S>(fz), Sz, Oz), far_max));                                                 \
+        const bool hit = tn <= __fmaf_rn(tf, RT_SLAB_FAR_WIDEN, t.e) && ref[S] != RT_BVH4_EMPTY;                                  \
+        key[S] = hit ? tn : __int_as_float(0x7f800000); /* +inf: misses sort to the end */                                       \
+        nhit += hit ? 1 : 0;                                                                                                      \
+    }
+    RT_CHILD(0) RT_CHILD(1) RT_CHILD(2) RT_CHILD(3)
+#undef RT_CHILD
+#endif
 #define RT_CSWAP(a, b)                       \
     {                                        \
         const bool sw = key[b] < key[a];     \
@@ -315,6 +364,8 @@ RT_DEV void trav_inner_q(const DScene& sc, const RayQ& q, float tmin, Trav& t, i
     if (nhit > 3 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[3];
     if (nhit > 2 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[2];
     if (nhit > 1 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[1];
+    // (requesting the second-nearest child into L1 with prefetch.global.L1 while the nearest is walked: C4 1 487 -> 1 420 Mrays/s,
+    // profiles/r02_c4_ab_travq.log — the kernel is short of load slots, not of hits)
     t.node = nhit ? ref[0] : (t.sp ? stack[--t.sp] : RT_TRAV_DONE);
 }
 // one leaf test (precondition: t.node < 0)

@@ -165,28 +165,77 @@ void launch_render_mega(const DScene& sc, const DRenderParams& rp, bool use_bvh,
 // vec3.h:138-151), saturate (vec3.h:349-356), gamma 2 = __fsqrt_rz (vec3.h:181-187).
 // out_rgb: reference framebuffer layout, index j*W+i with j = 0 the bottom row.
 // out_rgb8: the writer loop main.cu:476-487 — Y flip and int(255.999f*c) & 255.
-__global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accum, int width, int height,
-                                                 float* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8) {
-    size_t npix = size_t(width) * height;
-    for (size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < npix; idx += size_t(gridDim.x) * blockDim.x) {
-        float4 a = __ldg(&accum[idx]);
-        float inv = div_rz(1.0f, a.w);
-        float r = sqrt_rz(__saturatef(__fmul_rz(a.x, inv)));
-        float g = sqrt_rz(__saturatef(__fmul_rz(a.y, inv)));
-        float b = sqrt_rz(__saturatef(__fmul_rz(a.z, inv)));
-        if (out_rgb) {
-            out_rgb[idx * 3 + 0] = r;
-            out_rgb[idx * 3 + 1] = g;
-            out_rgb[idx * 3 + 2] = b;
-        }
-        if (out_rgb8) {
-            size_t i = idx % size_t(width), j = idx / size_t(width);
-            size_t rev = (size_t(height) - 1 - j) * size_t(width) + i;
-            out_rgb8[rev * 3 + 0] = uint8_t(int(255.999f * r) & 255);
-            out_rgb8[rev * 3 + 1] = uint8_t(int(255.999f * g) & 255);
-            out_rgb8[rev * 3 + 2] = uint8_t(int(255.999f * b) & 255);
+// Pixel finalisation of main.cu:124-127 (+ the writer's conversion, main.cu:476-487) for G consecutive pixels of one row.
+// G = 4 when the width allows it: four 16-byte loads, three 16-byte stores of float RGB, three 4-byte stores of rgb8 per
+// thread — the pass is pure streaming (16 B read + 15 B written per pixel) and the per-pixel index division and byte
+// stores of the scalar form kept it at 74 % of the copy bandwidth at 8K (profiles/r02_framebuffer_passes.md).
+struct Rgb {
+    float r, g, b;
+};
+RT_DEV Rgb finalise(float4 a) {
+    const float inv = div_rz(1.0f, a.w);
+    return Rgb{sqrt_rz(__saturatef(__fmul_rz(a.x, inv))), sqrt_rz(__saturatef(__fmul_rz(a.y, inv))), sqrt_rz(__saturatef(__fmul_rz(a.z, inv)))};
+}
+RT_DEV uint32_t q8(float c) { return uint32_t(int(255.999f * c) & 255); }
+template <int G>
+RT_DEV void store_pixels(const Rgb (&px)[G], size_t idx, int width, int height, const FastDiv& div_w, float* __restrict__ out_rgb,
+                         uint8_t* __restrict__ out_rgb8) {
+    if (out_rgb) {
+        if (G == 4) {
+            float4* o = reinterpret_cast<float4*>(out_rgb + idx * 3);
+            o[0] = make_float4(px[0].r, px[0].g, px[0].b, px[1].r);
+            o[1] = make_float4(px[1].g, px[1].b, px[2].r, px[2].g);
+            o[2] = make_float4(px[2].b, px[3].r, px[3].g, px[3].b);
+        } else {
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                out_rgb[(idx + k) * 3 + 0] = px[k].r;
+                out_rgb[(idx + k) * 3 + 1] = px[k].g;
+                out_rgb[(idx + k) * 3 + 2] = px[k].b;
+            }
         }
     }
+    if (out_rgb8) { // Y flip: row j of the frame is row height - 1 - j of the picture
+        const uint32_t j = fastdiv(uint32_t(idx), div_w), i = uint32_t(idx) - j * uint32_t(width);
+        const size_t rev = (size_t(height) - 1 - j) * size_t(width) + i;
+        if (G == 4) {
+            uint32_t* o = reinterpret_cast<uint32_t*>(out_rgb8 + rev * 3);
+            o[0] = q8(px[0].r) | q8(px[0].g) << 8 | q8(px[0].b) << 16 | q8(px[1].r) << 24;
+            o[1] = q8(px[1].g) | q8(px[1].b) << 8 | q8(px[2].r) << 16 | q8(px[2].g) << 24;
+            o[2] = q8(px[2].b) | q8(px[3].r) << 8 | q8(px[3].g) << 16 | q8(px[3].b) << 24;
+        } else {
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                out_rgb8[(rev + k) * 3 + 0] = uint8_t(q8(px[k].r));
+                out_rgb8[(rev + k) * 3 + 1] = uint8_t(q8(px[k].g));
+                out_rgb8[(rev + k) * 3 + 2] = uint8_t(q8(px[k].b));
+            }
+        }
+    }
+}
+template <int G>
+__global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accum, int width, int height, const __grid_constant__ FastDiv div_w,
+                                                 float* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8) {
+    const size_t ngroups = size_t(width) * height / G;
+    for (size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < ngroups; g += size_t(gridDim.x) * blockDim.x) {
+        const size_t idx = g * G;
+        Rgb px[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) px[k] = finalise(__ldg(&accum[idx + k]));
+        store_pixels<G>(px, idx, width, height, div_w, out_rgb, out_rgb8);
+    }
+}
+
+// Grid of a grid-stride streaming pass over `items` work items, 256 threads per CTA: exactly the CTAs that are resident at
+// once (SMs x occupancy of THIS kernel), so the pass has one wave and no partial second one (k_reduce_tonemap<4> holds
+// 5 CTAs per SM at 44 registers; a grid of 8 per SM ran 1.6 waves), or fewer when the frame is small.
+template <typename K>
+static unsigned stream_grid(K kernel, size_t items, int sm_count) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    const size_t want = (items + 255) / 256, cap = size_t(sm_count > 0 ? sm_count : 1) * size_t(per_sm);
+    const size_t n = want < cap ? want : cap;
+    return unsigned(n ? n : 1);
 }
 
 // --------------------------------------------------------------- fused reduce + tonemap ----
@@ -208,39 +257,31 @@ __device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
                  : "memory");
     return v;
 }
+template <int G>
 __global__ void __launch_bounds__(256) k_reduce_tonemap(const __grid_constant__ PeerPtrs peers, int n_peers,
                                                         const float4* __restrict__ multicast, int width, int height,
-                                                        int row_begin, int row_end, float* __restrict__ out_rgb,
-                                                        uint8_t* __restrict__ out_rgb8, float4* __restrict__ out_sum) {
-    const size_t first = size_t(row_begin) * size_t(width), last = size_t(row_end) * size_t(width);
-    for (size_t idx = first + size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < last; idx += size_t(gridDim.x) * blockDim.x) {
-        float4 a;
-        if (multicast) {
-            a = multimem_ld_reduce_add(multicast + idx);
-        } else {
-            a = peers.p[0][idx];
-            for (int k = 1; k < n_peers; ++k) {
-                float4 b = peers.p[k][idx];
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                                                        const __grid_constant__ FastDiv div_w, int row_begin, int row_end,
+                                                        float* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, float4* __restrict__ out_sum) {
+    const size_t first = size_t(row_begin) * size_t(width) / G, last = size_t(row_end) * size_t(width) / G;
+    for (size_t g = first + size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < last; g += size_t(gridDim.x) * blockDim.x) {
+        const size_t idx = g * G;
+        Rgb px[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            float4 a;
+            if (multicast) {
+                a = multimem_ld_reduce_add(multicast + idx + k);
+            } else {
+                a = __ldcg(&peers.p[0][idx + k]); // (L2 only: a peer's accumulator changes from frame to frame)
+                for (int m = 1; m < n_peers; ++m) {
+                    const float4 b = __ldcg(&peers.p[m][idx + k]);
+                    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                }
             }
+            if (out_sum) out_sum[idx + k] = a;
+            px[k] = finalise(a);
         }
-        if (out_sum) out_sum[idx] = a;
-        float inv = div_rz(1.0f, a.w);
-        float r = sqrt_rz(__saturatef(__fmul_rz(a.x, inv)));
-        float g = sqrt_rz(__saturatef(__fmul_rz(a.y, inv)));
-        float b = sqrt_rz(__saturatef(__fmul_rz(a.z, inv)));
-        if (out_rgb) {
-            out_rgb[idx * 3 + 0] = r;
-            out_rgb[idx * 3 + 1] = g;
-            out_rgb[idx * 3 + 2] = b;
-        }
-        if (out_rgb8) {
-            size_t i = idx % size_t(width), j = idx / size_t(width);
-            size_t rev = (size_t(height) - 1 - j) * size_t(width) + i;
-            out_rgb8[rev * 3 + 0] = uint8_t(int(255.999f * r) & 255);
-            out_rgb8[rev * 3 + 1] = uint8_t(int(255.999f * g) & 255);
-            out_rgb8[rev * 3 + 2] = uint8_t(int(255.999f * b) & 255);
-        }
+        store_pixels<G>(px, idx, width, height, div_w, out_rgb, out_rgb8);
     }
 }
 
@@ -251,12 +292,14 @@ void launch_reduce_tonemap(const void* const* peer_accum, int n_peers, const voi
     PeerPtrs pp{};
     if (peer_accum) // (NULL with a multicast address: the kernel then never reads the table)
         for (int k = 0; k < n_peers && k < 16; ++k) pp.p[k] = static_cast<const float4*>(peer_accum[k]);
-    size_t npix = size_t(row_end - row_begin) * size_t(width);
-    size_t want = (npix + 255) / 256;
-    const size_t cap = size_t(sm_count > 0 ? sm_count : 1) * 8u; // 8 CTAs of 256 threads per SM, grid-stride beyond
-    unsigned blocks = unsigned(want < cap ? want : cap);
-    k_reduce_tonemap<<<blocks, 256, 0, st>>>(pp, n_peers, static_cast<const float4*>(multicast), width, height, row_begin, row_end,
-                                             out_rgb, out_rgb8, out_sum);
+    const size_t npix = size_t(row_end - row_begin) * size_t(width);
+    const FastDiv div_w = make_fastdiv(uint32_t(width));
+    if (width % 4 == 0 && uintptr_t(out_rgb) % 16 == 0 && uintptr_t(out_rgb8) % 4 == 0) // (vector stores need the alignment)
+        k_reduce_tonemap<4><<<stream_grid(k_reduce_tonemap<4>, npix / 4, sm_count), 256, 0, st>>>(
+            pp, n_peers, static_cast<const float4*>(multicast), width, height, div_w, row_begin, row_end, out_rgb, out_rgb8, out_sum);
+    else
+        k_reduce_tonemap<1><<<stream_grid(k_reduce_tonemap<1>, npix, sm_count), 256, 0, st>>>(
+            pp, n_peers, static_cast<const float4*>(multicast), width, height, div_w, row_begin, row_end, out_rgb, out_rgb8, out_sum);
 }
 
 // --------------------------------------------------------------- self-test of the arithmetic helpers ----
@@ -273,12 +316,13 @@ void launch_selftest_rz(const float* x, const float* y, size_t n, float* out, cu
 }
 
 void launch_tonemap(const float4* accum, int width, int height, float* out_rgb, uint8_t* out_rgb8, int sm_count, cudaStream_t st) {
-    size_t npix = size_t(width) * height;
+    const size_t npix = size_t(width) * height;
     if (npix == 0) return;
-    size_t want = (npix + 255) / 256;
-    const size_t cap = size_t(sm_count > 0 ? sm_count : 1) * 16u;
-    unsigned blocks = unsigned(want < cap ? want : cap);
-    k_tonemap<<<blocks, 256, 0, st>>>(accum, width, height, out_rgb, out_rgb8);
+    const FastDiv div_w = make_fastdiv(uint32_t(width));
+    if (width % 4 == 0 && uintptr_t(out_rgb) % 16 == 0 && uintptr_t(out_rgb8) % 4 == 0)
+        k_tonemap<4><<<stream_grid(k_tonemap<4>, npix / 4, sm_count), 256, 0, st>>>(accum, width, height, div_w, out_rgb, out_rgb8);
+    else
+        k_tonemap<1><<<stream_grid(k_tonemap<1>, npix, sm_count), 256, 0, st>>>(accum, width, height, div_w, out_rgb, out_rgb8);
 }
 
 __global__ void __launch_bounds__(256) k_rgb_to_rgba(const float* __restrict__ rgb, float4* __restrict__ rgba, size_t n) {

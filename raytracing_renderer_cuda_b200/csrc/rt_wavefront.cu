@@ -75,7 +75,13 @@ struct WfBuffers {
     uint2* next_ps;                // [2], same rotation: (next_path % pixels, next_path / pixels), kept by the kernels so that
                                    // no thread divides a 64-bit path number (PathMap)
     uint32_t pool;
+    // Thin end of a frame (k_wf_tail): once no path is left to start and at most `tail_paths` are alive, the step kernel
+    // that sees it records its iteration and the queue sizes in tail[0], tail[1 + q] and leaves; k_wf_tail finishes
+    // those paths in place.  tail_paths = 0: never.
+    uint32_t tail_paths;
+    uint32_t* tail; // [2 + NQ]: iteration (WF_TAIL_NONE: not armed), queue sizes, CTAs of k_wf_tail that have finished
 };
+#define WF_TAIL_NONE 0xffffffffu
 
 // Where the new paths of an iteration start: entry idx of Q_NEW is path next_path + idx, i.e. pixel
 // (pix_base + idx) % npix of sample smp_base + (pix_base + idx) / npix — one 32-bit division by an invariant
@@ -366,11 +372,19 @@ RT_DEV int wf_process_entry(const DScene& sc, const DRenderParams& rp, const WfB
 
 // The frame is over when no path is alive and none can start any more; launches the host enqueued ahead of its
 // polling then have nothing to do.
-RT_DEV bool wf_frame_done(const uint32_t (&n_q)[NQ], unsigned long long path_base, unsigned long long npaths) {
+// ... or when few enough are alive for k_wf_tail to finish them in place (wb.tail_paths): block 0 then notes the
+// iteration and the queue sizes for that kernel (later iterations find empty queues and zero this one's counters).
+RT_DEV bool wf_frame_done(const WfBuffers& wb, const uint32_t* cnt_cur, int it, const uint32_t (&n_q)[NQ], unsigned long long path_base,
+                          unsigned long long npaths) {
     uint32_t live = 0;
 #pragma unroll
     for (int k = 0; k < NQ; ++k) live += k == Q_NEW ? 0u : n_q[k];
-    return path_base >= npaths && live == 0u;
+    if (path_base < npaths || live > wb.tail_paths) return false;
+    if (live != 0u && blockIdx.x == 0 && threadIdx.x < NQ) {
+        wb.tail[1 + threadIdx.x] = __ldg(cnt_cur + threadIdx.x);
+        if (threadIdx.x == 0) wb.tail[0] = uint32_t(it);
+    }
+    return true;
 }
 
 // Work granularity, variant 1: a CTA takes WF_CTA_THREADS consecutive entries of ONE queue (chunks are drawn from a
@@ -426,7 +440,7 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     const unsigned long long npaths = npix * (unsigned long long)rp.spp;
     if (blockIdx.x == 0 && threadIdx.x == 0) wf_advance_paths(wb, it, path_base, n_q[Q_NEW], npix);
     if (blockIdx.x >= total_chunks) return;
-    if (wf_frame_done(n_q, path_base, npaths)) return;
+    if (wf_frame_done(wb, cnt_cur, it, n_q, path_base, npaths)) return;
     const PathMap pm = make_pathmap(wb, it, path_base, n_q[Q_NEW], npaths);
     if (sc.has_noise && (blockIdx.x < chunk_end[1] || n_q[Q_EMIT] != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     if (threadIdx.x < 2 * NQ) (&s_count[0][0])[threadIdx.x] = 0u;
@@ -501,6 +515,66 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
 }
 
 
+// The thin end of a frame: every thread finishes ONE path in place — shade, scatter, extend, classify, and again —
+// instead of handing it from launch to launch (C1: 58 of 70 iterations carry fewer paths than one wave of threads
+// and cost a launch each, ~12 us; this launch lasts as long as its longest path).  The path state goes through the
+// slot's record exactly as between two iterations (wf_finish stores it, wf_begin re-reads it: same thread, plain
+// accesses), so the kernel is the two entry halves in a loop and traces the same paths.  A separate kernel, not a
+// loop inside the step kernels: that form was measured in this round and cost the bulk 0.8 ms through code generation
+// (profiles/r02_c1_instruction_diet.md, section 5).  Launched after every batch of step launches; does nothing until a
+// step kernel has set wb.tail[0] (wf_frame_done).
+template <bool USE_BVH, bool NEE, int LIST = 0>
+__global__ void __launch_bounds__(WF_CTA_THREADS)
+    k_wf_tail(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
+              float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
+    WF_PDL_PROLOGUE();
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t it = wb.tail[0];
+    if (it == WF_TAIL_NONE) return;
+    const PerlinTab pt{smem, threadIdx.x & 31u};
+    if (sc.has_noise) perlin_stage(smem, threadIdx.x, blockDim.x);
+    __syncthreads();
+
+    // entry -> (queue, position): the queues in shading-cost order, as in the step kernels
+    const int order[NQ - 1] = {Q_LAMB_NOISE6, Q_LAMB_NOISE1, Q_LAMB_IMAGE, Q_EMIT, Q_DIEL, Q_METAL, Q_LAMB_CONST};
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int kind = Q_NONE;
+#pragma unroll
+    for (int k = 0; k < NQ - 1; ++k) {
+        const uint32_t n = wb.tail[1 + order[k]];
+        if (kind == Q_NONE) {
+            if (idx < n) kind = order[k];
+            else idx -= n;
+        }
+    }
+    unsigned long long nrays = 0;
+    if (kind != Q_NONE) {
+        const uint32_t slot = __ldg(wf_queue(wb, int(it & 1u), kind) + idx);
+        const PathMap pm{0u, 0u, 0u}; // no path left to start
+        for (;;) {
+            WfLane ln;
+            int out_q;
+            const bool has_ray = wf_begin<NEE, WF_ACC_PLAIN>(sc, rp, wb, pt, kind, true, slot, 0u, pm, accum, ln, out_q);
+            if (NEE) nrays += ln.shadow_rays;
+            if (!has_ray) break; // emitter, absorbed, depth limit: accumulated by wf_begin
+            const RayQ q = make_rayq(ln.r);
+            const Hit h = USE_BVH ? closest_hit_bvh(sc, q, rp.tmin) : closest_hit_list<LIST>(sc, q, rp.tmin);
+            ++nrays;
+            out_q = wf_finish<NEE, WF_ACC_PLAIN>(sc, rp, wb, accum, ln, q, h);
+            if (out_q == Q_NEW) break; // miss or constant emitter: accumulated by wf_finish
+            kind = out_q;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
+    if ((threadIdx.x & 31u) == 0u && nrays) atomicAdd(ray_counter, nrays);
+    // the CTA that finishes last (every CTA has read the flag by then) disarms it: the tail launches that follow do nothing
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&wb.tail[1 + NQ], 1u) == gridDim.x - 1u) {
+        wb.tail[1 + NQ] = 0u;
+        wb.tail[0] = WF_TAIL_NONE;
+    }
+}
+
 // Work granularity, variant 2: a WARP draws WF_WCHUNK consecutive entries of ONE queue (WF_ROUNDS rounds of 32) from a
 // ticket counter and pushes its results with one global atomic per target queue.  No block-wide barrier inside the
 // loop: a warp whose rays finish early moves on instead of waiting for the slowest BVH traversal of the CTA
@@ -514,6 +588,9 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
 #endif
 #ifndef RT_WF_BATCH
 #define RT_WF_BATCH 8u // launches enqueued between two looks at the polled queue sizes
+#endif
+#ifndef RT_WF_TAIL_PATHS_DEFAULT
+#define RT_WF_TAIL_PATHS_DEFAULT 131072u // live paths from which k_wf_tail takes over (sweep: profiles/r02_tail_kernel.md)
 #endif
 #ifndef RT_PT_MIN_SPHERES
 #define RT_PT_MIN_SPHERES 4096u // persistent-lane kernel from this many primitives on (measured: see profiles/)
@@ -568,7 +645,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
     if (blockIdx.x == 0 && threadIdx.x == 0) wf_advance_paths(wb, it, path_base, n_q[Q_NEW], npix);
     const uint32_t warps_per_cta = WF_THREADS / 32;
     if (blockIdx.x * warps_per_cta >= total_chunks) return;
-    if (wf_frame_done(n_q, path_base, npaths)) return;
+    if (wf_frame_done(wb, cnt_cur, it, n_q, path_base, npaths)) return;
     const PathMap pm = make_pathmap(wb, it, path_base, n_q[Q_NEW], npaths);
     if (sc.has_noise && (chunk_end[1] != 0u || n_q[Q_EMIT] != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     __syncthreads(); // the only block-wide barrier of the kernel
@@ -819,6 +896,7 @@ __global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots
     if (i < n_slots) wf_queue(wb, 0, Q_NEW)[i] = i;
     if (i < 3 * NQ) wb.counts[i] = (i == Q_NEW) ? n_slots : 0u;
     if (i < 3) wb.tickets[i] = 0u;
+    if (i < 2 + NQ) wb.tail[i] = i == 0 ? WF_TAIL_NONE : 0u;
     if (i == 0) {
         wb.next_path[0] = wb.next_path[1] = 0ull;
         wb.next_ps[0] = wb.next_ps[1] = make_uint2(0u, 0u);
@@ -850,6 +928,7 @@ static bool ensure_slot_buffers(WavefrontState* ws) {
     ok = ok && cudaMalloc(&ws->b.tickets, 3 * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.next_path, 2 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&ws->b.next_ps, 2 * sizeof(uint2)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ws->b.tail, (2 + NQ) * sizeof(uint32_t)) == cudaSuccess;
     return ok;
 }
 
@@ -861,6 +940,7 @@ void wavefront_destroy(WavefrontState* ws) {
     if (ws->b.tickets) cudaFree(ws->b.tickets);
     if (ws->b.next_path) cudaFree(ws->b.next_path);
     if (ws->b.next_ps) cudaFree(ws->b.next_ps);
+    if (ws->b.tail) cudaFree(ws->b.tail);
     for (auto& e : ws->poll_ev)
         if (e) cudaEventDestroy(e);
     if (ws->h_status) cudaFreeHost(ws->h_status);
@@ -887,6 +967,7 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     // slots in use: never more than there are paths
     WfBuffers wb = ws->b;
     const uint32_t slots = uint32_t(npaths < wb.pool ? npaths : wb.pool);
+    wb.tail_paths = 0u; // set below, once the granularity is known; k_wf_init does not read it
     k_wf_init<<<(slots + 255) / 256 > 0 ? (slots + 255) / 256 : 1, 256, 0, st>>>(wb, slots);
     ++*launches;
 
@@ -907,6 +988,14 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         if (v >= 1 && v <= 32) leaf_lanes = v;
     }
     const bool warp_grain = grain != G_CTA;
+    // The thin end of the frame is finished in place by k_wf_tail (CTA- and warp-chunk kernels; the persistent-lane kernel
+    // walks other nodes than the per-lane loop and its frames spend nothing in the tail).  RT_WF_TAIL_PATHS overrides, 0 = off.
+    uint32_t tail_paths = grain == G_PT ? 0u : RT_WF_TAIL_PATHS_DEFAULT;
+    if (const char* e = getenv("RT_WF_TAIL_PATHS")) {
+        const long v = atol(e);
+        if (v >= 0 && v <= (1l << 22) && grain != G_PT) tail_paths = uint32_t(v);
+    }
+    wb.tail_paths = tail_paths;
     // node form of the persistent-lane kernel: the 64-byte quantised nodes when the scene has them (RT_BVH4=f: the 128-byte ones)
     bool quant = sc.nodes4q != nullptr;
     if (const char* e = getenv("RT_BVH4")) quant = quant && e[0] != 'f';
@@ -950,10 +1039,10 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     }
 
     // every step launch carries the programmatic-stream-serialization attribute (see WF_PDL_PROLOGUE)
-    auto launch = [&](auto kernel, auto... args) {
+    auto launch_dims = [&](unsigned n_blocks, unsigned n_threads, auto kernel, auto... args) {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(warp_grain ? WF_THREADS : WF_CTA_THREADS);
+        cfg.gridDim = dim3(n_blocks);
+        cfg.blockDim = dim3(n_threads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -967,6 +1056,7 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         cfg.numAttrs = 1;
         cudaLaunchKernelEx(&cfg, kernel, args...);
     };
+    auto launch = [&](auto kernel, auto... args) { launch_dims(grid, warp_grain ? WF_THREADS : WF_CTA_THREADS, kernel, args...); };
     uint32_t it = 0;
     auto enqueue = [&](uint32_t count) {
         for (uint32_t k = 0; k < count; ++k, ++it) {
@@ -1000,6 +1090,20 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
             ++*launches;
         }
     };
+    auto enqueue_tail = [&]() {
+        if (!tail_paths) return;
+        const unsigned nb = (tail_paths + WF_CTA_THREADS - 1) / WF_CTA_THREADS, nt = WF_CTA_THREADS; // a thread per path that may be alive
+        if (nee) {
+            if (use_bvh) launch_dims(nb, nt, k_wf_tail<true, true>, sc, rp, wb, accum, ray_counter);
+            else if (sc.n_list) launch_dims(nb, nt, k_wf_tail<false, true, 1>, sc, rp, wb, accum, ray_counter);
+            else launch_dims(nb, nt, k_wf_tail<false, true, 2>, sc, rp, wb, accum, ray_counter);
+        } else {
+            if (use_bvh) launch_dims(nb, nt, k_wf_tail<true, false>, sc, rp, wb, accum, ray_counter);
+            else if (sc.n_list) launch_dims(nb, nt, k_wf_tail<false, false, 1>, sc, rp, wb, accum, ray_counter);
+            else launch_dims(nb, nt, k_wf_tail<false, false, 2>, sc, rp, wb, accum, ray_counter);
+        }
+        ++*launches;
+    };
     // Iterations are enqueued in batches.  After each batch the queue sizes and the path counter are copied to
     // pinned memory; the host looks at the copy of batch k only AFTER batch k+1 has been enqueued, so the GPU
     // never waits for the host.  Once the frame is finished the launches still in flight find empty queues and
@@ -1020,10 +1124,12 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     const unsigned long long max_iters = (generations + 1ull) * ((unsigned long long)rp.max_depth + 2ull) + 64ull;
     bool complete = false;
     enqueue(uint32_t(2ull * generations + 4ull < max_iters ? 2ull * generations + 4ull : max_iters)); // a path lives ~2 iterations
+    enqueue_tail();
     snapshot(0);
     int par = 0;
     while (true) {
         enqueue(RT_WF_BATCH);
+        enqueue_tail();
         snapshot(par ^ 1);
         if (cudaEventSynchronize(ws->poll_ev[par]) != cudaSuccess) break;
         const uint32_t* c = ws->h_counts + par * 3 * NQ + (polled[par].it_after % 3) * NQ; // queues of the next iteration
