@@ -359,8 +359,35 @@ RT_DEV void trav_inner_q(const DScene& sc, const RayQ& q, float tmin, Trav& t, i
         ref[a] = sw ? rb : ra;               \
         ref[b] = sw ? ra : rb;               \
     }
+#if defined(RT_TRAVQ_NOSORT) // A/B: no ordering at all — hit children in slot order
+#undef RT_CSWAP
+    {
+        const float inf = __int_as_float(0x7f800000);
+        int nxt = RT_TRAV_DONE;
+#pragma unroll
+        for (int s = 3; s >= 0; --s)
+            if (key[s] < inf) {
+                if (nxt != RT_TRAV_DONE && t.sp < RT_BVH_STACK) stack[t.sp++] = nxt;
+                nxt = ref[s];
+            }
+        t.node = nxt != RT_TRAV_DONE ? nxt : (t.sp ? stack[--t.sp] : RT_TRAV_DONE);
+        return;
+    }
+#elif defined(RT_TRAVQ_NEAR1) // A/B: the nearest child first, the others in any order
+    RT_CSWAP(0, 1) RT_CSWAP(2, 3) RT_CSWAP(0, 2) RT_CSWAP(1, 3)
+#undef RT_CSWAP
+    {
+        const float inf = __int_as_float(0x7f800000);
+        if (key[3] < inf && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[3];
+        if (key[2] < inf && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[2];
+        if (key[1] < inf && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[1];
+        t.node = nhit ? ref[0] : (t.sp ? stack[--t.sp] : RT_TRAV_DONE);
+        return;
+    }
+#else
     RT_CSWAP(0, 1) RT_CSWAP(2, 3) RT_CSWAP(0, 2) RT_CSWAP(1, 3) RT_CSWAP(1, 2)
 #undef RT_CSWAP
+#endif
     if (nhit > 3 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[3];
     if (nhit > 2 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[2];
     if (nhit > 1 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[1];

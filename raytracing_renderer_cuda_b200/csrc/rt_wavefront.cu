@@ -595,8 +595,14 @@ __global__ void __launch_bounds__(WF_CTA_THREADS)
 #ifndef RT_PT_MIN_SPHERES
 #define RT_PT_MIN_SPHERES 4096u // persistent-lane kernel from this many primitives on (measured: see profiles/)
 #endif
+#ifndef WF_PT_THREADS
+#define WF_PT_THREADS 128 // CTA size of the persistent-lane kernel
+#endif
 #ifndef WF_PT_MINBLOCKS
-#define WF_PT_MINBLOCKS 3 // 80 registers, no spills in the traversal loop: C4 1000 -> 1040 Mrays/s against 4 CTAs/SM (64 registers)
+// 7 CTAs of 128 threads = 28 warps per SM at 72 registers.  The kernel waits on dependent node fetches; measured on the full C4
+// frame (profiles/r02_c4_traversal.md section 5): 24 warps (80 registers, no spills) 1 489 Mrays/s, 28 warps 1 545, 32 warps
+// (64 registers, 100 bytes of spills) 1 539.
+#define WF_PT_MINBLOCKS 7
 #endif
 #ifndef RT_PT_LEAF_LANES_DEFAULT
 #define RT_PT_LEAF_LANES_DEFAULT 1
@@ -729,7 +735,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MINBLOCKS)
 // partial-width shading of refilled lanes costs more than the traversal gains (C2: 10.3 -> 7.1 Grays/s), so the
 // kernel is used from RT_PT_MIN_SPHERES primitives on.
 template <bool NEE, bool QUANT>
-__global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
+__global__ void __launch_bounds__(WF_PT_THREADS, WF_PT_MINBLOCKS)
     k_wf_step_pt(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
                  int it, float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter, int refill, int leaf_lanes) {
     WF_PDL_PROLOGUE();
@@ -766,7 +772,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_PT_MINBLOCKS)
     const unsigned long long npix = (unsigned long long)rp.width * rp.height;
     const unsigned long long npaths = npix * (unsigned long long)rp.spp;
     if (blockIdx.x == 0 && threadIdx.x == 0) wf_advance_paths(wb, it, path_base, n_new, npix);
-    if (blockIdx.x * (WF_THREADS / 32) >= total_chunks) return;
+    if (blockIdx.x * (WF_PT_THREADS / 32) >= total_chunks) return;
     const PathMap pm = make_pathmap(wb, it, path_base, n_new, npaths);
     if (sc.has_noise && (noise_chunks != 0u || n_emit != 0u)) perlin_stage(smem, threadIdx.x, blockDim.x);
     __syncthreads(); // the only block-wide barrier of the kernel
@@ -1002,7 +1008,8 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     unsigned grid;
     if (warp_grain) { // resident CTAs only: work is drawn dynamically
         const unsigned cap = unsigned(sm_count) * (grain == G_PT ? WF_PT_MINBLOCKS : WF_MINBLOCKS);
-        const unsigned need = (slots + WF_WCHUNK * (WF_THREADS / 32) - 1) / (WF_WCHUNK * (WF_THREADS / 32)) + NQ;
+        const unsigned cta_warps = (grain == G_PT ? WF_PT_THREADS : WF_THREADS) / 32;
+        const unsigned need = (slots + WF_WCHUNK * cta_warps - 1) / (WF_WCHUNK * cta_warps) + NQ;
         grid = need < cap ? need : cap;
     } else { // two waves of CTAs, chunks by stride
         const unsigned cap = unsigned(sm_count) * WF_CTA_WAVES * WF_CTA_MINBLOCKS;
@@ -1056,7 +1063,7 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
         cfg.numAttrs = 1;
         cudaLaunchKernelEx(&cfg, kernel, args...);
     };
-    auto launch = [&](auto kernel, auto... args) { launch_dims(grid, warp_grain ? WF_THREADS : WF_CTA_THREADS, kernel, args...); };
+    auto launch = [&](auto kernel, auto... args) { launch_dims(grid, grain == G_PT ? WF_PT_THREADS : (warp_grain ? WF_THREADS : WF_CTA_THREADS), kernel, args...); };
     uint32_t it = 0;
     auto enqueue = [&](uint32_t count) {
         for (uint32_t k = 0; k < count; ++k, ++it) {
