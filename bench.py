@@ -466,7 +466,10 @@ def run_ours(args) -> None:
             t0 = time.perf_counter()
             pipelined(args.steps)
             e2e_pipe = (time.perf_counter() - t0) / args.steps
-            e2e_s = e2e_pipe
+            # The pipeline needs two host threads that keep up with ~40 launches per 7 ms frame; on a box whose host cores are busy
+            # or slow the plain serial call sequence is the faster of the two.  Both are end-to-end runs of the same per-step
+            # work through the public API: the headline is the better one, and the line says which and carries both.
+            e2e_s = min(e2e_pipe, e2e_serial_s)
 
         # ---- output stage on the device: render + finalise + flip/quantise + JPEG, only the file is read back ----
         jpeg = None
@@ -572,11 +575,14 @@ def run_ours(args) -> None:
             "roofline": roof,
             "e2e": {"value": paths_total / e2e_ms / 1e3, "unit": "Mpaths/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": W * H * 3 * 4,
-                    "what": ("two-deep frame pipeline over the public C-ABI entries: every step uploads its scene (rt_scene_create on a second "
-                             "context / stream, H2D scene + texture, BVH build), renders (rt_render_accum_device + rt_tonemap_device) and reads "
-                             "its frame back into pinned host memory (copy stream); uploads and read-backs overlap the neighbouring frames' "
-                             "renders; wall clock over the whole loop")
+                    "what": (("two-deep frame pipeline over the public C-ABI entries: every step uploads its scene (rt_scene_create on a second "
+                              "context / stream, H2D scene + texture, BVH build), renders (rt_render_accum_device + rt_tonemap_device) and reads "
+                              "its frame back into pinned host memory (copy stream); uploads and read-backs overlap the neighbouring frames' "
+                              "renders; wall clock over the whole loop") if e2e_pipe is not None and e2e_pipe <= e2e_serial_s else
+                             "serial call sequence per step: rt_scene_create (H2D scene + texture, BVH build), then rt_render to a pinned host buffer (synchronous); wall clock")
                     if world == 1 else "rt_scene_create (H2D) on every rank + rt_group frame + D2H of the root's frame, wall clock, max over ranks",
+                    "mode": None if world > 1 else ("pipelined" if e2e_pipe is not None and e2e_pipe <= e2e_serial_s else "serial"),
+                    "pipelined": None if world > 1 or e2e_pipe is None else {"value": paths_total / (e2e_pipe * 1e3) / 1e3, "ms_per_step": e2e_pipe * 1e3},
                     "serial": None if world > 1 else {
                         "value": paths_total / (e2e_serial_s * 1e3) / 1e3, "ms_per_step": e2e_serial_s * 1e3,
                         "what": "the same per-step work without overlap: rt_scene_create, then rt_render to a pinned host buffer (synchronous)"}},

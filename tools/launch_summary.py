@@ -11,15 +11,15 @@ for k, v in d:
     tot[name][0] += 1
     tot[name][1] += v
 total = sum(v for _, v in d)
-print(f"# r01 — launch list of `{sys.argv[2]}`\n")
-print(f"`ncu --metrics gpu__time_duration.sum --clock-control none -c 700` (first {len(d)} launches; cold-cache, serialised: compare shares, "
+print(f"# launch list of `{sys.argv[2]}`\n")
+print(f"`ncu --metrics gpu__time_duration.sum --clock-control none -c 900` (first {len(d)} launches; cold-cache, serialised: compare shares, "
       f"not absolutes).  Raw list: `profiles/{sys.argv[3] if len(sys.argv) > 3 else 'r01_launches_bench_c1.csv'}`.\n")
 print("| kernel | launches | total ms | share |\n|---|---|---|---|")
 for name, (n, v) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"| `{name[:70]}` | {n} | {v / 1e3:.3f} | {100 * v / total:.1f} % |")
-step = [v for k, v in d if "k_wf_step" in k]
+step = [v for k, v in d if ("k_wf_step" in k or "k_wf_tail" in k)]
 init = [i for i, (k, _) in enumerate(d) if "k_wf_init" in k]
 if len(init) >= 2:
-    frame = [v for k, v in d[init[0]:init[1]] if "k_wf_step" in k]
-    print(f"\nOne frame = {len(frame)} `k_wf_step_*` launches, {sum(frame) / 1e3:.3f} ms under ncu.")
+    frame = [v for k, v in d[init[0]:init[1]] if ("k_wf_step" in k or "k_wf_tail" in k)]
+    print(f"\nOne frame = {len(frame)} `k_wf_step_*` / `k_wf_tail` launches, {sum(frame) / 1e3:.3f} ms under ncu.")
     print("Per-iteration durations of the first frame (us): " + str([round(v) for v in frame]))
