@@ -107,7 +107,8 @@ struct WavefrontState {
     uint32_t* h_counts = nullptr;           // pinned [2][3 * NQ]: queue sizes, one copy per polling parity
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     cudaStream_t stream = nullptr;
-    int persist_max = -1, window_max = 0; // L2 persistence limits of this state's device, queried on first use
+    bool persist_set = false;
+    int persist_max = -1, window_max = 0, l2_bytes = 0; // L2 size and persistence limits of this state's device, queried on first use
 };
 
 // Streaming accesses to data that is read once and written once per iteration (path records, queue entries): L1
@@ -515,55 +516,96 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
 }
 
 
-// The thin end of a frame: every thread finishes ONE path in place — shade, scatter, extend, classify, and again —
-// instead of handing it from launch to launch (C1: 58 of 70 iterations carry fewer paths than one wave of threads
-// and cost a launch each, ~12 us; this launch lasts as long as its longest path).  The path state goes through the
-// slot's record exactly as between two iterations (wf_finish stores it, wf_begin re-reads it: same thread, plain
-// accesses), so the kernel is the two entry halves in a loop and traces the same paths.  A separate kernel, not a
-// loop inside the step kernels: that form was measured in this round and cost the bulk 0.8 ms through code generation
+// The thin end of a frame: a CTA-LOCAL wavefront.  Once no path is left to start and few are alive, handing them from
+// launch to launch costs a launch per bounce (C1: 58 of 70 iterations carried fewer paths than one wave of threads),
+// and nothing a path does from here on concerns another CTA: no path starts, slots retire.  So every CTA takes a share
+// of the live paths and runs them to their end on its own: bounce by bounce it regroups its slots by shading class in
+// shared memory (class segments padded to whole warps, so a warp still runs one shader with full lanes), processes them
+// with the step kernels' entry code (wf_process_entry: shade, scatter, extend, classify; the record carries the path
+// between bounces exactly as between two iterations), and block barriers are the only synchronisation.  The first form
+// of this kernel gave every path ONE thread for the rest of its life: ncu showed 6.9 of 32 lanes active and 18 times the
+// warp instructions of a coherent run (profiles/r02_tail_kernel.md) — the classes of a warp's paths diverge after one bounce.
+// A separate kernel, not a loop inside the step kernels: that form cost the bulk 0.8 ms through code generation
 // (profiles/r02_c1_instruction_diet.md, section 5).  Launched after every batch of step launches; does nothing until a
 // step kernel has set wb.tail[0] (wf_frame_done).
+#ifndef WF_TAIL_CAP
+#define WF_TAIL_CAP 1280u // slots a CTA can hold, class padding (7 x 31) included
+#endif
+#define WF_TAIL_DEAD 0xffffffffu
 template <bool USE_BVH, bool NEE, int LIST = 0>
-__global__ void __launch_bounds__(WF_CTA_THREADS)
+__global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
     k_wf_tail(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
     WF_PDL_PROLOGUE();
     extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t s_in[WF_TAIL_CAP];  // slots grouped by class, class segments start at multiples of 32
+    __shared__ uint32_t s_out[WF_TAIL_CAP]; // slot | class << 28 of the paths that go on, WF_TAIL_DEAD for the others
+    __shared__ uint32_t s_cnt[NQ], s_cin[NQ], s_off[NQ + 1], s_cur[NQ];
     const uint32_t it = wb.tail[0];
     if (it == WF_TAIL_NONE) return;
     const PerlinTab pt{smem, threadIdx.x & 31u};
     if (sc.has_noise) perlin_stage(smem, threadIdx.x, blockDim.x);
+    if (threadIdx.x < NQ) s_cnt[threadIdx.x] = 0u;
     __syncthreads();
 
-    // entry -> (queue, position): the queues in shading-cost order, as in the step kernels
+    // this CTA's share [lo, hi) of the armed queues, concatenated in shading-cost order
     const int order[NQ - 1] = {Q_LAMB_NOISE6, Q_LAMB_NOISE1, Q_LAMB_IMAGE, Q_EMIT, Q_DIEL, Q_METAL, Q_LAMB_CONST};
-    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int kind = Q_NONE;
+    uint32_t total = 0;
 #pragma unroll
-    for (int k = 0; k < NQ - 1; ++k) {
-        const uint32_t n = wb.tail[1 + order[k]];
-        if (kind == Q_NONE) {
-            if (idx < n) kind = order[k];
-            else idx -= n;
+    for (int k = 0; k < NQ - 1; ++k) total += wb.tail[1 + order[k]];
+    const uint32_t per = (total + gridDim.x - 1u) / gridDim.x;
+    const uint32_t lo = min(blockIdx.x * per, total), hi = min(lo + per, total);
+    uint32_t n_out = hi - lo; // entries of s_out in use
+    for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+        uint32_t idx = lo + i;
+        int kind = Q_NONE;
+#pragma unroll
+        for (int k = 0; k < NQ - 1; ++k) {
+            const uint32_t n = wb.tail[1 + order[k]];
+            if (kind == Q_NONE) {
+                if (idx < n) kind = order[k];
+                else idx -= n;
+            }
         }
-    }
-    unsigned long long nrays = 0;
-    if (kind != Q_NONE) {
         const uint32_t slot = __ldg(wf_queue(wb, int(it & 1u), kind) + idx);
-        const PathMap pm{0u, 0u, 0u}; // no path left to start
-        for (;;) {
-            WfLane ln;
-            int out_q;
-            const bool has_ray = wf_begin<NEE, WF_ACC_PLAIN>(sc, rp, wb, pt, kind, true, slot, 0u, pm, accum, ln, out_q);
-            if (NEE) nrays += ln.shadow_rays;
-            if (!has_ray) break; // emitter, absorbed, depth limit: accumulated by wf_begin
-            const RayQ q = make_rayq(ln.r);
-            const Hit h = USE_BVH ? closest_hit_bvh(sc, q, rp.tmin) : closest_hit_list<LIST>(sc, q, rp.tmin);
-            ++nrays;
-            out_q = wf_finish<NEE, WF_ACC_PLAIN>(sc, rp, wb, accum, ln, q, h);
-            if (out_q == Q_NEW) break; // miss or constant emitter: accumulated by wf_finish
-            kind = out_q;
+        s_out[i] = slot | uint32_t(kind) << 28;
+        atomicAdd(&s_cnt[kind], 1u);
+    }
+    const PathMap pm{0u, 0u, 0u}; // no path left to start
+    unsigned long long nrays = 0;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) { // class segments of the next bounce, each starting at a multiple of 32
+            uint32_t o = 0;
+            for (int k = 0; k < NQ; ++k) {
+                s_off[k] = o;
+                s_cur[k] = 0u;
+                s_cin[k] = s_cnt[k];
+                o += (s_cnt[k] + 31u) & ~31u;
+                s_cnt[k] = 0u;
+            }
+            s_off[NQ] = o;
         }
+        __syncthreads();
+        const uint32_t n_in = s_off[NQ];
+        if (n_in == 0u) break;
+        for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+            const uint32_t e = s_out[i];
+            if (e != WF_TAIL_DEAD) s_in[s_off[e >> 28] + atomicAdd(&s_cur[e >> 28], 1u)] = e & 0x0fffffffu;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n_in; i += blockDim.x) { // n_in is a multiple of 32: whole warps take every trip
+            int kind = 0;
+#pragma unroll
+            for (int k = 1; k < NQ; ++k) kind += (i >= s_off[k]) ? 1 : 0; // (an empty class has s_off[k] == s_off[k + 1]: skipped)
+            const bool valid = i - s_off[kind] < s_cin[kind];
+            const uint32_t slot = valid ? s_in[i] : 0u;
+            const int out_q = wf_process_entry<USE_BVH, NEE, WF_ACC_PLAIN, LIST>(sc, rp, wb, pt, kind, valid, slot, 0u, pm, accum, nrays);
+            const bool live = valid && out_q != Q_NONE && out_q != Q_NEW;
+            s_out[i] = live ? (slot | uint32_t(out_q) << 28) : WF_TAIL_DEAD;
+            if (live) atomicAdd(&s_cnt[out_q], 1u);
+        }
+        n_out = n_in;
     }
     for (int off = 16; off > 0; off >>= 1) nrays += __shfl_down_sync(0xffffffffu, nrays, off);
     if ((threadIdx.x & 31u) == 0u && nrays) atomicAdd(ray_counter, nrays);
@@ -996,11 +1038,14 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     const bool warp_grain = grain != G_CTA;
     // The thin end of the frame is finished in place by k_wf_tail (CTA- and warp-chunk kernels; the persistent-lane kernel
     // walks other nodes than the per-lane loop and its frames spend nothing in the tail).  RT_WF_TAIL_PATHS overrides, 0 = off.
+    const unsigned tail_grid = unsigned(sm_count) * WF_CTA_MINBLOCKS;            // one wave: every CTA owns its paths to their end
+    const uint32_t tail_max = tail_grid * (WF_TAIL_CAP - 7u * 31u - 32u);          // what the CTAs' slot lists can hold
     uint32_t tail_paths = grain == G_PT ? 0u : RT_WF_TAIL_PATHS_DEFAULT;
     if (const char* e = getenv("RT_WF_TAIL_PATHS")) {
         const long v = atol(e);
-        if (v >= 0 && v <= (1l << 22) && grain != G_PT) tail_paths = uint32_t(v);
+        if (v >= 0 && grain != G_PT) tail_paths = uint32_t(v < (1l << 24) ? v : (1l << 24));
     }
+    if (tail_paths > tail_max) tail_paths = tail_max;
     wb.tail_paths = tail_paths;
     // node form of the persistent-lane kernel: the 64-byte quantised nodes when the scene has them (RT_BVH4=f: the 128-byte ones)
     bool quant = sc.nodes4q != nullptr;
@@ -1028,12 +1073,21 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev);
             cudaDeviceGetAttribute(&window_max, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-            if (persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(persist_max));
+            cudaDeviceGetAttribute(&ws->l2_bytes, cudaDevAttrL2CacheSize, dev);
         }
-        if (persist_max > 0 && window_max > 0) {
+        const bool wide = grain == G_PT;
+        size_t bytes = size_t(wide ? sc.n_nodes4 : sc.n_nodes) * (wide ? (quant ? sizeof(BvhNode4Q) : sizeof(BvhNode4)) : sizeof(BvhNode));
+        // Only for node arrays that the record stream can actually push out: the 32 MB of quantised nodes of the 1 M-sphere scene
+        // stay in the 126 MB L2 on their own, and carving a persisting region out of it costs the sphere data and the records
+        // more than it saves (C4 1 546 -> 1 570 Mrays/s without the window, profiles/r02_c4_ab_knobs.log; the 64 MB float nodes
+        // of round 1 gained from it).
+        const bool worth = bytes > size_t(ws->l2_bytes) / 3u || getenv("RT_L2_PERSIST_ALWAYS");
+        if (worth && persist_max > 0 && !ws->persist_set) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(persist_max));
+            ws->persist_set = true;
+        }
+        if (worth && persist_max > 0 && window_max > 0) {
             cudaStreamAttrValue av{};
-            const bool wide = grain == G_PT;
-            size_t bytes = size_t(wide ? sc.n_nodes4 : sc.n_nodes) * (wide ? (quant ? sizeof(BvhNode4Q) : sizeof(BvhNode4)) : sizeof(BvhNode));
             if (bytes > size_t(window_max)) bytes = size_t(window_max);
             av.accessPolicyWindow.base_ptr = wide ? (quant ? (void*)sc.nodes4q : (void*)sc.nodes4) : (void*)sc.nodes;
             av.accessPolicyWindow.num_bytes = bytes;
@@ -1099,7 +1153,7 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     };
     auto enqueue_tail = [&]() {
         if (!tail_paths) return;
-        const unsigned nb = (tail_paths + WF_CTA_THREADS - 1) / WF_CTA_THREADS, nt = WF_CTA_THREADS; // a thread per path that may be alive
+        const unsigned nb = tail_grid, nt = WF_CTA_THREADS;
         if (nee) {
             if (use_bvh) launch_dims(nb, nt, k_wf_tail<true, true>, sc, rp, wb, accum, ray_counter);
             else if (sc.n_list) launch_dims(nb, nt, k_wf_tail<false, true, 1>, sc, rp, wb, accum, ray_counter);
