@@ -531,9 +531,14 @@ __global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
 #ifndef WF_TAIL_CAP
 #define WF_TAIL_CAP 1280u // slots a CTA can hold, class padding (7 x 31) included
 #endif
+#ifndef WF_TAIL_THREADS
+#define WF_TAIL_THREADS 512 // CTA size of k_wf_tail; one wave of (1024 / WF_TAIL_THREADS) CTAs per SM at 64 registers.  Fewer, larger CTAs keep the
+                            // class segments of a CTA dense: 128 x 8 per SM ran at 13 of 32 lanes (profiles/r02_c1_tail_ncu.md); 512 x 2: C2 probe -1.2 %, C3 probe -3 %
+#endif
+#define WF_TAIL_MINBLOCKS (1024 / WF_TAIL_THREADS)
 #define WF_TAIL_DEAD 0xffffffffu
 template <bool USE_BVH, bool NEE, int LIST = 0>
-__global__ void __launch_bounds__(WF_CTA_THREADS, WF_CTA_MINBLOCKS)
+__global__ void __launch_bounds__(WF_TAIL_THREADS, WF_TAIL_MINBLOCKS)
     k_wf_tail(const __grid_constant__ DScene sc, const __grid_constant__ DRenderParams rp, const __grid_constant__ WfBuffers wb,
               float4* __restrict__ accum, unsigned long long* __restrict__ ray_counter) {
     WF_PDL_PROLOGUE();
@@ -1038,7 +1043,7 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     const bool warp_grain = grain != G_CTA;
     // The thin end of the frame is finished in place by k_wf_tail (CTA- and warp-chunk kernels; the persistent-lane kernel
     // walks other nodes than the per-lane loop and its frames spend nothing in the tail).  RT_WF_TAIL_PATHS overrides, 0 = off.
-    const unsigned tail_grid = unsigned(sm_count) * WF_CTA_MINBLOCKS;            // one wave: every CTA owns its paths to their end
+    const unsigned tail_grid = unsigned(sm_count) * WF_TAIL_MINBLOCKS;           // one wave: every CTA owns its paths to their end
     const uint32_t tail_max = tail_grid * (WF_TAIL_CAP - 7u * 31u - 32u);          // what the CTAs' slot lists can hold
     uint32_t tail_paths = grain == G_PT ? 0u : RT_WF_TAIL_PATHS_DEFAULT;
     if (const char* e = getenv("RT_WF_TAIL_PATHS")) {
@@ -1153,7 +1158,7 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     };
     auto enqueue_tail = [&]() {
         if (!tail_paths) return;
-        const unsigned nb = tail_grid, nt = WF_CTA_THREADS;
+        const unsigned nb = tail_grid, nt = WF_TAIL_THREADS;
         if (nee) {
             if (use_bvh) launch_dims(nb, nt, k_wf_tail<true, true>, sc, rp, wb, accum, ray_counter);
             else if (sc.n_list) launch_dims(nb, nt, k_wf_tail<false, true, 1>, sc, rp, wb, accum, ray_counter);

@@ -1,6 +1,7 @@
-"""k_wf_tail (the thin end of a frame finished in place) against the per-iteration step kernels alone: the same paths —
-equal ray and sample counts, equal sums up to the order of the float atomics — on every scene kind, on small frames
-(which run almost entirely in the tail kernel), on frames that switch to it in mid-flight, and with emitter sampling."""
+"""k_wf_tail (the thin end of a frame finished by CTA-local wavefronts) against the per-iteration step kernels alone: the
+same paths — equal ray and sample counts, equal sums up to the order of the float atomics — on every scene kind, on small
+frames (which run almost entirely in the tail kernel), on frames that switch to it in mid-flight, with emitter sampling,
+and with a path pool much smaller than the frame (many generations of slots before the tail)."""
 import numpy as np
 import pytest
 
@@ -60,3 +61,18 @@ def test_deep_paths_finish_in_the_tail_kernel(ctx, monkeypatch):
     got, st = _render(sc, p, monkeypatch, 1 << 20)
     assert st.rays == st_ref.rays
     assert np.array_equal(got[..., 3], ref[..., 3]) and np.allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_tail_kernel_after_many_slot_generations(scene_descs, monkeypatch, name):
+    """A 4 Ki-slot pool under a 147 k-path frame: 36 generations of slots, then the tail (a context of its own: the pool of
+    a context only grows)."""
+    monkeypatch.setenv("RT_WF_POOL", "4096")
+    small = rt.Context(0)
+    sc = rt.Scene(small, scene_descs[name])
+    p = rt.default_params(width=96, height=48, spp=32)
+    ref, st_ref = _render(sc, p, monkeypatch, 0)
+    got, st = _render(sc, p, monkeypatch, 131072)
+    assert st.paths == st_ref.paths == 96 * 48 * 32 and st.rays == st_ref.rays
+    assert np.array_equal(got[..., 3], ref[..., 3]) and np.allclose(got, ref, rtol=1e-5, atol=1e-5)
+    assert st.iterations < st_ref.iterations
