@@ -584,6 +584,15 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
             bstats.depth += uint32_t(big.size());
         }
     }
+    rtd::BvhNodeCH* dnodes_ch = nullptr;
+    if (dnodes && n_nodes) { // the form the binary traversal reads
+        if ((st = dev_alloc(s, &dnodes_ch, n_nodes)) != RT_OK) return st;
+        cudaError_t e = rtd::bvh_nodes_ch(dnodes, n_nodes, dnodes_ch, stream);
+        if (e != cudaSuccess) {
+            set_error("BVH node conversion failed: %s", cudaGetErrorString(e));
+            return RT_ERR_CUDA;
+        }
+    }
     rtd::BvhNode4* dnodes4 = nullptr;
     rtd::BvhNode4Q* dnodes4q = nullptr;
     uint32_t n_nodes4 = 0, root4 = 0;
@@ -700,6 +709,7 @@ rt_status rt_scene_create(rt_context* ctx, const rt_scene_desc* desc, rt_scene**
     s->d.n_spheres = n;
     s->d.n_static = n_static;
     s->d.nodes = dnodes;
+    s->d.nodes_ch = dnodes_ch;
     s->d.nodes4 = dnodes4;
     s->d.nodes4q = dnodes4q;
     s->d.n_nodes4 = n_nodes4;

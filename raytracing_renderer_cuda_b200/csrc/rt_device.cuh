@@ -102,6 +102,14 @@ struct BvhNode {
     float4 rmax; // (R.max.xyz, unused)
 };
 
+// The binary node as the traversal reads it (round 2): every child box as CENTRE and HALF-EXTENT,
+//   (L.centre.xyz, as_float(left child)), (L.half.xyz, as_float(right child)), (R.centre.xyz, -), (R.half.xyz, -),
+// written by k_nodes_ch (rt_lbvh.cu) from the min/max node with the half-extent rounded UP, so that
+// [centre - half, centre + half] contains the min/max box.  The slab test then needs no ordering of two bounds per axis:
+// entry = tm - half * |1/d|, exit = tm + half * |1/d| with tm = centre * (1/d) - o * (1/d) — three FFMA per axis
+// instead of two FFMA and two FMNMX (the ALU pipe is the busiest one of the BVH kernels: 58 % on C2).
+typedef BvhNode BvhNodeCH;
+
 // 128-byte 4-wide node: the two children of a binary node replaced by their own children (a leaf child stays).
 // Slot s: box (mn?.s, mx?.s), reference refs.s (>= 0 inner node — the index of the BINARY node it was made from —,
 // < 0 leaf ~prim, RT_BVH4_EMPTY unused).  Built from the binary array by k_collapse4 (rt_lbvh.cu).
@@ -138,6 +146,7 @@ struct DScene {
     uint32_t n_static;
     const BvhNode* nodes; // nullptr => brute force
     const BvhNode4* nodes4; // 4-wide form of the same tree (densely renumbered), nullptr if not built
+    const BvhNodeCH* nodes_ch; // the binary nodes in centre / half-extent form (same numbering): what trav_inner<false> reads
     const BvhNode4Q* nodes4q; // ... and its 64-byte quantised form (same numbering), nullptr if not built / not representable
     uint32_t n_nodes4;
     uint32_t root4;

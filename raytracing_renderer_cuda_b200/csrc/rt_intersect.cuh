@@ -164,6 +164,19 @@ RT_DEV bool slab(float4 lo, float4 hi, const V3& inv, const V3& noi, float e, fl
     return tn <= __fmaf_rn(tf, RT_SLAB_FAR_WIDEN, e);
 }
 
+// The same test on a box given as centre c and half-extent h (BvhNodeCH): tm = c * (1/d) - o * (1/d) is the ray parameter at
+// the box's centre plane, entry and exit lie half * |1/d| before and behind it — no ordering of two bounds per axis.
+// Rounding: tm carries the error of the min/max form's bounds (one FFMA on the per-ray products, covered by `e` and the box
+// padding), the second FFMA adds at most 2^-24 of the larger bound — against an acceptance test that is 2^-8 wide.
+RT_DEV bool slab_ch(float4 c, float4 h, const V3& inv, const V3& noi, float e, float tmin, float tmax, float& tnear) {
+    const float tmx = __fmaf_rn(c.x, inv.x, noi.x), tmy = __fmaf_rn(c.y, inv.y, noi.y), tmz = __fmaf_rn(c.z, inv.z, noi.z);
+    const float ax = fabsf(inv.x), ay = fabsf(inv.y), az = fabsf(inv.z);
+    const float tn = fmaxf(fmaxf(__fmaf_rn(-h.x, ax, tmx), __fmaf_rn(-h.y, ay, tmy)), fmaxf(__fmaf_rn(-h.z, az, tmz), tmin));
+    const float tf = fminf(fminf(__fmaf_rn(h.x, ax, tmx), __fmaf_rn(h.y, ay, tmy)), fminf(__fmaf_rn(h.z, az, tmz), tmax));
+    tnear = tn;
+    return tn <= __fmaf_rn(tf, RT_SLAB_FAR_WIDEN, e);
+}
+
 #define RT_BVH_STACK RT_BVH_STACK_DEPTH
 
 // Flattened-BVH closest hit: short per-thread stack, both child boxes fetched with four
@@ -252,11 +265,19 @@ RT_DEV void trav_inner(const DScene& sc, const RayQ& q, float tmin, Trav& t, int
     if (nhit > 1 && t.sp < RT_BVH_STACK) stack[t.sp++] = ref[1];
     t.node = nhit ? ref[0] : (t.sp ? stack[--t.sp] : RT_TRAV_DONE);
   } else {
+#ifdef RT_BVH_MINMAX // A/B: the min/max nodes
     const float4* np = reinterpret_cast<const float4*>(sc.nodes + t.node);
     float4 lmin = __ldg(np + 0), lmax = __ldg(np + 1), rmin = __ldg(np + 2), rmax = __ldg(np + 3);
     float tl, tr;
     const bool hl = slab(lmin, lmax, t.inv, t.noi, t.e, tmin, t.best.t, tl);
     const bool hr = slab(rmin, rmax, t.inv, t.noi, t.e, tmin, t.best.t, tr);
+#else // (lmin / lmax / rmin / rmax: centre and half-extent of the left, then of the right child)
+    const float4* np = reinterpret_cast<const float4*>(sc.nodes_ch + t.node);
+    float4 lmin = __ldg(np + 0), lmax = __ldg(np + 1), rmin = __ldg(np + 2), rmax = __ldg(np + 3);
+    float tl, tr;
+    const bool hl = slab_ch(lmin, lmax, t.inv, t.noi, t.e, tmin, t.best.t, tl);
+    const bool hr = slab_ch(rmin, rmax, t.inv, t.noi, t.e, tmin, t.best.t, tr);
+#endif
     const int cl = __float_as_int(lmin.w), cr = __float_as_int(lmax.w);
     if (hl && hr) {
         const bool left_first = tl <= tr;

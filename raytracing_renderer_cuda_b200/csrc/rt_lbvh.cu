@@ -343,6 +343,35 @@ __global__ void __launch_bounds__(256) k_quantize4(const BvhNode4* __restrict__ 
 }
 } // namespace
 
+namespace {
+// one box: centre rounded to nearest, half-extent = the larger of the two distances from THAT centre to the bounds, rounded up
+__device__ __forceinline__ void box_ch(float lo, float hi, float& c, float& h) {
+    c = __fadd_rn(__fmul_rn(0.5f, lo), __fmul_rn(0.5f, hi));
+    h = fmaxf(__fsub_ru(hi, c), __fsub_ru(c, lo));
+    if (!(h >= 0.f)) h = 0.f; // (an inverted / NaN box stays empty)
+}
+__global__ void __launch_bounds__(256) k_nodes_ch(const BvhNode* __restrict__ in, uint32_t n, BvhNodeCH* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const BvhNode nd = in[i];
+    BvhNodeCH o;
+    o.lmin.w = nd.lmin.w; // left child
+    o.lmax.w = nd.lmax.w; // right child
+    o.rmin.w = o.rmax.w = 0.f;
+    box_ch(nd.lmin.x, nd.lmax.x, o.lmin.x, o.lmax.x);
+    box_ch(nd.lmin.y, nd.lmax.y, o.lmin.y, o.lmax.y);
+    box_ch(nd.lmin.z, nd.lmax.z, o.lmin.z, o.lmax.z);
+    box_ch(nd.rmin.x, nd.rmax.x, o.rmin.x, o.rmax.x);
+    box_ch(nd.rmin.y, nd.rmax.y, o.rmin.y, o.rmax.y);
+    box_ch(nd.rmin.z, nd.rmax.z, o.rmin.z, o.rmax.z);
+    out[i] = o;
+}
+} // namespace
+cudaError_t bvh_nodes_ch(const BvhNode* nodes, uint32_t n, BvhNodeCH* out, cudaStream_t st) {
+    if (n) k_nodes_ch<<<(n + 255) / 256, 256, 0, st>>>(nodes, n, out);
+    return cudaGetLastError();
+}
+
 // out_q (may be nullptr) receives the quantised form of the first *n_out nodes of `out`; *quant_ok tells whether every node
 // was representable.
 cudaError_t bvh_quantize4(const BvhNode4* nodes4, uint32_t n4, BvhNode4Q* out_q, bool* quant_ok, cudaStream_t st) {
