@@ -943,10 +943,17 @@ __global__ void __launch_bounds__(WF_PT_THREADS, WF_PT_MINBLOCKS)
     if (lane == 0 && nrays) atomicAdd(ray_counter, nrays);
 }
 
-// fills Q_NEW of iteration 0 with every slot and resets the path counter
-__global__ void k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_slots) wf_queue(wb, 0, Q_NEW)[i] = i;
+// fills Q_NEW of iteration 0 with every slot (four entries per thread, one 16-byte store: the queue base is 256-byte aligned)
+// and resets the counters
+__global__ void __launch_bounds__(256) k_wf_init(const __grid_constant__ WfBuffers wb, uint32_t n_slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t* q = wf_queue(wb, 0, Q_NEW);
+    const uint32_t first = 4u * i;
+    if (first + 3u < n_slots) {
+        __stcs(reinterpret_cast<uint4*>(q) + i, make_uint4(first, first + 1u, first + 2u, first + 3u));
+    } else {
+        for (uint32_t k = first; k < n_slots; ++k) q[k] = k;
+    }
     if (i < 3 * NQ) wb.counts[i] = (i == Q_NEW) ? n_slots : 0u;
     if (i < 3) wb.tickets[i] = 0u;
     if (i < 2 + NQ) wb.tail[i] = i == 0 ? WF_TAIL_NONE : 0u;
@@ -1021,7 +1028,7 @@ bool wavefront_render(WavefrontState* ws, const DScene& sc, const DRenderParams&
     WfBuffers wb = ws->b;
     const uint32_t slots = uint32_t(npaths < wb.pool ? npaths : wb.pool);
     wb.tail_paths = 0u; // set below, once the granularity is known; k_wf_init does not read it
-    k_wf_init<<<(slots + 255) / 256 > 0 ? (slots + 255) / 256 : 1, 256, 0, st>>>(wb, slots);
+    k_wf_init<<<(slots / 4u + 256u) / 256u, 256, 0, st>>>(wb, slots); // (at least one block: it also resets the counters)
     ++*launches;
 
     // Granularity: CTA chunks (4x fewer queue atomics) when all rays cost the same — the brute-force list —, warp
