@@ -2,7 +2,7 @@
 # Round-2 GPU job 1 (one B200, through gpurun): reference-kernel golden for the C4 generator at n = 10^4, baseline
 # bench lines of the round-1 kernels on this box, and ncu --set full captures of the two kernels the round works on.
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python tools/make_gpu_golden_c4.py > gpurun_out/golden_c4.log 2>&1; tail -n 3 gpurun_out/golden_c4.log
 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/r02_base_c1.json 2> gpurun_out/r02_base_c1.err

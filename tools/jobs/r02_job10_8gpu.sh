@@ -2,7 +2,7 @@
 # Round-2 GPU job 10 (gpurun --gpus 8): the rt_group path at 4 and 8 ranks (bit-exact sums), rt_multi with 8 devices,
 # bench at N = 8 and 4 (weak C1 headline + c5 + strong sub-records).
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 600 > gpurun_out/pytest_multi8.log 2>&1; tail -n 12 gpurun_out/pytest_multi8.log

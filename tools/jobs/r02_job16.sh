@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU job 16: pipelined e2e of the new bench.py, framebuffer passes at 8K (timing + ncu), 9/10 CTAs per SM for the C1 kernel
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python bench.py --no-cpu-baseline --no-other-configs > gpurun_out/r02_bench_e2e.json 2> gpurun_out/r02_bench_e2e.err; tail -n 5 gpurun_out/r02_bench_e2e.err | cut -c1-300; python -c "
 import json; d=json.load(open('gpurun_out/r02_bench_e2e.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['e2e']['serial'])"

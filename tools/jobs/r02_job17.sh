@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU job 17: full GPU suite on the vectorised framebuffer passes, their 8K timing + ncu, per-iteration launch list of a full C4 frame
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 600 > gpurun_out/pytest_gpu_17.log 2>&1; tail -n 5 gpurun_out/pytest_gpu_17.log | cut -c1-300
 timeout 300 python tools/tonemap_8k_once.py > gpurun_out/tonemap_8k_v4.log 2>&1; cat gpurun_out/tonemap_8k_v4.log

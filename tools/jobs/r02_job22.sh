@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU job 22: pipelined vs serial e2e of bench.py with and without k_wf_tail (two runs each, one box)
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for rep in 1 2; do
 for tp in default 0; do

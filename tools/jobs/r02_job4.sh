@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU job 4 (1 GPU): GPU suite, smoke, the new bench.py (other_configs, clean reference arm).
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out; rm -f gpurun_out/parity.jsonl
 timeout 1800 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; tail -n 8 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -n 1 gpurun_out/smoke.log

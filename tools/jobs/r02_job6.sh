@@ -2,7 +2,7 @@
 # Round-2 GPU job 6: profiles of k_wf_blk (why is it slower?) and of k_wf_step_cta in the j4 and cur libraries (same source
 # of the shading code, 7.4 against 8.1 ms on one box), plus the A/B again with the in-tree library.
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 cp raytracing_renderer_cuda_b200/librt_b200.so gpurun_variants/librt_intree.so
 AB_NO_MEGA=1 AB_CASES=c1 timeout 600 python tools/ab_test.py j4 cur intree j4 cur intree > gpurun_out/ab_place2.log 2>&1; cat gpurun_out/ab_place2.log

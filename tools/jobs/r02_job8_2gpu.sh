@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 GPU job 8 (gpurun --gpus 2): the multi-GPU entries of the C-ABI on real hardware.
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader
 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 600 > gpurun_out/pytest_multi2.log 2>&1; tail -n 25 gpurun_out/pytest_multi2.log
