@@ -15,7 +15,7 @@
 //                   still in shared memory the same threads compute the bit length of each block's AC symbols
 //   k_jpeg_dcbits   adds the DC symbol (needs the previous block of the component) -> bit length per block
 //   k_jpeg_dct + k_jpeg_entropy<false>   the same two steps for 4:2:0 (quality <= 90, chroma averaged as stb:1526-1535)
-//   cub::DeviceScan exclusive sum -> bit offset of every block
+//   exclusive sum (rt_prims.cuh) -> bit offset of every block
 //   k_jpeg_entropy<true>   one persistent warp per block, two zigzag positions per lane, zero runs from ballots of the
 //                   non-zero mask (stb:1325-1365); the block's bits are assembled in shared memory and leave as words
 //   k_jpeg_ffcount / scan / k_jpeg_stuff   the 0xFF -> 0xFF 0x00 byte stuffing of stb:1229-1232 as a
@@ -25,7 +25,7 @@
 // Bound (ncu, profiles/r01_jpeg_ncu.md): instruction issue — k_jpeg_dct444 issues at 80 % of peak, k_jpeg_entropy<true> at
 // 67 % with 23 of 32 lanes active — not HBM (3 B/pixel read, 6 B/pixel of int16 coefficients written and read once,
 // ~1-2 B/pixel of stream: 6-11 % of the DRAM bandwidth).  Measured 1.13 ms for an 8K frame, 0.09 ms for 1200x600.
-#include <cub/device/device_scan.cuh>
+#include "rt_prims.cuh"
 
 #include <cstring>
 #include <vector>
@@ -722,8 +722,7 @@ cudaError_t jpeg_encode(JpegState* s, const uint8_t* rgb8_dev, int w, int h, int
     if (!grow(s->coef, s->coef_cap, n_blocks * 64) || !grow(s->bits, s->bits_cap, n_blocks + 1) ||
         !grow(s->offs, s->offs_cap, n_blocks + 1))
         return cudaErrorMemoryAllocation;
-    size_t tmp_bytes = 0;
-    JPG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, s->bits, s->offs, int(n_blocks + 1), st));
+    size_t tmp_bytes = prims::scan_scratch_elems(n_blocks + 1) * sizeof(unsigned long long);
     if (!grow(s->scan_tmp, s->scan_tmp_cap, tmp_bytes)) return cudaErrorMemoryAllocation;
 
     JPG_TRY(cudaEventRecord(s->ev[0], st));
@@ -744,8 +743,7 @@ cudaError_t jpeg_encode(JpegState* s, const uint8_t* rgb8_dev, int w, int h, int
         k_jpeg_entropy<false><<<ent_grid, JPG_ENT_THREADS, 0, st>>>(s->coef, uint32_t(n_blocks), 1, s->d_tab, s->bits, nullptr, nullptr);
     else
         k_jpeg_dcbits<<<unsigned((n_blocks + 255) / 256), 256, 0, st>>>(s->coef, s->ac_bits, uint32_t(n_blocks), s->d_tab, s->bits);
-    tmp_bytes = s->scan_tmp_cap;
-    JPG_TRY(cub::DeviceScan::ExclusiveSum(s->scan_tmp, tmp_bytes, s->bits, s->offs, int(n_blocks + 1), st));
+    JPG_TRY(prims::exclusive_sum<unsigned long long>(s->bits, s->offs, n_blocks + 1, reinterpret_cast<unsigned long long*>(s->scan_tmp), st));
     // total bits -> host: sizes the word buffer and the stuffing grid
     JPG_TRY(cudaMemcpyAsync(s->h_pin, s->offs + n_blocks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     JPG_TRY(cudaStreamSynchronize(st));
@@ -758,14 +756,12 @@ cudaError_t jpeg_encode(JpegState* s, const uint8_t* rgb8_dev, int w, int h, int
                                                                s->offs, s->words);
     const size_t n_threads = stream_bytes ? (stream_bytes + JPG_STUFF_BYTES - 1) / JPG_STUFF_BYTES : 1;
     if (!grow(s->ff, s->ff_cap, n_threads + 1) || !grow(s->ff_off, s->ff_off_cap, n_threads + 1)) return cudaErrorMemoryAllocation;
-    size_t tmp2 = 0;
-    JPG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, s->ff, s->ff_off, int(n_threads + 1), st));
+    const size_t tmp2 = prims::scan_scratch_elems(n_threads + 1) * sizeof(unsigned long long);
     if (!grow(s->scan_tmp, s->scan_tmp_cap, tmp2)) return cudaErrorMemoryAllocation;
     JPG_TRY(cudaMemsetAsync(s->ff + n_threads, 0, sizeof(unsigned long long), st));
     const unsigned st_grid = unsigned((n_threads + 255) / 256);
     k_jpeg_ffcount<<<st_grid, 256, 0, st>>>(s->words, s->offs + n_blocks, uint32_t(n_threads), s->ff);
-    tmp2 = s->scan_tmp_cap;
-    JPG_TRY(cub::DeviceScan::ExclusiveSum(s->scan_tmp, tmp2, s->ff, s->ff_off, int(n_threads + 1), st));
+    JPG_TRY(prims::exclusive_sum<unsigned long long>(s->ff, s->ff_off, n_threads + 1, reinterpret_cast<unsigned long long*>(s->scan_tmp), st));
     // worst case every byte is stuffed; the exact size comes back with the second sync
     const size_t hdr = s->header.size();
     if (!grow(s->out, s->out_cap, hdr + 2 * stream_bytes + 2)) return cudaErrorMemoryAllocation;

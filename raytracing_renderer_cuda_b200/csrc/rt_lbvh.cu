@@ -7,8 +7,9 @@
 #include "rt_lbvh.cuh"
 #include "rt_kernels.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include <utility>
+
+#include "rt_prims.cuh"
 
 namespace rtd {
 
@@ -422,7 +423,7 @@ cudaError_t bvh_collapse4(const BvhNode* nodes, uint32_t n_nodes, uint32_t root,
     C4_TRY(rtd::malloc_async(&level, size_t(n_nodes + 1) * sizeof(uint32_t), st));
     C4_TRY(rtd::malloc_async(&used, size_t(n_nodes + 1) * sizeof(uint32_t), st));
     C4_TRY(rtd::malloc_async(&idx, size_t(n_nodes + 1) * sizeof(uint32_t), st));
-    C4_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, used, idx, int(n_nodes + 1), st));
+    tmp_bytes = prims::scan_scratch_elems(size_t(n_nodes) + 1) * sizeof(uint32_t);
     C4_TRY(rtd::malloc_async(&tmp, tmp_bytes, st));
     const unsigned blocks = (n_nodes + 255) / 256;
     k_collapse4<<<blocks, 256, 0, st>>>(nodes, n_nodes, wide);
@@ -431,7 +432,7 @@ cudaError_t bvh_collapse4(const BvhNode* nodes, uint32_t n_nodes, uint32_t root,
     C4_TRY(cudaMemcpyAsync(level + root, &one, sizeof one, cudaMemcpyHostToDevice, st));
     for (uint32_t cur = 1; cur <= depth / 2 + 2; ++cur) k_mark4<<<blocks, 256, 0, st>>>(wide, n_nodes, level, cur);
     k_used4<<<(n_nodes + 256) / 256, 256, 0, st>>>(level, n_nodes + 1, used); // level[n_nodes] == 0: the scan's total slot
-    C4_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, used, idx, int(n_nodes + 1), st));
+    C4_TRY(prims::exclusive_sum<uint32_t>(used, idx, size_t(n_nodes) + 1, static_cast<uint32_t*>(tmp), st));
     k_compact4<<<blocks, 256, 0, st>>>(wide, level, idx, n_nodes, out);
     C4_TRY(cudaGetLastError());
     uint32_t h[2] = {0, 0};
@@ -483,7 +484,7 @@ cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n_stat
     LB_TRY(rtd::malloc_async(&parent_leaf, n * sizeof(int), st));
     LB_TRY(rtd::malloc_async(&visits, n * sizeof(unsigned), st));
     LB_TRY(rtd::malloc_async(&scal, 16 * sizeof(unsigned), st));
-    LB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, vals_out, int(n), 0, 63, st));
+    tmp_bytes = prims::sort_scratch_elems(n) * sizeof(uint32_t);
     LB_TRY(rtd::malloc_async(&tmp, tmp_bytes, st));
     LB_TRY(cudaEventCreate(&e0));
     LB_TRY(cudaEventCreate(&e1));
@@ -495,7 +496,14 @@ cudaError_t lbvh_build(const float4* sph_a, const float4* sph_b, uint32_t n_stat
     const unsigned blocks = (n + 255) / 256;
     k_prim_boxes<<<blocks, 256, 0, st>>>(sph_a, sph_b, ids, n, n_static, lo, hi, scal);
     k_morton<<<blocks, 256, 0, st>>>(lo, hi, n, scal, keys, vals);
-    LB_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, vals_out, int(n), 0, 63, st));
+    { // stable LSD radix sort of the (63-bit Morton code, primitive) pairs: 8 passes of 8 bits (rt_prims.cuh)
+        bool in_alt = false;
+        LB_TRY(prims::sort_pairs_u64_u32(keys, vals, keys_out, vals_out, n, 8, static_cast<uint32_t*>(tmp), &in_alt, st));
+        if (!in_alt) { // the sorted pairs are in (keys, vals): the code below reads (keys_out, vals_out)
+            std::swap(keys, keys_out);
+            std::swap(vals, vals_out);
+        }
+    }
     k_topology<<<blocks, 256, 0, st>>>(keys_out, vals_out, ids, int(n), nodes, parent_inner, parent_leaf);
     k_refit<<<blocks, 256, 0, st>>>(vals_out, ids, int(n), lo, hi, nodes, parent_inner, parent_leaf, visits,
                                     reinterpret_cast<float*>(scal + 8));
