@@ -462,14 +462,19 @@ def run_ours(args) -> None:
                 for sc_k in old:
                     sc_k.close()
 
-            pipelined(3)
-            t0 = time.perf_counter()
-            pipelined(args.steps)
-            e2e_pipe = (time.perf_counter() - t0) / args.steps
+            try:
+                pipelined(3)
+                t0 = time.perf_counter()
+                pipelined(args.steps)
+                e2e_pipe = (time.perf_counter() - t0) / args.steps
+            except Exception as ex:  # the serial measurement above stands; say why the pipelined one is missing
+                print(f"bench.py: pipelined e2e leg failed ({ex!r}); reporting the serial call sequence", file=sys.stderr)
+                e2e_pipe = None
+                torch.cuda.synchronize()
             # The pipeline needs two host threads that keep up with ~40 launches per 7 ms frame; on a box whose host cores are busy
             # or slow the plain serial call sequence is the faster of the two.  Both are end-to-end runs of the same per-step
             # work through the public API: the headline is the better one, and the line says which and carries both.
-            e2e_s = min(e2e_pipe, e2e_serial_s)
+            e2e_s = min(e2e_pipe, e2e_serial_s) if e2e_pipe is not None else e2e_serial_s
 
         # ---- output stage on the device: render + finalise + flip/quantise + JPEG, only the file is read back ----
         jpeg = None
