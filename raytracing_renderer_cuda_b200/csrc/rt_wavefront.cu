@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(WF_PT_THREADS, WF_PT_MINBLOCKS)
         // ---- 1. second half of the entries whose ray is done ----
         {
             int out_q = Q_NONE;
-            if (tracing && t.node == RT_TRAV_DONE) {
+            if (tracing && t.node == RT_TRAV_DONE && t.leaf >= 0) { // (t.leaf < 0: a postponed leaf, -DRT_PT_POSTPONE only)
                 ++nrays;
                 out_q = wf_finish<NEE, WF_PT_STREAM>(sc, rp, wb, accum, ln, q, t.best);
                 tracing = false;
@@ -920,6 +920,31 @@ __global__ void __launch_bounds__(WF_PT_THREADS, WF_PT_MINBLOCKS)
         const int keep = more ? max(__popc(live) - refill, 0) : 0;
         int nlive;
         do {
+#ifdef RT_PT_POSTPONE // A/B: a lane that reaches a leaf postpones it and keeps walking (as the warp-chunk kernel does); the postponed
+                      // leaves are tested when RT_PT_POSTPONE lanes hold one, when a lane stands at a second leaf, or when nobody can walk
+            if (t.node >= 0 && t.node != RT_TRAV_DONE) {
+                if (QUANT) trav_inner_q(sc, q, rp.tmin, t, stack);
+                else trav_inner<true>(sc, q, rp.tmin, t, stack);
+                if (t.node < 0 && t.leaf >= 0) {
+                    t.leaf = t.node;
+                    t.node = t.sp ? stack[--t.sp] : RT_TRAV_DONE;
+                }
+            }
+            const unsigned pend = __ballot_sync(0xffffffffu, t.leaf < 0);
+            const unsigned blocked = __ballot_sync(0xffffffffu, t.node < 0);
+            const unsigned can_go = __ballot_sync(0xffffffffu, t.node >= 0 && t.node != RT_TRAV_DONE);
+            if (__popc(pend) >= RT_PT_POSTPONE || blocked != 0u || can_go == 0u) {
+                if (t.leaf < 0) {
+                    test_prim(sc, q, uint32_t(~t.leaf), rp.tmin, t.best);
+                    t.leaf = 0;
+                }
+                if (t.node < 0) { // the node after the postponed leaf is a leaf too: it waits in its place
+                    t.leaf = t.node;
+                    t.node = t.sp ? stack[--t.sp] : RT_TRAV_DONE;
+                }
+            }
+            nlive = __popc(__ballot_sync(0xffffffffu, t.node != RT_TRAV_DONE || t.leaf < 0));
+#else
             // One inner-node step for every lane that stands at an inner node; lanes that stand at a leaf (or just
             // arrived at one) test it once `leaf_lanes` of them wait, or when no lane can take an inner step.
 #ifdef RT_PT_BINARY // A/B: the binary tree
@@ -936,6 +961,7 @@ __global__ void __launch_bounds__(WF_PT_THREADS, WF_PT_MINBLOCKS)
                 if (t.node < 0) trav_leaf(sc, q, rp.tmin, t, stack);
             }
             nlive = __popc(__ballot_sync(0xffffffffu, t.node != RT_TRAV_DONE));
+#endif
         } while (nlive > keep);
     }
 
