@@ -1,4 +1,6 @@
 // rt_kernels.cu — parity hook, per-path megakernel, tonemap.  sm_100a only.
+#include <cstdlib>
+
 #include "rt_kernels.cuh"
 #include "rt_shade.cuh"
 
@@ -294,7 +296,12 @@ void launch_reduce_tonemap(const void* const* peer_accum, int n_peers, const voi
         for (int k = 0; k < n_peers && k < 16; ++k) pp.p[k] = static_cast<const float4*>(peer_accum[k]);
     const size_t npix = size_t(row_end - row_begin) * size_t(width);
     const FastDiv div_w = make_fastdiv(uint32_t(width));
-    if (width % 4 == 0 && uintptr_t(out_rgb) % 16 == 0 && uintptr_t(out_rgb8) % 4 == 0) // (vector stores need the alignment)
+    // Four pixels per thread give 16-byte stores, but a warp's loads of one pixel slot then touch every other 16 bytes of 2 KB:
+    // fine from local HBM, half-used 32-byte requests over NVLink.  With peers (or RT_REDUCE_G=1) one pixel per thread: a warp
+    // reads 512 contiguous bytes of every member (A/B: profiles/r02_framebuffer_passes.md).
+    const char* g_env = getenv("RT_REDUCE_G");
+    const bool wide = g_env ? g_env[0] == '4' : (n_peers <= 1 && multicast == nullptr);
+    if (wide && width % 4 == 0 && uintptr_t(out_rgb) % 16 == 0 && uintptr_t(out_rgb8) % 4 == 0) // (vector stores need the alignment)
         k_reduce_tonemap<4><<<stream_grid(k_reduce_tonemap<4>, npix / 4, sm_count), 256, 0, st>>>(
             pp, n_peers, static_cast<const float4*>(multicast), width, height, div_w, row_begin, row_end, out_rgb, out_rgb8, out_sum);
     else
